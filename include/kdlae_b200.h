@@ -1,0 +1,113 @@
+/*
+ * kdlae_b200.h - C ABI of the B200-native (sm_100a) KDLAE / ASDQE forward path.
+ *
+ * The reference (yangtaihong59/Rethink_Acoustic_Image_Enhancement) has no FFI layer: its hot path is
+ * three Python nn.Modules.  This header is the boundary a binding (ctypes / cffi / pybind / cgo) links
+ * against; each entry point names the reference interface it replaces.  Conventions:
+ *
+ *   - plain pointers and sizes only; every device pointer is caller-owned (torch / cudaMalloc);
+ *   - no hidden allocation: packed weights and workspace are caller buffers sized by the *_bytes queries;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation;
+ *   - return 0 on success, non-zero on error with text in kdlae_last_error() (thread-local);
+ *   - `precision`: KDLAE_PREC_FP32 = fp32 storage + fp32 FFMA kernels (reference-grade, <=1e-4),
+ *                  KDLAE_PREC_BF16 = NHWC bf16 storage, tcgen05/TMEM tensor-core convs, fp32 accumulate;
+ *   - images cross the boundary in the reference's own layout: contiguous NCHW fp32.
+ */
+#ifndef KDLAE_B200_H_
+#define KDLAE_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDLAE_ABI_VERSION 1
+#define KDLAE_PREC_FP32 0
+#define KDLAE_PREC_BF16 1
+
+/* ---- library / device probes ---------------------------------------------------------------- */
+int kdlae_abi_version(void);
+const char* kdlae_last_error(void);
+/* 0 if `device` is an sm_100 (B200) GPU this build can run on; fails cleanly (non-zero + message) otherwise. */
+int kdlae_device_check(int device);
+/* number of kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
+unsigned long long kdlae_launch_count(void);
+
+/* ---- KDLAE-T : KDLAE_teacher (KDLAE/KDLAE_model.py:204-336), alias RestormerSuperResolutionParam2 ------ */
+typedef struct kdlae_teacher_cfg {
+  int inp_channels;          /* KDLAE_model.py:206 */
+  int out_channels;          /* :207 */
+  int dim;                   /* :208 (48) */
+  int num_blocks[4];         /* :209 ([4,6,6,8]) */
+  int num_refinement_blocks; /* :210 (4) */
+  int heads[4];              /* :211 ([1,2,4,8]) */
+  int hidden[4];             /* int(dim*2^l*ffn_expansion_factor) per level l, computed by the caller (:93) */
+  int ln_with_bias;          /* LayerNorm_type != 'BiasFree' (:214) */
+  int sr_head;               /* static == "train" (:262-267) */
+  int params_cat;            /* params == 'cat' (:315) */
+} kdlae_teacher_cfg;
+
+/* number of state_dict tensors expected by kdlae_teacher_pack, in state_dict() order (483 for the shipped config) */
+int kdlae_teacher_num_tensors(const kdlae_teacher_cfg* cfg);
+size_t kdlae_teacher_packed_bytes(const kdlae_teacher_cfg* cfg, int precision);
+/* Replaces nn.Module.load_state_dict-time weight placement: re-lays the fp32 state_dict tensors (device
+ * pointers, state_dict() order, contiguous) into kernel operands: K-major bf16/fp32 GEMM weights with the
+ * LayerNorm weight folded in, FFN halves padded (127->128...), PixelShuffle row order, depthwise [9][C]. */
+int kdlae_teacher_pack(const kdlae_teacher_cfg* cfg, const float* const* tensors, int n_tensors, void* packed,
+                       size_t packed_bytes, int precision, void* stream);
+size_t kdlae_teacher_workspace_bytes(const kdlae_teacher_cfg* cfg, int micro_batch, int H, int W, int precision);
+/* Replaces KDLAE_teacher.forward (KDLAE_model.py:270-336).
+ *   img  [B, inp_channels, H, W] fp32, H % 8 == 0 and W % 8 == 0 (else error, like pixel_unshuffle raising)
+ *   rate [B, 1, H, W] fp32 (input["denoise_rate"]); may be NULL when params_cat == 0
+ *   hq   [B, out_channels, H, W] fp32 out;  sr [B, out_channels, 2H, 2W] fp32 out (NULL iff sr_head == 0)
+ * Images are processed `micro_batch` at a time inside the call (workspace is sized for micro_batch). */
+int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, float* hq,
+                          float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes,
+                          int precision, void* stream);
+
+/* ---- KDLAE-S : KDLAE_student (KDLAE/KDLAE_model.py:340-430) ------------------------------------------ */
+typedef struct kdlae_student_cfg {
+  int hidden[3];   /* hidden_channels (:342), 2 levels + fusion: [16,32,64] */
+  int residual;    /* :341 */
+} kdlae_student_cfg;
+size_t kdlae_student_packed_bytes(const kdlae_student_cfg* cfg, int precision);
+int kdlae_student_pack(const kdlae_student_cfg* cfg, const float* const* tensors, int n_tensors /* 26 */, void* packed,
+                       size_t packed_bytes, int precision, void* stream);
+size_t kdlae_student_workspace_bytes(const kdlae_student_cfg* cfg, int micro_batch, int F, int H, int W, int precision);
+/* Replaces KDLAE_student.forward (:395-430): x [B, F, H, W] fp32 -> y [B, F, H, W] fp32; H % 4 == 0, W % 4 == 0. */
+int kdlae_student_forward(const kdlae_student_cfg* cfg, const void* packed, const float* x, float* y, int B, int F, int H, int W,
+                          int micro_batch, void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* ---- ASDQE : DenoiseRatePredictor (ASDQE/ASDQE_model.py:123-171), eval mode --------------------------- */
+typedef struct kdlae_asdqe_cfg {
+  int in_channels; /* :127 (3) */
+  int dim;         /* :127 (16) */
+} kdlae_asdqe_cfg;
+size_t kdlae_asdqe_packed_bytes(const kdlae_asdqe_cfg* cfg, int precision);
+/* tensors: the 148 state_dict entries in order; num_batches_tracked entries are passed as NULL. */
+int kdlae_asdqe_pack(const kdlae_asdqe_cfg* cfg, const float* const* tensors, int n_tensors, void* packed, size_t packed_bytes,
+                     int precision, void* stream);
+size_t kdlae_asdqe_workspace_bytes(const kdlae_asdqe_cfg* cfg, int micro_batch, int H, int W, int precision);
+/* Replaces DenoiseRatePredictor.forward (:158-171): lq, gt [B, in_channels, H, W] fp32 -> score [B] fp32 in (-1,1).
+ * feat (nullable): the U-Net output `enhanced_feat` (:167) as [B, 3*dim, Hp, Wp] fp32 with Hp/Wp = H/W padded to %16. */
+int kdlae_asdqe_forward(const kdlae_asdqe_cfg* cfg, const void* packed, const float* lq, const float* gt, float* score,
+                        float* feat, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes,
+                        int precision, void* stream);
+
+/* ---- single fused stages (unit parity tests and profiling; same kernels the forwards launch) ---------- */
+/* Implicit-GEMM conv over NHWC activations: out[p, n] = act(rs[p] * sum_{tap,c} A[p+tap, c] W[n, tap, c] + bias[n]) (+ res).
+ * Replaces nn.Conv2d 1x1 / 3x3 (KDLAE_model.py:95,99,118,120,186,196,238,243; ASDQE_model.py:24-31).
+ * `a`,`w`,`res`,`out` are bf16 (precision 1) or fp32 (precision 0); w is [N][kh*kw][C] K-major. */
+int kdlae_conv_gemm(const void* a, int C, const void* w, int N, int nimg, int H, int W, int ksize, const float* row_scale,
+                    const float* col_bias, int relu, const void* res, void* out, int precision, int force_simt, void* stream);
+/* Per-pixel channel LayerNorm statistics (KDLAE_model.py:50-52,:67-70). x: [rows][C]. */
+int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int precision, void* stream);
+/* Depthwise 3x3 (+ optional GELU gate) (KDLAE_model.py:97,103-104,119). w9c fp32 [9][C]. */
+int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H, int W, int C, int gate, int precision,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDLAE_B200_H_ */

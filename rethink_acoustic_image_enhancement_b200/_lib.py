@@ -1,0 +1,97 @@
+"""ctypes binding of libkdlae_b200.so (the C ABI declared in include/kdlae_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libkdlae_b200.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+class TeacherCfg(C.Structure):
+    _fields_ = [
+        ("inp_channels", C.c_int), ("out_channels", C.c_int), ("dim", C.c_int),
+        ("num_blocks", C.c_int * 4), ("num_refinement_blocks", C.c_int),
+        ("heads", C.c_int * 4), ("hidden", C.c_int * 4),
+        ("ln_with_bias", C.c_int), ("sr_head", C.c_int), ("params_cat", C.c_int),
+    ]
+
+
+class StudentCfg(C.Structure):
+    _fields_ = [("hidden", C.c_int * 3), ("residual", C.c_int)]
+
+
+class AsdqeCfg(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("dim", C.c_int)]
+
+
+_PP = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol declared in include/kdlae_b200.h
+SIGNATURES = {
+    "kdlae_abi_version": (C.c_int, []),
+    "kdlae_last_error": (C.c_char_p, []),
+    "kdlae_device_check": (C.c_int, [C.c_int]),
+    "kdlae_launch_count": (C.c_ulonglong, []),
+    "kdlae_teacher_num_tensors": (C.c_int, [C.POINTER(TeacherCfg)]),
+    "kdlae_teacher_packed_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int]),
+    "kdlae_teacher_pack": (C.c_int, [C.POINTER(TeacherCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_teacher_workspace_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kdlae_teacher_forward": (C.c_int, [C.POINTER(TeacherCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_student_packed_bytes": (C.c_size_t, [C.POINTER(StudentCfg), C.c_int]),
+    "kdlae_student_pack": (C.c_int, [C.POINTER(StudentCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_student_workspace_bytes": (C.c_size_t, [C.POINTER(StudentCfg), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kdlae_student_forward": (C.c_int, [C.POINTER(StudentCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_asdqe_packed_bytes": (C.c_size_t, [C.POINTER(AsdqeCfg), C.c_int]),
+    "kdlae_asdqe_pack": (C.c_int, [C.POINTER(AsdqeCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_asdqe_workspace_bytes": (C.c_size_t, [C.POINTER(AsdqeCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kdlae_asdqe_forward": (C.c_int, [C.POINTER(AsdqeCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "kdlae_conv_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "kdlae_ln_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kdlae_dwconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and bind every declared symbol. Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m rethink_acoustic_image_enhancement_b200.build` "
+            "(there is no CPU or PyTorch fallback for the KDLAE/ASDQE forward path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.kdlae_abi_version() != 1:
+        raise RuntimeError("libkdlae_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().kdlae_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().kdlae_launch_count())

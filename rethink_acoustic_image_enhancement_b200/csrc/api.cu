@@ -1,0 +1,182 @@
+// extern "C" boundary (include/kdlae_b200.h): argument checking, precision dispatch, error text.
+#include "models.cuh"
+
+namespace kd {
+
+static thread_local char g_err[1024] = "";
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+}  // namespace kd
+
+using namespace kd;
+
+#define API_BEGIN() kd::set_error("")
+#define CHECK_PREC(p) KD_CHECK((p) == KDLAE_PREC_FP32 || (p) == KDLAE_PREC_BF16, "precision must be KDLAE_PREC_FP32 or KDLAE_PREC_BF16")
+
+extern "C" {
+
+int kdlae_abi_version(void) { return KDLAE_ABI_VERSION; }
+const char* kdlae_last_error(void) { return kd::get_error(); }
+unsigned long long kdlae_launch_count(void) { return kd::g_launch_count; }
+
+int kdlae_device_check(int device) {
+  API_BEGIN();
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    kd::set_error("no CUDA device available (%s)", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return 3;
+  }
+  KD_CHECK(device >= 0 && device < n, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  KD_CUDA(cudaGetDeviceProperties(&prop, device));
+  KD_CHECK(prop.major == 10, "device %d (%s, sm_%d%d) is not an sm_100 (B200) GPU; this library only carries sm_100a code",
+           device, prop.name, prop.major, prop.minor);
+  return 0;
+}
+
+// ---------------- teacher ----------------
+int kdlae_teacher_num_tensors(const kdlae_teacher_cfg* cfg) { return cfg ? kd::teacher_num_tensors(*cfg) : -1; }
+
+size_t kdlae_teacher_packed_bytes(const kdlae_teacher_cfg* cfg, int precision) {
+  if (!cfg) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::teacher_packed_bytes<bf16>(*cfg) : kd::teacher_packed_bytes<float>(*cfg);
+}
+int kdlae_teacher_pack(const kdlae_teacher_cfg* cfg, const float* const* tensors, int n_tensors, void* packed, size_t packed_bytes,
+                       int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && tensors && packed, "kdlae_teacher_pack: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16 ? kd::teacher_pack<bf16>(*cfg, tensors, n_tensors, packed, packed_bytes, s)
+                                      : kd::teacher_pack<float>(*cfg, tensors, n_tensors, packed, packed_bytes, s);
+}
+size_t kdlae_teacher_workspace_bytes(const kdlae_teacher_cfg* cfg, int micro_batch, int H, int W, int precision) {
+  if (!cfg || micro_batch < 1 || H < 8 || W < 8) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::teacher_workspace_bytes<bf16>(*cfg, micro_batch, H, W)
+                                      : kd::teacher_workspace_bytes<float>(*cfg, micro_batch, H, W);
+}
+int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, float* hq,
+                          float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes, int precision,
+                          void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && packed && img && hq && workspace, "kdlae_teacher_forward: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16
+             ? kd::teacher_forward<bf16>(*cfg, packed, img, rate, hq, sr, B, H, W, micro_batch, workspace, workspace_bytes, s)
+             : kd::teacher_forward<float>(*cfg, packed, img, rate, hq, sr, B, H, W, micro_batch, workspace, workspace_bytes, s);
+}
+
+// ---------------- student ----------------
+size_t kdlae_student_packed_bytes(const kdlae_student_cfg* cfg, int precision) {
+  if (!cfg) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::student_packed_bytes<bf16>(*cfg) : kd::student_packed_bytes<float>(*cfg);
+}
+int kdlae_student_pack(const kdlae_student_cfg* cfg, const float* const* tensors, int n_tensors, void* packed, size_t packed_bytes,
+                       int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && tensors && packed, "kdlae_student_pack: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16 ? kd::student_pack<bf16>(*cfg, tensors, n_tensors, packed, packed_bytes, s)
+                                      : kd::student_pack<float>(*cfg, tensors, n_tensors, packed, packed_bytes, s);
+}
+size_t kdlae_student_workspace_bytes(const kdlae_student_cfg* cfg, int micro_batch, int F, int H, int W, int precision) {
+  if (!cfg || micro_batch < 1 || F < 1 || H < 4 || W < 4) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::student_workspace_bytes<bf16>(*cfg, micro_batch, F, H, W)
+                                      : kd::student_workspace_bytes<float>(*cfg, micro_batch, F, H, W);
+}
+int kdlae_student_forward(const kdlae_student_cfg* cfg, const void* packed, const float* x, float* y, int B, int F, int H, int W,
+                          int micro_batch, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && packed && x && y && workspace, "kdlae_student_forward: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16
+             ? kd::student_forward<bf16>(*cfg, packed, x, y, B, F, H, W, micro_batch, workspace, workspace_bytes, s)
+             : kd::student_forward<float>(*cfg, packed, x, y, B, F, H, W, micro_batch, workspace, workspace_bytes, s);
+}
+
+// ---------------- ASDQE ----------------
+size_t kdlae_asdqe_packed_bytes(const kdlae_asdqe_cfg* cfg, int precision) {
+  if (!cfg) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::asdqe_packed_bytes<bf16>(*cfg) : kd::asdqe_packed_bytes<float>(*cfg);
+}
+int kdlae_asdqe_pack(const kdlae_asdqe_cfg* cfg, const float* const* tensors, int n_tensors, void* packed, size_t packed_bytes,
+                     int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && tensors && packed, "kdlae_asdqe_pack: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16 ? kd::asdqe_pack<bf16>(*cfg, tensors, n_tensors, packed, packed_bytes, s)
+                                      : kd::asdqe_pack<float>(*cfg, tensors, n_tensors, packed, packed_bytes, s);
+}
+size_t kdlae_asdqe_workspace_bytes(const kdlae_asdqe_cfg* cfg, int micro_batch, int H, int W, int precision) {
+  if (!cfg || micro_batch < 1 || H < 1 || W < 1) return 0;
+  return precision == KDLAE_PREC_BF16 ? kd::asdqe_workspace_bytes<bf16>(*cfg, micro_batch, H, W)
+                                      : kd::asdqe_workspace_bytes<float>(*cfg, micro_batch, H, W);
+}
+int kdlae_asdqe_forward(const kdlae_asdqe_cfg* cfg, const void* packed, const float* lq, const float* gt, float* score, float* feat,
+                        int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(cfg && packed && lq && gt && score && workspace, "kdlae_asdqe_forward: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16
+             ? kd::asdqe_forward<bf16>(*cfg, packed, lq, gt, score, feat, B, H, W, micro_batch, workspace, workspace_bytes, s)
+             : kd::asdqe_forward<float>(*cfg, packed, lq, gt, score, feat, B, H, W, micro_batch, workspace, workspace_bytes, s);
+}
+
+// ---------------- single stages ----------------
+int kdlae_conv_gemm(const void* a, int C, const void* w, int N, int nimg, int H, int W, int ksize, const float* row_scale,
+                    const float* col_bias, int relu, const void* res, void* out, int precision, int force_simt, void* stream) {
+  API_BEGIN();
+  KD_CHECK(a && w && out, "kdlae_conv_gemm: NULL argument");
+  KD_CHECK(ksize == 1 || ksize == 3, "kdlae_conv_gemm: ksize must be 1 or 3");
+  CHECK_PREC(precision);
+  ConvOp g;
+  g.a0 = a; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.kh = g.kw = ksize;
+  g.w = w; g.w_ld = (long)ksize * ksize * C; g.w_tap_ld = C;
+  g.epi.row_scale = row_scale; g.epi.col_bias = col_bias; g.epi.relu = relu; g.epi.res = res; g.epi.res_ld = N;
+  g.epi.out = out; g.epi.out_ld = N; g.epi.N = N; g.epi.H = H; g.epi.W = W;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == KDLAE_PREC_FP32) return kd::conv_gemm_simt<float>(g, s);
+  if (force_simt) return kd::conv_gemm_simt<bf16>(g, s);
+  KD_CHECK(kd::conv_gemm_tc_eligible(g), "kdlae_conv_gemm: shape not eligible for the tcgen05 kernel (C=%d N=%d)", C, N);
+  return kd::conv_gemm_tc(g, s);
+}
+
+int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int precision, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && rstd, "kdlae_ln_stats: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return precision == KDLAE_PREC_BF16 ? kd::ln_stats<bf16>(reinterpret_cast<const bf16*>(x), C, C, rows, rstd, mu, s)
+                                      : kd::ln_stats<float>(reinterpret_cast<const float*>(x), C, C, rows, rstd, mu, s);
+}
+
+int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H, int W, int C, int gate, int precision,
+                    void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && out && w9c, "kdlae_dwconv3x3: NULL argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long ldo = gate ? C / 2 : C;
+  return precision == KDLAE_PREC_BF16
+             ? kd::dwconv3x3<bf16>(reinterpret_cast<const bf16*>(x), C, reinterpret_cast<bf16*>(out), ldo, w9c, nullptr, nimg, H, W,
+                                   C, gate, s)
+             : kd::dwconv3x3<float>(reinterpret_cast<const float*>(x), C, reinterpret_cast<float*>(out), ldo, w9c, nullptr, nimg, H,
+                                    W, C, gate, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Common device/host helpers for the KDLAE / ASDQE sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+
+namespace kd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local text returned by kdlae_last_error) -------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define KD_CHECK(cond, ...)                          \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ::kd::set_error(__VA_ARGS__);                  \
+      return 1;                                      \
+    }                                                \
+  } while (0)
+
+#define KD_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      ::kd::set_error("%s:%d CUDA error %s (%s)", __FILE__, __LINE__,              \
+                      cudaGetErrorName(_e), cudaGetErrorString(_e));               \
+      return 2;                                                                    \
+    }                                                                              \
+  } while (0)
+
+#define KD_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+#define KD_LAUNCH_CHECK() KD_CUDA(cudaGetLastError())
+
+// ---- launch counter (bench.py reports gpu_launches) -------------------------------------
+extern unsigned long long g_launch_count;
+inline void count_launch() { ++g_launch_count; }
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- scalar conversion ------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 8-wide vector load/store (16 B for bf16, 32 B for fp32); pointers must be aligned ---
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {  // exact GELU (F.gelu default)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- epilogue shared by the SIMT and the tcgen05 implicit-GEMM kernels --------------------
+// Row = one output pixel of the conv (b*D+d, y, x) in a D x H x W grid, column n = output channel.
+enum OutMode { OUT_IDENTITY = 0, OUT_PIXEL_SHUFFLE = 1, OUT_PIXEL_UNSHUFFLE = 2 };
+
+struct Epilogue {
+  const float* row_scale = nullptr;  // [rows]  LayerNorm rstd folded behind the GEMM
+  const float* row_mu = nullptr;     // [rows]  WithBias LN: v -= rstd*mu*col_s1[n]
+  const float* col_s1 = nullptr;     // [N]
+  const float* col_bias = nullptr;   // [N]
+  int relu = 0;
+  const void* res = nullptr;         // residual / skip, indexed like the destination
+  long res_ld = 0;
+  void* out = nullptr;
+  long out_ld = 0;                   // destination row stride in elements
+  int out_coff = 0;                  // destination channel offset
+  int mode = OUT_IDENTITY;
+  int cq = 0;                        // PIXEL_SHUFFLE: channels per sub-pixel (N = 4*cq, packed sub-pixel major)
+  int H = 0, W = 0;                  // conv-output pixel grid (per image/frame)
+  int N = 0;                         // valid output channels
+};
+
+// Store 8 consecutive columns n0..n0+7 (n0 % 8 == 0) of one row. `img` = b*D+d, `prow` = linear row.
+template <typename T>
+__device__ __forceinline__ void epilogue_store8(const Epilogue& e, long prow, int img, int y, int x, int n0, float (&v)[8]) {
+  if (n0 >= e.N) return;
+  const float rs = e.row_scale ? e.row_scale[prow] : 1.0f;
+  const float rmu = e.row_mu ? e.row_mu[prow] * rs : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + i;
+    float t = v[i] * rs;
+    if (n < e.N) {
+      if (e.row_mu) t -= rmu * e.col_s1[n];
+      if (e.col_bias) t += e.col_bias[n];
+    }
+    v[i] = t;
+  }
+  T* out = reinterpret_cast<T*>(e.out);
+  const T* res = reinterpret_cast<const T*>(e.res);
+  if (e.mode == OUT_PIXEL_UNSHUFFLE) {
+    // nn.PixelUnshuffle(2): out[c*4 + 2*(y&1) + (x&1), y/2, x/2] = conv[c, y, x]
+    const long dpix = ((long)img * (e.H >> 1) + (y >> 1)) * (e.W >> 1) + (x >> 1);
+    const int sub = ((y & 1) << 1) | (x & 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      if (n < e.N) {
+        float t = v[i];
+        const long di = dpix * e.out_ld + e.out_coff + n * 4 + sub;
+        if (res) t += to_f<T>(res[dpix * e.res_ld + n * 4 + sub]);
+        if (e.relu) t = fmaxf(t, 0.f);
+        out[di] = from_f<T>(t);
+      }
+    }
+    return;
+  }
+  long dpix = prow;
+  int c0 = n0;
+  if (e.mode == OUT_PIXEL_SHUFFLE) {
+    // nn.PixelShuffle(2) (and ConvTranspose 2x2 stride 2): weight rows are packed sub-pixel major,
+    // n' = s*cq + c with s = 2*dy + dx  ->  out[c, 2y+dy, 2x+dx]
+    const int s = n0 / e.cq;
+    c0 = n0 - s * e.cq;
+    dpix = ((long)img * (e.H * 2) + (2 * y + (s >> 1))) * (e.W * 2) + (2 * x + (s & 1));
+  }
+  T* dst = out + dpix * e.out_ld + e.out_coff + c0;
+  const T* rsrc = res ? res + dpix * e.res_ld + c0 : nullptr;
+  const bool full = (n0 + 8 <= e.N);
+  const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(dst) & (sizeof(T) * 8 - 1)) == 0) &&
+                      (!rsrc || (reinterpret_cast<uintptr_t>(rsrc) & (sizeof(T) * 8 - 1)) == 0);
+  if (vec_ok) {
+    if (rsrc) {
+      float r[8];
+      load8<T>(rsrc, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += r[i];
+    }
+    if (e.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store8<T>(dst, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (n0 + i < e.N) {
+        float t = v[i];
+        if (rsrc) t += to_f<T>(rsrc[i]);
+        if (e.relu) t = fmaxf(t, 0.f);
+        dst[i] = from_f<T>(t);
+      }
+    }
+  }
+}
+
+}  // namespace kd

@@ -1,0 +1,143 @@
+// CUDA-core implicit-GEMM convolution (fp32 accumulate) for the reference-grade fp32 path and for
+// the shapes the tcgen05 kernel does not take.  Implements the same ConvOp / Epilogue contract as
+// gemm_tc.cu so both paths share the host orchestration.
+//
+// Tile: 128 pixels x 64 output channels x 16 K per step, 256 threads, 4x8 outputs per thread.
+#include "ops.cuh"
+
+namespace kd {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+
+struct SimtParams {
+  ConvOp op;
+  int ctot, taps, ktot;     // channels per tap, number of taps, taps*ctot
+  long rows_per_group;      // rows handled by one weight group
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) k_conv_gemm_simt(const SimtParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const ConvOp& op = p.op;
+  const int tid = threadIdx.x;
+  const int g = blockIdx.z;
+  const long row0 = (long)g * p.rows_per_group + (long)blockIdx.x * BM;
+  const long row_end = (long)(g + 1) * p.rows_per_group;
+  const int n0 = blockIdx.y * BN;
+  const T* __restrict__ a0 = reinterpret_cast<const T*>(op.a0);
+  const T* __restrict__ a1 = reinterpret_cast<const T*>(op.a1);
+  const T* __restrict__ w = reinterpret_cast<const T*>(op.w) + (long)g * op.w_group_stride;
+
+  // A loader: thread -> (row = tid % 128, k half = tid / 128 -> 8 consecutive k)
+  const int lrow = tid & (BM - 1);
+  const int lk0 = (tid >> 7) * 8;
+  const long prow = row0 + lrow;
+  const bool row_ok = prow < row_end;
+  int px = 0, py = 0, pd = 0, pb = 0;
+  if (row_ok) {
+    long t = prow;
+    px = (int)(t % op.W); t /= op.W;
+    py = (int)(t % op.H); t /= op.H;
+    pd = (int)(t % op.D); pb = (int)(t / op.D);
+  }
+  // B loader: thread -> (n = tid / 4 -> 64 rows, k quarter = tid % 4 -> 4 consecutive k)
+  const int bn = tid >> 2, bk0 = (tid & 3) * 4;
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int rg = tid >> 3, cg = tid & 7;  // 32 row groups x 8 col groups
+  const int hk = op.kh / 2, hw_ = op.kw / 2, hd = op.kd / 2;
+
+  for (int k0 = 0; k0 < p.ktot; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = k0 + lk0 + i;
+      float v = 0.f;
+      if (row_ok && kk < p.ktot) {
+        const int tap = kk / p.ctot, c = kk - tap * p.ctot;
+        int tx = tap % op.kw, ty = (tap / op.kw) % op.kh, td = tap / (op.kw * op.kh);
+        const int x = px + (tx - hw_) * op.dil, y = py + (ty - hk) * op.dil, d = pd + (td - hd);
+        if (x >= 0 && x < op.W && y >= 0 && y < op.H && d >= 0 && d < op.D) {
+          const long sp = (((long)pb * op.D + d) * op.H + y) * op.W + x;
+          v = (c < op.c0) ? to_f<T>(a0[sp * op.ld0 + c]) : to_f<T>(a1[sp * op.ld1 + (c - op.c0)]);
+        }
+      }
+      As[lk0 + i][lrow] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k0 + bk0 + i, n = n0 + bn;
+      float v = 0.f;
+      if (kk < p.ktot && n < op.epi.N) {
+        const int tap = kk / p.ctot, c = kk - tap * p.ctot;
+        v = to_f<T>(w[(long)n * op.w_ld + (long)tap * op.w_tap_ld + c]);
+      }
+      Bs[bk0 + i][bn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[8];
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][rg * 4]);
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][cg * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][cg * 8 + 4]);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long r = row0 + rg * 4 + i;
+    if (r >= row_end) continue;
+    long t = r;
+    const int x = (int)(t % op.W); t /= op.W;
+    const int y = (int)(t % op.H); t /= op.H;   // t = b*D + d
+    epilogue_store8<T>(op.epi, r, (int)t, y, x, n0 + cg * 8, acc[i]);
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int conv_gemm_simt(const ConvOp& op, cudaStream_t s) {
+  SimtParams p;
+  p.op = op;
+  p.ctot = op.c0 + op.c1;
+  p.taps = op.kd * op.kh * op.kw;
+  p.ktot = p.taps * p.ctot;
+  const long rows = (long)op.nimg * op.H * op.W;
+  KD_CHECK(op.groups >= 1 && rows % op.groups == 0, "conv_gemm_simt: rows %ld not divisible by groups %d", rows, op.groups);
+  p.rows_per_group = rows / op.groups;
+  KD_CHECK(op.epi.N > 0 && op.epi.out != nullptr, "conv_gemm_simt: bad epilogue");
+  if (op.epi.mode == OUT_PIXEL_SHUFFLE) KD_CHECK(op.epi.cq % 8 == 0 && op.epi.N == 4 * op.epi.cq, "pixel-shuffle needs cq%%8==0");
+  dim3 grid(cdiv(p.rows_per_group, BM), cdiv(op.epi.N, BN), op.groups);
+  KD_CHECK(grid.y <= 65535 && grid.z <= 65535, "conv_gemm_simt: grid too large");
+  k_conv_gemm_simt<T><<<grid, NT, 0, s>>>(p);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+template int conv_gemm_simt<float>(const ConvOp&, cudaStream_t);
+template int conv_gemm_simt<bf16>(const ConvOp&, cudaStream_t);
+
+template <> int conv_gemm<float>(const ConvOp& op, cudaStream_t s) { return conv_gemm_simt<float>(op, s); }
+template <> int conv_gemm<bf16>(const ConvOp& op, cudaStream_t s) {
+  if (conv_gemm_tc_eligible(op)) return conv_gemm_tc(op, s);
+  return conv_gemm_simt<bf16>(op, s);
+}
+
+}  // namespace kd

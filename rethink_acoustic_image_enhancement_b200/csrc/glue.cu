@@ -1,0 +1,618 @@
+// Memory-bound glue kernels (NHWC, vectorised 8 channels per access, fp32 math):
+// LayerNorm statistics, depthwise 3x3 (+GELU gate), MDTA Gram/norm reduction and softmax fold,
+// tiny-channel direct convolutions, pooling, bilinear up-sampling, GAP+MLP head, layout conversion.
+#include "ops.cuh"
+
+namespace kd {
+
+// =====================================================================================
+// LayerNorm statistics (KDLAE_model.py:50-52, :67-70): biased variance over channels, eps 1e-5
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_ln_stats(const T* __restrict__ x, long ld, int C, long rows,
+                                                  float* __restrict__ rstd, float* __restrict__ mu) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const T* p = x + r * ld;
+  float s = 0.f;
+  float v[8];
+  for (int c = 0; c < C; c += 8) {
+    load8<T>(p + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+  }
+  const float m = s / (float)C;
+  float q = 0.f;
+  for (int c = 0; c < C; c += 8) {
+    load8<T>(p + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - m; q = fmaf(d, d, q); }
+  }
+  rstd[r] = rsqrtf(q / (float)C + 1e-5f);
+  if (mu) mu[r] = m;
+}
+
+template <typename T>
+int ln_stats(const T* x, long ld, int C, long rows, float* rstd, float* mu, cudaStream_t s) {
+  KD_CHECK(C % 8 == 0 && ld % 8 == 0, "ln_stats: C=%d ld=%ld must be multiples of 8", C, ld);
+  k_ln_stats<T><<<cdiv(rows, 256), 256, 0, s>>>(x, ld, C, rows, rstd, mu);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int ln_stats<float>(const float*, long, int, long, float*, float*, cudaStream_t);
+template int ln_stats<bf16>(const bf16*, long, int, long, float*, float*, cudaStream_t);
+
+// =====================================================================================
+// Depthwise 3x3 (qkv_dwconv :119, ffn.dwconv :97) with optional fused GELU gate (:103-104)
+// thread = (image row y, 4 consecutive x, 8 channels)
+// =====================================================================================
+template <typename T, int GATE>
+__global__ void __launch_bounds__(128) k_dwconv3x3(const T* __restrict__ x, long ldx, T* __restrict__ out, long ldo,
+                                                   const float* __restrict__ w9c, const float* __restrict__ bias,
+                                                   int nimg, int H, int W, int C) {
+  constexpr int PX = 4;
+  const int cgroups = (GATE ? C / 2 : C) / 8;
+  const int xblocks = (W + PX - 1) / PX;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)nimg * H * xblocks * cgroups;
+  if (idx >= total) return;
+  const int cg = (int)(idx % cgroups); idx /= cgroups;
+  const int xb = (int)(idx % xblocks); idx /= xblocks;
+  const int y = (int)(idx % H);
+  const int img = (int)(idx / H);
+  const int x0 = xb * PX;
+  const int hp = C / 2;
+
+  float res[PX][8];
+#pragma unroll
+  for (int half = 0; half < (GATE ? 2 : 1); ++half) {
+    const int c0 = half * hp + cg * 8;
+    float wt[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 a = *reinterpret_cast<const float4*>(w9c + (long)t * C + c0);
+      const float4 b = *reinterpret_cast<const float4*>(w9c + (long)t * C + c0 + 4);
+      wt[t][0] = a.x; wt[t][1] = a.y; wt[t][2] = a.z; wt[t][3] = a.w;
+      wt[t][4] = b.x; wt[t][5] = b.y; wt[t][6] = b.z; wt[t][7] = b.w;
+    }
+    float acc[PX][8];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = bias ? bias[c0 + i] : 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= H) continue;
+      const T* rowp = x + ((long)img * H + yy) * W * ldx + c0;
+#pragma unroll
+      for (int cx = 0; cx < PX + 2; ++cx) {
+        const int xx = x0 + cx - 1;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        load8<T>(rowp + (long)xx * ldx, v);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int dx = cx - p;  // tap column 0..2
+          if (dx >= 0 && dx < 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(v[i], wt[dy * 3 + dx][i], acc[p][i]);
+          }
+        }
+      }
+    }
+    if (half == 0) {
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[p][i] = acc[p][i];
+    } else {
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[p][i] = gelu_erf(res[p][i]) * acc[p][i];
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int xx = x0 + p;
+    if (xx < W) store8<T>(out + (((long)img * H + y) * W + xx) * ldo + cg * 8, res[p]);
+  }
+}
+
+template <typename T>
+int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias, int nimg, int H, int W, int C,
+              int gate, cudaStream_t s) {
+  KD_CHECK(C % (gate ? 16 : 8) == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dwconv3x3: C=%d ldx=%ld ldo=%ld alignment", C, ldx, ldo);
+  const long total = (long)nimg * H * ((W + 3) / 4) * ((gate ? C / 2 : C) / 8);
+  if (gate) k_dwconv3x3<T, 1><<<cdiv(total, 128), 128, 0, s>>>(x, ldx, out, ldo, w9c, bias, nimg, H, W, C);
+  else k_dwconv3x3<T, 0><<<cdiv(total, 128), 128, 0, s>>>(x, ldx, out, ldo, w9c, bias, nimg, H, W, C);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int dwconv3x3<float>(const float*, long, float*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
+template int dwconv3x3<bf16>(const bf16*, long, bf16*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
+
+// =====================================================================================
+// MDTA reductions (KDLAE_model.py:134-137): partial Gram q k^T + squared L2 norms over pixels
+// grid = (splits, heads, nimg); thread tile 8x8 of the ch x ch Gram, pixel sub-groups share tiles
+// =====================================================================================
+constexpr int GRAM_PT = 32;  // pixels staged per step
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_mdta_gram(const T* __restrict__ qk, long ld, int HW, int C, int heads, int splits,
+                                                   float* __restrict__ part) {
+  extern __shared__ float sm[];
+  const int ch = C / heads;
+  const int split = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  float* qs = sm;                   // [PT][ch]
+  float* ks = sm + GRAM_PT * ch;    // [PT][ch]
+  const int nb = ch / 8, nblk = nb * nb;
+  const int psub = max(1, min(GRAM_PT, 256 / nblk));
+  const int tid = threadIdx.x;
+  const int blk = tid % nblk, ps = tid / nblk;
+  const bool active = ps < psub && tid < nblk * psub;
+  const int i0 = (blk / nb) * 8, j0 = (blk % nb) * 8;
+
+  const int per = (HW + splits - 1) / splits;
+  const int p_begin = split * per, p_end = min(HW, p_begin + per);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float nrm = 0.f;  // thread t < ch: |q_t|^2 ; ch <= t < 2ch: |k_t|^2
+
+  const T* base = qk + (long)img * HW * ld + head * ch;
+  const int vec_per_row = ch / 8;
+  for (int p0 = p_begin; p0 < p_end; p0 += GRAM_PT) {
+    const int np = min(GRAM_PT, p_end - p0);
+    for (int e = tid; e < GRAM_PT * vec_per_row * 2; e += 256) {
+      const int which = e / (GRAM_PT * vec_per_row);
+      const int r = e % (GRAM_PT * vec_per_row);
+      const int p = r / vec_per_row, cv = (r % vec_per_row) * 8;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (p < np) load8<T>(base + (long)(p0 + p) * ld + which * C + cv, v);
+      float* dst = (which ? ks : qs) + p * ch + cv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = v[i];
+    }
+    __syncthreads();
+    if (active) {
+      for (int p = ps; p < GRAM_PT; p += psub) {
+        const float4 qa = *reinterpret_cast<const float4*>(qs + p * ch + i0);
+        const float4 qb = *reinterpret_cast<const float4*>(qs + p * ch + i0 + 4);
+        const float4 ka = *reinterpret_cast<const float4*>(ks + p * ch + j0);
+        const float4 kb = *reinterpret_cast<const float4*>(ks + p * ch + j0 + 4);
+        const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        const float k[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(q[i], k[j], acc[i][j]);
+      }
+    }
+    if (tid < 2 * ch) {
+      const float* src = (tid < ch) ? (qs + tid) : (ks + tid - ch);
+      for (int p = 0; p < GRAM_PT; ++p) { const float v = src[p * ch]; nrm = fmaf(v, v, nrm); }
+    }
+    __syncthreads();
+  }
+  // deterministic reduction over pixel sub-groups through shared memory
+  float* G = sm;  // [ch][ch] (reuses the staging tiles; ch*ch <= 2*PT*ch needs ch <= 64, else extra space was reserved)
+  for (int e = tid; e < ch * ch; e += 256) G[e] = 0.f;
+  __syncthreads();
+  for (int r = 0; r < psub; ++r) {
+    if (active && ps == r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) G[(i0 + i) * ch + j0 + j] += acc[i][j];
+    }
+    __syncthreads();
+  }
+  float* dst = part + (((long)img * heads + head) * splits + split) * (long)(ch * ch + 2 * ch);
+  for (int e = tid; e < ch * ch; e += 256) dst[e] = G[e];
+  if (tid < 2 * ch) dst[ch * ch + tid] = nrm;
+}
+
+int mdta_gram_splits(int HW) {
+  int s = HW / 1024;
+  return s < 1 ? 1 : (s > 256 ? 256 : s);
+}
+
+template <typename T>
+int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s) {
+  const int ch = C / heads;
+  KD_CHECK(C % heads == 0 && ch % 8 == 0 && ch <= 128 && 2 * ch <= 256, "mdta_gram: unsupported channels/head %d", ch);
+  const size_t smem = sizeof(float) * (size_t)max(2 * GRAM_PT * ch, ch * ch);
+  static bool attr_f = false, attr_b = false;
+  bool& attr = std::is_same<T, float>::value ? attr_f : attr_b;
+  if (!attr) {
+    KD_CUDA(cudaFuncSetAttribute(k_mdta_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  dim3 grid(splits, heads, nimg);
+  k_mdta_gram<T><<<grid, 256, smem, s>>>(qk, ld, HW, C, heads, splits, part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int mdta_gram<float>(const float*, long, int, int, int, int, int, float*, cudaStream_t);
+template int mdta_gram<bf16>(const bf16*, long, int, int, int, int, int, float*, cudaStream_t);
+
+// softmax(cosine-Gram * temperature) (KDLAE_model.py:134-138) folded into project_out (:140,:144):
+//   project_out(attn @ v) = (Wp . blockdiag(attn)) @ v   ->  per-image C x C matrix Mb
+template <typename T>
+__global__ void __launch_bounds__(256) k_mdta_fold(const float* __restrict__ part, int C, int heads, int splits,
+                                                   const float* __restrict__ temperature, const float* __restrict__ wproj,
+                                                   T* __restrict__ mb, long mb_ld, long mb_img_stride) {
+  extern __shared__ float sm[];
+  const int ch = C / heads;
+  const int head = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  float* G = sm;                 // [ch][ch]
+  float* nq = sm + ch * ch;      // [ch]
+  float* nk = nq + ch;           // [ch]
+  const long psz = (long)ch * ch + 2 * ch;
+  const float* src = part + ((long)img * heads + head) * splits * psz;
+  for (int e = tid; e < psz; e += 256) {
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += src[(long)sp * psz + e];
+    sm[e] = s;
+  }
+  __syncthreads();
+  if (tid < 2 * ch) nq[tid] = fmaxf(sqrtf(nq[tid]), 1e-12f);  // F.normalize eps
+  __syncthreads();
+  const float temp = temperature[head];
+  for (int i = tid; i < ch; i += 256) {  // one softmax row per thread
+    float mx = -INFINITY;
+    for (int j = 0; j < ch; ++j) {
+      const float l = G[i * ch + j] / (nq[i] * nk[j]) * temp;
+      G[i * ch + j] = l;
+      mx = fmaxf(mx, l);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < ch; ++j) { const float e = expf(G[i * ch + j] - mx); G[i * ch + j] = e; sum += e; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < ch; ++j) G[i * ch + j] *= inv;
+  }
+  __syncthreads();
+  T* dst = mb + (long)img * mb_img_stride + head * ch;
+  for (int e = tid; e < C * ch; e += 256) {
+    const int n = e / ch, j = e % ch;
+    const float* wrow = wproj + (long)n * C + head * ch;
+    float s = 0.f;
+    for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], G[i * ch + j], s);
+    dst[(long)n * mb_ld + j] = from_f<T>(s);
+  }
+}
+
+template <typename T>
+int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const float* temperature, const float* wproj, T* mb,
+              long mb_ld, long mb_img_stride, cudaStream_t s) {
+  const int ch = C / heads;
+  const size_t smem = sizeof(float) * ((size_t)ch * ch + 2 * ch);
+  static bool attr_f = false, attr_b = false;
+  bool& attr = std::is_same<T, float>::value ? attr_f : attr_b;
+  if (!attr) {
+    KD_CUDA(cudaFuncSetAttribute(k_mdta_fold<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  k_mdta_fold<T><<<dim3(heads, nimg), 256, smem, s>>>(part, C, heads, splits, temperature, wproj, mb, mb_ld, mb_img_stride);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int mdta_fold<float>(const float*, int, int, int, int, const float*, const float*, float*, long, long, cudaStream_t);
+template int mdta_fold<bf16>(const float*, int, int, int, int, const float*, const float*, bf16*, long, long, cudaStream_t);
+
+// =====================================================================================
+// Direct convolutions with very few input channels (patch_embed, output_param, cen, student conv 1,
+// ASDQE stems).  thread = (pixel, 8 output channels); planar fp32 inputs.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
+  const int cgroups = op.cout / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)op.nimg * op.H * op.W * cgroups;
+  if (idx >= total) return;
+  const int cg = (int)(idx % cgroups); idx /= cgroups;
+  const int x = (int)(idx % op.W); idx /= op.W;
+  const int y = (int)(idx % op.H); idx /= op.H;
+  const int img = (int)idx;
+  const int d = img % op.D, b = img / op.D;
+  const int cin = op.cin0 + op.cin1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
+  const int hd = op.kd / 2;
+  for (int td = 0; td < op.kd; ++td) {
+    const int dd = d + td - hd;
+    if (dd < 0 || dd >= op.D) continue;
+    const long im = (long)b * op.D + dd;
+    for (int ty = 0; ty < 3; ++ty) {
+      const int yy = y + (ty - 1) * op.dil;
+      if (yy < 0 || yy >= Hin) continue;
+      for (int tx = 0; tx < 3; ++tx) {
+        const int xx = x + (tx - 1) * op.dil;
+        if (xx < 0 || xx >= Win) continue;
+        const int tap = (td * 3 + ty) * 3 + tx;
+        const long sp = (long)yy * Win + xx;
+        for (int c = 0; c < cin; ++c) {
+          float v;
+          if (c < op.cin0) {
+            const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
+            v = op.in0[o];
+            if (op.sub0) v -= op.sub0[o];
+          } else {
+            v = op.in1[im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp];
+          }
+          const float* wp = op.w + ((long)tap * cin + c) * op.cout + cg * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wp);
+          const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]);
+          acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
+          acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]);
+          acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+        }
+      }
+    }
+  }
+  if (op.relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+  }
+  T* out = reinterpret_cast<T*>(op.out);
+  store8<T>(out + (((long)img * op.H + y) * op.W + x) * op.out_ld + cg * 8, acc);
+}
+
+template <typename T>
+int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
+  KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
+  const long total = (long)op.nimg * op.H * op.W * (op.cout / 8);
+  k_conv_few_in<T><<<cdiv(total, 128), 128, 0, s>>>(op, Hin, Win);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T> int conv_few_in(const SmallConv& op, cudaStream_t s) { return conv_few_in_sized<T>(op, op.H, op.W, s); }
+template int conv_few_in<float>(const SmallConv&, cudaStream_t);
+template int conv_few_in<bf16>(const SmallConv&, cudaStream_t);
+template int conv_few_in_sized<float>(const SmallConv&, int, int, cudaStream_t);
+template int conv_few_in_sized<bf16>(const SmallConv&, int, int, cudaStream_t);
+
+// Few output channels (output, output2, outputen, student out_conv): thread = pixel, weights in smem.
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_few_out(const SmallConvOut op) {
+  extern __shared__ float wsm[];  // [cout][taps][cin]
+  const int taps = op.k * op.k;
+  const int wn = op.cout * taps * op.cin;
+  for (int e = threadIdx.x; e < wn; e += blockDim.x) wsm[e] = op.w[e];
+  __syncthreads();
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)op.nimg * op.H * op.W;
+  if (idx >= total) return;
+  const int x = (int)(idx % op.W);
+  const int y = (int)((idx / op.W) % op.H);
+  const int img = (int)(idx / ((long)op.W * op.H));
+  const T* in = reinterpret_cast<const T*>(op.in);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int hk = op.k / 2;
+  for (int ty = 0; ty < op.k; ++ty) {
+    const int yy = y + ty - hk;
+    if (yy < 0 || yy >= op.H) continue;
+    for (int tx = 0; tx < op.k; ++tx) {
+      const int xx = x + tx - hk;
+      if (xx < 0 || xx >= op.W) continue;
+      const T* p = in + (((long)img * op.H + yy) * op.W + xx) * op.in_ld;
+      const float* wt = wsm + (ty * op.k + tx) * op.cin;
+      for (int c = 0; c < op.cin; c += 8) {
+        float v[8];
+        load8<T>(p + c, v);
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+          if (co < op.cout) {
+            const float* wc = wt + (long)co * taps * op.cin + c;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[co] = fmaf(v[i], wc[i], acc[co]);
+          }
+        }
+      }
+    }
+  }
+  const long sp = (long)y * op.W + x;
+  for (int co = 0; co < op.cout; ++co) {
+    float t = acc[co] + (op.bias ? op.bias[co] : 0.f);
+    if (op.res) t += op.res[(long)img * op.res_img + (long)co * op.res_ch + sp];
+    op.out[(long)img * op.out_img + (long)co * op.out_ch + sp] = t;
+  }
+}
+
+template <typename T>
+int conv_few_out(const SmallConvOut& op, cudaStream_t s) {
+  KD_CHECK(op.cout >= 1 && op.cout <= 4 && op.cin % 8 == 0 && op.in_ld % 8 == 0, "conv_few_out: cout=%d cin=%d", op.cout, op.cin);
+  const size_t smem = sizeof(float) * (size_t)op.cout * op.k * op.k * op.cin;
+  KD_CHECK(smem <= 48 * 1024, "conv_few_out: weights do not fit shared memory");
+  const long total = (long)op.nimg * op.H * op.W;
+  k_conv_few_out<T><<<cdiv(total, 128), 128, smem, s>>>(op);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int conv_few_out<float>(const SmallConvOut&, cudaStream_t);
+template int conv_few_out<bf16>(const SmallConvOut&, cudaStream_t);
+
+// =====================================================================================
+// MaxPool 2x2 (MaxPool3d(1,2,2) / MaxPool2d(2)), bilinear x2 align_corners=True, GAP+MLP, layout
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_maxpool2x2(const T* __restrict__ x, T* __restrict__ out, int nimg, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, cg = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)nimg * OH * OW * cg;
+  if (idx >= total) return;
+  const int c = (int)(idx % cg) * 8; idx /= cg;
+  const int ox = (int)(idx % OW); idx /= OW;
+  const int oy = (int)(idx % OH);
+  const int img = (int)(idx / OH);
+  float m[8], v[8];
+  const T* p = x + (((long)img * H + 2 * oy) * W + 2 * ox) * C + c;
+  load8<T>(p, m);
+  load8<T>(p + C, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+  load8<T>(p + (long)W * C, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+  load8<T>(p + (long)W * C + C, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+  store8<T>(out + (((long)img * OH + oy) * OW + ox) * C + c, m);
+}
+template <typename T>
+int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s) {
+  KD_CHECK(C % 8 == 0, "maxpool2x2: C=%d", C);
+  const long total = (long)nimg * (H / 2) * (W / 2) * (C / 8);
+  k_maxpool2x2<T><<<cdiv(total, 256), 256, 0, s>>>(x, out, nimg, H, W, C);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int maxpool2x2<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template int maxpool2x2<bf16>(const bf16*, bf16*, int, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample2x(const T* __restrict__ x, T* __restrict__ out, int nimg, int H, int W, int C,
+                                                    int OH, int OW) {
+  const int cg = C / 8;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)nimg * OH * OW * cg;
+  if (idx >= total) return;
+  const int c = (int)(idx % cg) * 8; idx /= cg;
+  const int ox = (int)(idx % OW); idx /= OW;
+  const int oy = (int)(idx % OH);
+  const int img = (int)(idx / OH);
+  // align_corners=True: src = dst * (in-1)/(out-1)   (ASDQE_model.py:54)
+  const float sy = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float sx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  float a[8], b[8], cc[8], d[8], r[8];
+  const T* base = x + (long)img * H * W * C + c;
+  load8<T>(base + ((long)y0 * W + x0) * C, a);
+  load8<T>(base + ((long)y0 * W + x1) * C, b);
+  load8<T>(base + ((long)y1 * W + x0) * C, cc);
+  load8<T>(base + ((long)y1 * W + x1) * C, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    r[i] = (1.f - ly) * ((1.f - lx) * a[i] + lx * b[i]) + ly * ((1.f - lx) * cc[i] + lx * d[i]);
+  store8<T>(out + (((long)img * OH + oy) * OW + ox) * C + c, r);
+}
+template <typename T>
+int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s) {
+  KD_CHECK(C % 8 == 0, "upsample: C=%d", C);
+  const long total = (long)nimg * OH * OW * (C / 8);
+  k_upsample2x<T><<<cdiv(total, 256), 256, 0, s>>>(x, out, nimg, H, W, C, OH, OW);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int upsample_bilinear2x<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+template int upsample_bilinear2x<bf16>(const bf16*, bf16*, int, int, int, int, int, int, cudaStream_t);
+
+// GAP partial sums: grid (chunks, nimg), each block sums a pixel range for all C channels (C <= 64)
+template <typename T>
+__global__ void __launch_bounds__(256) k_gap_partial(const T* __restrict__ f, int HW, int C, int chunks, float* __restrict__ scratch) {
+  __shared__ float red[256];
+  const int chunk = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  const int lanes_per_c = 256 / C;       // pixel lanes per channel
+  const int c = tid % C, lane = tid / C;
+  float s = 0.f;
+  if (lane < lanes_per_c)
+    for (int p = p0 + lane; p < p1; p += lanes_per_c) s += to_f<T>(f[((long)img * HW + p) * C + c]);
+  red[tid] = (lane < lanes_per_c) ? s : 0.f;
+  __syncthreads();
+  if (tid < C) {
+    float t = 0.f;
+    for (int l = 0; l < lanes_per_c; ++l) t += red[l * C + tid];
+    scratch[((long)img * chunks + chunk) * C + tid] = t;
+  }
+}
+// regressor (ASDQE_model.py:143-154): mean -> Linear(C,256) ReLU -> Linear(256,64) ReLU -> Linear(64,1) -> tanh
+__global__ void __launch_bounds__(256) k_mlp_tanh(const float* __restrict__ scratch, int chunks, int C, float inv_hw,
+                                                  const float* __restrict__ w1, const float* __restrict__ b1,
+                                                  const float* __restrict__ w2, const float* __restrict__ b2,
+                                                  const float* __restrict__ w3, const float* __restrict__ b3,
+                                                  float* __restrict__ score) {
+  __shared__ float f[64], h1[256], h2[64];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  if (tid < C) {
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += scratch[((long)img * chunks + k) * C + tid];
+    f[tid] = t * inv_hw;
+  }
+  __syncthreads();
+  {
+    float t = b1[tid];
+    for (int c = 0; c < C; ++c) t = fmaf(w1[tid * C + c], f[c], t);
+    h1[tid] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float t = b2[tid];
+    for (int c = 0; c < 256; ++c) t = fmaf(w2[tid * 256 + c], h1[c], t);
+    h2[tid] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t = b3[0];
+    for (int c = 0; c < 64; ++c) t = fmaf(w3[c], h2[c], t);
+    score[img] = tanhf(t);
+  }
+}
+template <typename T>
+int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* w1, const float* b1, const float* w2, const float* b2,
+                 const float* w3, const float* b3, float* score, float* scratch, cudaStream_t s) {
+  KD_CHECK(C <= 64, "gap_mlp_tanh: C=%d > 64", C);
+  const int chunks = 64;
+  k_gap_partial<T><<<dim3(chunks, nimg), 256, 0, s>>>(feat, HW, C, chunks, scratch);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_mlp_tanh<<<nimg, 256, 0, s>>>(scratch, chunks, C, 1.f / (float)HW, w1, b1, w2, b2, w3, b3, score);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int gap_mlp_tanh<float>(const float*, int, int, int, const float*, const float*, const float*, const float*, const float*,
+                                 const float*, float*, float*, cudaStream_t);
+template int gap_mlp_tanh<bf16>(const bf16*, int, int, int, const float*, const float*, const float*, const float*, const float*,
+                                const float*, float*, float*, cudaStream_t);
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_nhwc_to_planar(const T* __restrict__ x, long ld, float* __restrict__ out, int HW, int C, long total) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int p = (int)(idx % HW);
+  const int c = (int)((idx / HW) % C);
+  const long img = idx / ((long)HW * C);
+  out[idx] = to_f<T>(x[(img * HW + p) * ld + c]);
+}
+template <typename T>
+int nhwc_to_planar(const T* x, long ld, float* out, int nimg, int HW, int C, cudaStream_t s) {
+  const long total = (long)nimg * HW * C;
+  k_nhwc_to_planar<T><<<cdiv(total, 256), 256, 0, s>>>(x, ld, out, HW, C, total);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int nhwc_to_planar<float>(const float*, long, float*, int, int, int, cudaStream_t);
+template int nhwc_to_planar<bf16>(const bf16*, long, float*, int, int, int, cudaStream_t);
+
+}  // namespace kd

@@ -1,0 +1,106 @@
+// Host-side launchers of every kernel class (one per fused stage).  All launchers enqueue on
+// `stream`, never allocate and never synchronise.  T is the storage type (float = reference-grade
+// path, bf16 = throughput path); accumulation and statistics are always fp32.
+#pragma once
+#include "common.cuh"
+
+namespace kd {
+
+// Implicit-GEMM convolution: out[pixel, n] = epi( sum_{tap, c} A[shift(pixel, tap), c] * W[n, tap, c] )
+struct ConvOp {
+  const void* a0 = nullptr; int c0 = 0; long ld0 = 0;   // source 0: channels [0, c0)
+  const void* a1 = nullptr; int c1 = 0; long ld1 = 0;   // source 1 (channel concat): [c0, c0+c1)
+  int nimg = 1;                 // images * frames; rows = nimg*H*W
+  int D = 1, H = 1, W = 1;      // frames per batch element (3-D convs), height, width
+  int kd = 1, kh = 1, kw = 1;   // taps (1 or 3 each)
+  int dil = 1;                  // spatial dilation (padding = dil*(k/2), zero fill)
+  const void* w = nullptr;      // weights: element (n, tap, c) at w[n*w_ld + tap*w_tap_ld + c]
+  long w_ld = 0, w_tap_ld = 0;
+  int groups = 1;               // >1: per-image weights (w + g*w_group_stride), rows split evenly
+  long w_group_stride = 0;
+  Epilogue epi;
+};
+
+template <typename T> int conv_gemm_simt(const ConvOp& op, cudaStream_t s);
+// tcgen05/TMEM/TMA implicit GEMM (bf16 storage). Returns -1 if the shape is not eligible.
+int conv_gemm_tc(const ConvOp& op, cudaStream_t s);
+bool conv_gemm_tc_eligible(const ConvOp& op);
+// dispatch: bf16 -> tcgen05 when eligible, SIMT otherwise; fp32 -> SIMT
+template <typename T> int conv_gemm(const ConvOp& op, cudaStream_t s);
+
+// per-pixel LayerNorm statistics over C channels: rstd = 1/sqrt(var+1e-5) (biased), mu optional
+template <typename T> int ln_stats(const T* x, long ld, int C, long rows, float* rstd, float* mu, cudaStream_t s);
+
+// depthwise 3x3 (pad 1) NHWC; w packed [9][C] (fp32).  gate=0: out[...,C]; gate=1: C = 2*hp,
+// out[..., j] = gelu(dw(x)[j]) * dw(x)[hp + j], j < hp
+template <typename T> int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias,
+                                    int nimg, int H, int W, int C, int gate, cudaStream_t s);
+
+// MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
+// qk: [nimg*HW, ld] with q at channel 0 and k at channel C.  part: [nimg][heads][splits][ch*ch + 2*ch] fp32
+template <typename T> int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s);
+int mdta_gram_splits(int HW);
+// softmax(normalised Gram * temperature) folded into project_out: Mb[img][n][head*ch + j] = sum_i Wp[n][head*ch+i]*attn[i][j]
+template <typename T> int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const float* temperature,
+                                    const float* wproj /*[C][C] fp32*/, T* mb, long mb_ld, long mb_img_stride, cudaStream_t s);
+
+// direct convolutions for very small channel counts (CUDA cores, HBM-bound)
+// few-in: cin <= 4 (input given as planes with explicit strides, optionally a second 1-plane source),
+struct SmallConv {
+  const float* in0 = nullptr; long in0_img = 0, in0_ch = 0; int cin0 = 0;   // fp32 planar (NCHW) source
+  const float* in1 = nullptr; long in1_img = 0, in1_ch = 0; int cin1 = 0;   // concatenated second planar source
+  const float* sub0 = nullptr;                                              // optional: value = in0 - sub0 (same strides)
+  int nimg = 1, D = 1, H = 1, W = 1, kd = 1, dil = 1;                       // 3x3 (kd=1) or 3x3x3 (kd=3) taps
+  const float* w = nullptr;    // [taps][cin][cout] fp32
+  const float* bias = nullptr; // [cout] or null
+  int cout = 0, relu = 0;
+  void* out = nullptr; long out_ld = 0;
+};
+template <typename T> int conv_few_in(const SmallConv& op, cudaStream_t s);
+// few-out: cout <= 4, NHWC input of C channels, planar fp32 output (+ planar fp32 residual)
+struct SmallConvOut {
+  const void* in = nullptr; long in_ld = 0; int cin = 0;
+  int nimg = 1, H = 1, W = 1, k = 3;      // k = 1 or 3
+  const float* w = nullptr;    // [cout][taps][cin] fp32
+  const float* bias = nullptr;
+  int cout = 0;
+  const float* res = nullptr; long res_img = 0, res_ch = 0;   // planar residual
+  float* out = nullptr; long out_img = 0, out_ch = 0;          // planar output
+};
+template <typename T> int conv_few_out(const SmallConvOut& op, cudaStream_t s);
+
+// pooling / resampling / misc glue
+template <typename T> int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s);
+template <typename T> int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s);
+template <typename T> int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* w1, const float* b1, const float* w2,
+                                       const float* b2, const float* w3, const float* b3, float* score, float* scratch, cudaStream_t s);
+template <typename T> int nhwc_to_planar(const T* x, long ld, float* out, int nimg, int HW, int C, cudaStream_t s);
+
+// weight packing (once per load_state_dict)
+enum PackMode { PACK_PLAIN = 0, PACK_HALVES = 1, PACK_PIXEL_SHUFFLE = 2, PACK_CONVT = 3 };
+struct PackOp {
+  const float* src = nullptr;   // PyTorch layout [N][Cin][taps] (or ConvTranspose [Cin][Cout][4])
+  int n_src = 0, c_src = 0, taps = 1;
+  int mode = PACK_PLAIN;
+  int h = 0, hp = 0;            // PACK_HALVES: source half size / padded half size
+  int halves_on_k = 0;          // PACK_HALVES applied to K (dst k -> src k) instead of N
+  const float* kscale = nullptr;   // [c_src]  (LayerNorm weight fold)
+  const float* nscale = nullptr;   // [n_src]  (BatchNorm scale fold)
+  void* dst = nullptr;          // [n_dst][taps][c_dst]
+  int n_dst = 0, c_dst = 0;
+};
+template <typename T> int pack_weights(const PackOp& op, cudaStream_t s);
+// WithBias-LN fold column vectors of a packed 1x1 weight: s1[n] = sum_k W'[n][k], s2[n] = sum_k lnb[k]*W[src(n)][k]
+template <typename T> int pack_ln_cols(const PackOp& op, const float* lnb, float* s1, float* s2, cudaStream_t s);
+// depthwise weights [C][1][3][3] -> [9][Cdst] fp32 (optionally with the HALVES channel map)
+int pack_dw(const float* src, int c_src, int h, int hp, float* dst, int c_dst, cudaStream_t s);
+int pack_dw_bias(const float* src, int c_src, int h, int hp, float* dst, int c_dst, cudaStream_t s);
+// small-conv weights [Cout][Cin][taps] -> [taps][Cin][Cout] fp32 (few-in) ; -> [Cout][taps][Cin] (few-out)
+int pack_few_in(const float* src, int cout, int cin, int taps, const float* nscale, float* dst, cudaStream_t s);
+int pack_few_out(const float* src, int cout, int cin, int taps, float* dst, cudaStream_t s);
+// BatchNorm(eval) fold: scale = g/sqrt(var+eps); shift = beta + (bias - mean)*scale
+int bn_fold(const float* g, const float* beta, const float* mean, const float* var, const float* bias, int n, float eps,
+            float* scale, float* shift, cudaStream_t s);
+int copy_f32(const float* src, float* dst, long n, cudaStream_t s);
+
+}  // namespace kd

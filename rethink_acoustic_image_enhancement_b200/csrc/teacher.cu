@@ -1,0 +1,464 @@
+// KDLAE-T (KDLAE_teacher, KDLAE/KDLAE_model.py:204-336): packed-weight layout and forward schedule.
+//
+// Activations are NHWC; the residual stream of each U-Net level stays resident in the workspace.
+// A TransformerBlock (:159-163) is nine launches:
+//   ln_stats -> [1x1 qkv GEMM, LN folded: weight into W, rstd as epilogue row scale] -> dw3x3
+//   -> Gram/norm reduction -> softmax folded into project_out (per-image CxC) -> [1x1 GEMM on v + residual]
+//   ln_stats -> [1x1 project_in GEMM, LN folded] -> dw3x3 + GELU gate -> [1x1 project_out GEMM + residual]
+#include <vector>
+#include "models.cuh"
+
+namespace kd {
+
+namespace {
+
+template <typename T>
+struct BlockW {
+  int C, heads, h, hp;
+  T* wqkv; float* qkv_s1; float* qkv_s2;   // [3C][C] (+ WithBias column vectors)
+  float* wdw_qkv;                          // [9][3C]
+  float* wproj;                            // [C][C] fp32 (consumed by mdta_fold)
+  float* temp;                             // [heads]
+  T* win; float* in_s1; float* in_s2;      // [2hp][C]
+  float* wdw_ffn;                          // [9][2hp]
+  T* wout;                                 // [C][hp]
+};
+
+template <typename T>
+struct TeacherW {
+  float* patch_embed;                 // few-in [9][ic][dim]
+  std::vector<BlockW<T>> enc1, enc2, enc3, latent, dec3, dec2, dec1, refine, refine_out, enhance;
+  T *down1, *down2, *down3;           // [C/2][9][C]
+  T *up4, *up3, *up2, *upen;          // [2C][9][C], rows packed sub-pixel major
+  T *reduce3, *reduce2;               // 1x1 over the [upsampled, skip] concat
+  float *output, *output_param, *output2, *cen, *outputen;
+};
+
+template <typename T>
+void layout_block(Bump& b, BlockW<T>& w, int C, int heads, int hidden, bool lnb) {
+  w.C = C; w.heads = heads; w.h = hidden; w.hp = (hidden + 7) / 8 * 8;
+  w.wqkv = b.take<T>((size_t)3 * C * C);
+  w.qkv_s1 = lnb ? b.take<float>(3 * C) : nullptr;
+  w.qkv_s2 = lnb ? b.take<float>(3 * C) : nullptr;
+  w.wdw_qkv = b.take<float>((size_t)9 * 3 * C);
+  w.wproj = b.take<float>((size_t)C * C);
+  w.temp = b.take<float>(heads);
+  w.win = b.take<T>((size_t)2 * w.hp * C);
+  w.in_s1 = lnb ? b.take<float>(2 * w.hp) : nullptr;
+  w.in_s2 = lnb ? b.take<float>(2 * w.hp) : nullptr;
+  w.wdw_ffn = b.take<float>((size_t)9 * 2 * w.hp);
+  w.wout = b.take<T>((size_t)C * w.hp);
+}
+
+template <typename T>
+void layout_teacher(const kdlae_teacher_cfg& c, Bump& b, TeacherW<T>& w) {
+  const bool lnb = c.ln_with_bias != 0;
+  const int d = c.dim, ic = c.inp_channels, oc = c.out_channels;
+  auto blocks = [&](std::vector<BlockW<T>>& v, int n, int ch_level, int head_level) {
+    v.resize(n);
+    for (int i = 0; i < n; ++i) layout_block(b, v[i], d << ch_level, c.heads[head_level], c.hidden[ch_level], lnb);
+  };
+  w.patch_embed = b.take<float>((size_t)9 * ic * d);
+  blocks(w.enc1, c.num_blocks[0], 0, 0);
+  w.down1 = b.take<T>((size_t)(d / 2) * 9 * d);
+  blocks(w.enc2, c.num_blocks[1], 1, 1);
+  w.down2 = b.take<T>((size_t)d * 9 * 2 * d);
+  blocks(w.enc3, c.num_blocks[2], 2, 2);
+  w.down3 = b.take<T>((size_t)(2 * d) * 9 * 4 * d);
+  blocks(w.latent, c.num_blocks[3], 3, 3);
+  w.up4 = b.take<T>((size_t)(16 * d) * 9 * 8 * d);
+  w.reduce3 = b.take<T>((size_t)(4 * d) * 8 * d);
+  blocks(w.dec3, c.num_blocks[2], 2, 2);
+  w.up3 = b.take<T>((size_t)(8 * d) * 9 * 4 * d);
+  w.reduce2 = b.take<T>((size_t)(2 * d) * 4 * d);
+  blocks(w.dec2, c.num_blocks[1], 1, 1);
+  w.up2 = b.take<T>((size_t)(4 * d) * 9 * 2 * d);
+  blocks(w.dec1, c.num_blocks[0], 1, 0);            // dim*2 channels with heads[0] (KDLAE_model.py:246)
+  blocks(w.refine, c.num_refinement_blocks, 1, 0);
+  w.output = b.take<float>((size_t)oc * 9 * 2 * d);
+  w.output_param = b.take<float>((size_t)9 * (oc + 1) * 2 * d);
+  blocks(w.refine_out, c.num_refinement_blocks, 1, 0);
+  w.output2 = b.take<float>((size_t)oc * 9 * 2 * d);
+  w.cen = w.outputen = nullptr;
+  w.upen = nullptr;
+  if (c.sr_head) {
+    w.cen = b.take<float>((size_t)9 * oc * 2 * d);
+    w.upen = b.take<T>((size_t)(4 * d) * 9 * 2 * d);
+    blocks(w.enhance, c.num_refinement_blocks, 0, 0);
+    w.outputen = b.take<float>((size_t)oc * 9 * d);
+  }
+}
+
+struct Cursor {
+  const float* const* t; int n; int i;
+  const float* next() { const float* p = (i < n) ? t[i] : nullptr; ++i; return p; }
+};
+
+template <typename T>
+int pack_block(const BlockW<T>& w, Cursor& cur, bool lnb, cudaStream_t s) {
+  const int C = w.C;
+  const float* ln1w = cur.next(); const float* ln1b = lnb ? cur.next() : nullptr;
+  const float* temp = cur.next();
+  const float* qkv = cur.next(); const float* qkv_dw = cur.next(); const float* proj = cur.next();
+  const float* ln2w = cur.next(); const float* ln2b = lnb ? cur.next() : nullptr;
+  const float* pin = cur.next(); const float* dw = cur.next(); const float* pout = cur.next();
+  KD_CHECK(pout != nullptr && ln1w != nullptr, "teacher_pack: missing tensors inside a TransformerBlock");
+  PackOp p;
+  p.src = qkv; p.n_src = 3 * C; p.c_src = C; p.taps = 1; p.kscale = ln1w; p.dst = w.wqkv; p.n_dst = 3 * C; p.c_dst = C;
+  KD_TRY(pack_weights<T>(p, s));
+  if (lnb) KD_TRY(pack_ln_cols<T>(p, ln1b, w.qkv_s1, w.qkv_s2, s));
+  KD_TRY(pack_dw(qkv_dw, 3 * C, 0, 0, w.wdw_qkv, 3 * C, s));
+  KD_TRY(copy_f32(proj, w.wproj, (long)C * C, s));
+  KD_TRY(copy_f32(temp, w.temp, w.heads, s));
+  // project_in: the two chunk(2) halves of h rows are each padded to hp (127 -> 128 ...) so both start 8-aligned
+  p = PackOp();
+  p.src = pin; p.n_src = 2 * w.h; p.c_src = C; p.taps = 1; p.mode = PACK_HALVES; p.h = w.h; p.hp = w.hp; p.kscale = ln2w;
+  p.dst = w.win; p.n_dst = 2 * w.hp; p.c_dst = C;
+  KD_TRY(pack_weights<T>(p, s));
+  if (lnb) KD_TRY(pack_ln_cols<T>(p, ln2b, w.in_s1, w.in_s2, s));
+  KD_TRY(pack_dw(dw, 2 * w.h, w.h, w.hp, w.wdw_ffn, 2 * w.hp, s));
+  p = PackOp();
+  p.src = pout; p.n_src = C; p.c_src = w.h; p.taps = 1; p.mode = PACK_HALVES; p.halves_on_k = 1; p.h = w.h; p.hp = w.hp;
+  p.dst = w.wout; p.n_dst = C; p.c_dst = w.hp;
+  KD_TRY(pack_weights<T>(p, s));
+  return 0;
+}
+
+template <typename T>
+int pack_conv3(const float* src, T* dst, int cout, int cin, int mode, cudaStream_t s) {
+  KD_CHECK(src != nullptr, "teacher_pack: missing 3x3 conv weight");
+  PackOp p;
+  p.src = src; p.n_src = cout; p.c_src = cin; p.taps = 9; p.mode = mode; p.dst = dst; p.n_dst = cout; p.c_dst = cin;
+  return pack_weights<T>(p, s);
+}
+template <typename T>
+int pack_conv1(const float* src, T* dst, int cout, int cin, cudaStream_t s) {
+  KD_CHECK(src != nullptr, "teacher_pack: missing 1x1 conv weight");
+  PackOp p;
+  p.src = src; p.n_src = cout; p.c_src = cin; p.taps = 1; p.dst = dst; p.n_dst = cout; p.c_dst = cin;
+  return pack_weights<T>(p, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct Scratch {
+  T* bufA; T* bufB;          // qkv / project_in output ; dwconv output / gated hidden
+  float* rstd; float* mu;    // per-pixel LN statistics
+  float* gram;               // Gram partials
+  T* mb;                     // per-image folded attention matrices [nimg][C][C]
+};
+
+// One TransformerBlock (KDLAE_model.py:159-163) over `nimg` images of H x W pixels, C channels.
+// x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
+template <typename T>
+int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, int nimg, int H, int W, Scratch<T>& sc,
+              cudaStream_t s) {
+  const int C = w.C, HW = H * W;
+  const long rows = (long)nimg * HW;
+  // ---- x = x + project_out(attn(norm1(x))) ----
+  KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  ConvOp g;
+  g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
+  g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
+  g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.qkv_s1; g.epi.col_bias = w.qkv_s2;
+  g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
+  KD_TRY(conv_gemm<T>(g, s));
+  KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s));
+  const int splits = mdta_gram_splits(HW);
+  KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
+  KD_TRY(mdta_fold<T>(sc.gram, nimg, C, w.heads, splits, w.temp, w.wproj, sc.mb, C, (long)C * C, s));
+  g = ConvOp();
+  g.a0 = sc.bufB + 2 * C; g.c0 = C; g.ld0 = 3 * C; g.nimg = nimg; g.H = H; g.W = W;
+  g.w = sc.mb; g.w_ld = C; g.w_tap_ld = C; g.groups = nimg; g.w_group_stride = (long)C * C;
+  g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = x; g.epi.out_ld = ldx; g.epi.N = C; g.epi.H = H; g.epi.W = W;
+  KD_TRY(conv_gemm<T>(g, s));
+  // ---- x = x + ffn(norm2(x)) ----
+  KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  g = ConvOp();
+  g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
+  g.w = w.win; g.w_ld = C; g.w_tap_ld = C;
+  g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.in_s1; g.epi.col_bias = w.in_s2;
+  g.epi.out = sc.bufA; g.epi.out_ld = 2 * w.hp; g.epi.N = 2 * w.hp; g.epi.H = H; g.epi.W = W;
+  KD_TRY(conv_gemm<T>(g, s));
+  KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s));
+  g = ConvOp();
+  g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
+  g.w = w.wout; g.w_ld = w.hp; g.w_tap_ld = w.hp;
+  g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = xout; g.epi.out_ld = ldo; g.epi.N = C; g.epi.H = H; g.epi.W = W;
+  KD_TRY(conv_gemm<T>(g, s));
+  return 0;
+}
+
+template <typename T>
+int run_blocks(const std::vector<BlockW<T>>& v, bool lnb, T* x, long ldx, T* last_out, long last_ld, int nimg, int H, int W,
+               Scratch<T>& sc, cudaStream_t s) {
+  for (size_t i = 0; i < v.size(); ++i) {
+    const bool last = (i + 1 == v.size());
+    KD_TRY(run_block<T>(v[i], lnb, x, ldx, last ? last_out : x, last ? last_ld : ldx, nimg, H, W, sc, s));
+  }
+  return 0;
+}
+
+// dense 3x3 conv (pad 1, no bias) as implicit GEMM with PixelShuffle / PixelUnshuffle addressing in the epilogue
+template <typename T>
+int conv3x3(const T* a, int cin, long lda, const T* w, int cout, int nimg, int H, int W, int mode, T* out, long ldo, int coff,
+            cudaStream_t s) {
+  ConvOp g;
+  g.a0 = a; g.c0 = cin; g.ld0 = lda; g.nimg = nimg; g.H = H; g.W = W; g.kh = 3; g.kw = 3;
+  g.w = w; g.w_ld = 9L * cin; g.w_tap_ld = cin;
+  g.epi.out = out; g.epi.out_ld = ldo; g.epi.out_coff = coff; g.epi.N = cout; g.epi.H = H; g.epi.W = W; g.epi.mode = mode;
+  g.epi.cq = cout / 4;
+  return conv_gemm<T>(g, s);
+}
+
+struct WsLayout {
+  size_t x1, d1, x2, x3, x4, d3, d2, s0, bufA, bufB, o1, rstd, mu, gram, mb, total;
+};
+
+template <typename T>
+WsLayout ws_layout(const kdlae_teacher_cfg& c, int mb, int H, int W) {
+  Bump b;
+  WsLayout L;
+  const size_t P1 = (size_t)mb * H * W, d = c.dim;
+  const bool sr = c.sr_head != 0;
+  auto off = [&](size_t elems, size_t esz) { b.off = align_up(b.off, 256); size_t o = b.off; b.off += elems * esz; return o; };
+  const size_t hp1 = (c.hidden[0] + 7) / 8 * 8, hp2 = (c.hidden[1] + 7) / 8 * 8, hp3 = (c.hidden[2] + 7) / 8 * 8,
+               hp4 = (c.hidden[3] + 7) / 8 * 8;
+  L.x1 = off(P1 * d, sizeof(T));
+  L.d1 = off(P1 * 2 * d, sizeof(T));
+  L.x2 = off(P1 / 4 * 2 * d, sizeof(T));
+  L.x3 = off(P1 / 16 * 4 * d, sizeof(T));
+  L.x4 = off(P1 / 64 * 8 * d, sizeof(T));
+  L.d3 = off(P1 / 16 * 4 * d, sizeof(T));
+  L.d2 = off(P1 / 4 * 2 * d, sizeof(T));
+  L.s0 = off(sr ? P1 * 4 * d : 0, sizeof(T));
+  // bufA holds qkv (3C) or project_in output (2hp); bufB holds dwconv(qkv) (3C), the gated hidden (hp) or an upsampled map
+  size_t a = 0, bb = 0;
+  auto upd = [&](size_t pix, size_t C, size_t hp) {
+    a = std::max(a, pix * std::max(3 * C, 2 * hp));
+    bb = std::max(bb, pix * std::max(3 * C, hp));
+  };
+  upd(P1, d, hp1); upd(P1 / 4, 2 * d, hp2); upd(P1 / 16, 4 * d, hp3); upd(P1 / 64, 8 * d, hp4);
+  upd(P1, 2 * d, hp2);
+  if (sr) upd(P1 * 4, d, hp1);
+  L.bufA = off(a, sizeof(T));
+  L.bufB = off(bb, sizeof(T));
+  L.o1 = off(P1 * c.out_channels, sizeof(float));
+  const size_t maxpix = sr ? P1 * 4 : P1;
+  L.rstd = off(maxpix, sizeof(float));
+  L.mu = off(c.ln_with_bias ? maxpix : 0, sizeof(float));
+  // Gram partials: nimg * heads * splits * (ch*ch + 2ch); the largest case is a full-resolution stage
+  size_t gmax = 0;
+  auto gr = [&](size_t hw, size_t C, size_t heads) {
+    const size_t ch = C / heads;
+    gmax = std::max(gmax, (size_t)mb * heads * mdta_gram_splits((int)hw) * (ch * ch + 2 * ch));
+  };
+  const size_t HW = (size_t)H * W;
+  gr(HW, d, c.heads[0]); gr(HW / 4, 2 * d, c.heads[1]); gr(HW / 16, 4 * d, c.heads[2]); gr(HW / 64, 8 * d, c.heads[3]);
+  gr(HW, 2 * d, c.heads[0]);
+  if (sr) gr(HW * 4, d, c.heads[0]);
+  L.gram = off(gmax, sizeof(float));
+  L.mb = off((size_t)mb * 8 * d * 8 * d, sizeof(T));
+  L.total = align_up(b.off, 256);
+  return L;
+}
+
+}  // namespace
+
+int teacher_num_tensors(const kdlae_teacher_cfg& c) {
+  const int per_block = 9 + (c.ln_with_bias ? 2 : 0);
+  int nblk = c.num_blocks[0] * 2 + c.num_blocks[1] * 2 + c.num_blocks[2] * 2 + c.num_blocks[3] + c.num_refinement_blocks * 2;
+  int n = 1 + 3 + 3 + 2 + 3;  // patch_embed, downs, ups, reduce, output/output_param/output2
+  if (c.sr_head) { nblk += c.num_refinement_blocks; n += 3; }
+  return n + nblk * per_block;
+}
+
+template <typename T>
+size_t teacher_packed_bytes(const kdlae_teacher_cfg& cfg) {
+  Bump b;
+  TeacherW<T> w;
+  layout_teacher<T>(cfg, b, w);
+  return align_up(b.off, 256);
+}
+
+template <typename T>
+int teacher_pack(const kdlae_teacher_cfg& c, const float* const* tensors, int n_tensors, void* packed, size_t packed_bytes,
+                 cudaStream_t s) {
+  KD_CHECK(n_tensors == teacher_num_tensors(c), "teacher_pack: expected %d state_dict tensors, got %d", teacher_num_tensors(c),
+           n_tensors);
+  KD_CHECK(c.dim % 16 == 0, "teacher_pack: dim=%d must be a multiple of 16", c.dim);
+  for (int l = 0; l < 4; ++l)
+    KD_CHECK(c.heads[l] > 0 && (c.dim << l) % c.heads[l] == 0 && ((c.dim << l) / c.heads[l]) % 8 == 0,
+             "teacher_pack: channels per head must be a multiple of 8 (level %d)", l);
+  for (int l = 0; l < 4; ++l) KD_CHECK(c.num_blocks[l] >= 1, "teacher_pack: num_blocks[%d] must be >= 1", l);
+  Bump b;
+  b.base = reinterpret_cast<uint8_t*>(packed);
+  TeacherW<T> w;
+  layout_teacher<T>(c, b, w);
+  KD_CHECK(b.off <= packed_bytes, "teacher_pack: packed buffer too small (%zu < %zu)", packed_bytes, b.off);
+  const bool lnb = c.ln_with_bias != 0;
+  const int d = c.dim, ic = c.inp_channels, oc = c.out_channels;
+  Cursor cur{tensors, n_tensors, 0};
+  auto blocks = [&](std::vector<BlockW<T>>& v) -> int {
+    for (auto& bw : v) KD_TRY(pack_block<T>(bw, cur, lnb, s));
+    return 0;
+  };
+  KD_TRY(pack_few_in(cur.next(), d, ic, 9, nullptr, w.patch_embed, s));
+  KD_TRY(blocks(w.enc1));
+  KD_TRY(pack_conv3<T>(cur.next(), w.down1, d / 2, d, PACK_PLAIN, s));
+  KD_TRY(blocks(w.enc2));
+  KD_TRY(pack_conv3<T>(cur.next(), w.down2, d, 2 * d, PACK_PLAIN, s));
+  KD_TRY(blocks(w.enc3));
+  KD_TRY(pack_conv3<T>(cur.next(), w.down3, 2 * d, 4 * d, PACK_PLAIN, s));
+  KD_TRY(blocks(w.latent));
+  KD_TRY(pack_conv3<T>(cur.next(), w.up4, 16 * d, 8 * d, PACK_PIXEL_SHUFFLE, s));
+  KD_TRY(pack_conv1<T>(cur.next(), w.reduce3, 4 * d, 8 * d, s));
+  KD_TRY(blocks(w.dec3));
+  KD_TRY(pack_conv3<T>(cur.next(), w.up3, 8 * d, 4 * d, PACK_PIXEL_SHUFFLE, s));
+  KD_TRY(pack_conv1<T>(cur.next(), w.reduce2, 2 * d, 4 * d, s));
+  KD_TRY(blocks(w.dec2));
+  KD_TRY(pack_conv3<T>(cur.next(), w.up2, 4 * d, 2 * d, PACK_PIXEL_SHUFFLE, s));
+  KD_TRY(blocks(w.dec1));
+  KD_TRY(blocks(w.refine));
+  KD_TRY(pack_few_out(cur.next(), oc, 2 * d, 9, w.output, s));
+  KD_TRY(pack_few_in(cur.next(), 2 * d, oc + 1, 9, nullptr, w.output_param, s));
+  KD_TRY(blocks(w.refine_out));
+  KD_TRY(pack_few_out(cur.next(), oc, 2 * d, 9, w.output2, s));
+  if (c.sr_head) {
+    KD_TRY(pack_few_in(cur.next(), 2 * d, oc, 9, nullptr, w.cen, s));
+    KD_TRY(pack_conv3<T>(cur.next(), w.upen, 4 * d, 2 * d, PACK_PIXEL_SHUFFLE, s));
+    KD_TRY(blocks(w.enhance));
+    KD_TRY(pack_few_out(cur.next(), oc, d, 9, w.outputen, s));
+  }
+  KD_CHECK(cur.i == n_tensors, "teacher_pack: consumed %d of %d tensors", cur.i, n_tensors);
+  return 0;
+}
+
+template <typename T>
+size_t teacher_workspace_bytes(const kdlae_teacher_cfg& cfg, int mb, int H, int W) {
+  return ws_layout<T>(cfg, mb, H, W).total;
+}
+
+template <typename T>
+int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float* img, const float* rate, float* hq, float* sr,
+                    int B, int H, int W, int micro_batch, void* ws, size_t ws_bytes, cudaStream_t s) {
+  KD_CHECK(H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
+           "KDLAE_teacher: H and W must be multiples of 8 (got %dx%d) - pixel_unshuffle expects divisible sizes", H, W);
+  KD_CHECK(B >= 1 && micro_batch >= 1, "KDLAE_teacher: bad batch %d / micro_batch %d", B, micro_batch);
+  KD_CHECK(!c.params_cat || rate != nullptr, "KDLAE_teacher: denoise_rate is required when params == 'cat'");
+  KD_CHECK((c.sr_head != 0) == (sr != nullptr), "KDLAE_teacher: sr buffer must be given iff static == 'train'");
+  if (micro_batch > B) micro_batch = B;
+  const WsLayout L = ws_layout<T>(c, micro_batch, H, W);
+  KD_CHECK(ws_bytes >= L.total, "KDLAE_teacher: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  Bump b;
+  b.base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(packed));
+  TeacherW<T> w;
+  layout_teacher<T>(c, b, w);
+
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  T* x1 = reinterpret_cast<T*>(wsb + L.x1); T* d1 = reinterpret_cast<T*>(wsb + L.d1);
+  T* x2 = reinterpret_cast<T*>(wsb + L.x2); T* x3 = reinterpret_cast<T*>(wsb + L.x3);
+  T* x4 = reinterpret_cast<T*>(wsb + L.x4); T* d3 = reinterpret_cast<T*>(wsb + L.d3);
+  T* d2 = reinterpret_cast<T*>(wsb + L.d2); T* s0 = reinterpret_cast<T*>(wsb + L.s0);
+  float* o1 = reinterpret_cast<float*>(wsb + L.o1);
+  Scratch<T> sc;
+  sc.bufA = reinterpret_cast<T*>(wsb + L.bufA); sc.bufB = reinterpret_cast<T*>(wsb + L.bufB);
+  sc.rstd = reinterpret_cast<float*>(wsb + L.rstd); sc.mu = reinterpret_cast<float*>(wsb + L.mu);
+  sc.gram = reinterpret_cast<float*>(wsb + L.gram); sc.mb = reinterpret_cast<T*>(wsb + L.mb);
+
+  const bool lnb = c.ln_with_bias != 0;
+  const int d = c.dim, ic = c.inp_channels, oc = c.out_channels;
+  const long HW = (long)H * W;
+
+  for (int b0 = 0; b0 < B; b0 += micro_batch) {
+    const int n = std::min(micro_batch, B - b0);
+    const float* img_b = img + (long)b0 * ic * HW;
+    const float* rate_b = rate ? rate + (long)b0 * HW : nullptr;
+    float* hq_b = hq + (long)b0 * oc * HW;
+    float* sr_b = sr ? sr + (long)b0 * oc * HW * 4 : nullptr;
+
+    // 1. patch_embed 3x3 ic -> dim (:173)
+    SmallConv fi;
+    fi.in0 = img_b; fi.in0_img = ic * HW; fi.in0_ch = HW; fi.cin0 = ic; fi.nimg = n; fi.H = H; fi.W = W;
+    fi.w = w.patch_embed; fi.cout = d; fi.out = x1; fi.out_ld = d;
+    KD_TRY(conv_few_in<T>(fi, s));
+    // 2. encoder level 1; its last block writes the skip straight into the concat slot d1[..., d:2d]
+    KD_TRY(run_blocks<T>(w.enc1, lnb, x1, d, d1 + d, 2 * d, n, H, W, sc, s));
+    // 3. down1_2 (conv d -> d/2 + PixelUnshuffle) and level 2
+    KD_TRY(conv3x3<T>(d1 + d, d, 2 * d, w.down1, d / 2, n, H, W, OUT_PIXEL_UNSHUFFLE, x2, 2 * d, 0, s));
+    KD_TRY(run_blocks<T>(w.enc2, lnb, x2, 2 * d, x2, 2 * d, n, H / 2, W / 2, sc, s));
+    KD_TRY(conv3x3<T>(x2, 2 * d, 2 * d, w.down2, d, n, H / 2, W / 2, OUT_PIXEL_UNSHUFFLE, x3, 4 * d, 0, s));
+    KD_TRY(run_blocks<T>(w.enc3, lnb, x3, 4 * d, x3, 4 * d, n, H / 4, W / 4, sc, s));
+    KD_TRY(conv3x3<T>(x3, 4 * d, 4 * d, w.down3, 2 * d, n, H / 4, W / 4, OUT_PIXEL_UNSHUFFLE, x4, 8 * d, 0, s));
+    KD_TRY(run_blocks<T>(w.latent, lnb, x4, 8 * d, x4, 8 * d, n, H / 8, W / 8, sc, s));
+    // 4. up4_3 (conv 8d -> 16d + PixelShuffle) -> cat with enc3 -> reduce_chan_level3 (dual-source 1x1)
+    KD_TRY(conv3x3<T>(x4, 8 * d, 8 * d, w.up4, 16 * d, n, H / 8, W / 8, OUT_PIXEL_SHUFFLE, sc.bufB, 4 * d, 0, s));
+    {
+      ConvOp g;
+      g.a0 = sc.bufB; g.c0 = 4 * d; g.ld0 = 4 * d; g.a1 = x3; g.c1 = 4 * d; g.ld1 = 4 * d;
+      g.nimg = n; g.H = H / 4; g.W = W / 4; g.w = w.reduce3; g.w_ld = 8 * d; g.w_tap_ld = 8 * d;
+      g.epi.out = d3; g.epi.out_ld = 4 * d; g.epi.N = 4 * d; g.epi.H = H / 4; g.epi.W = W / 4;
+      KD_TRY(conv_gemm<T>(g, s));
+    }
+    KD_TRY(run_blocks<T>(w.dec3, lnb, d3, 4 * d, d3, 4 * d, n, H / 4, W / 4, sc, s));
+    KD_TRY(conv3x3<T>(d3, 4 * d, 4 * d, w.up3, 8 * d, n, H / 4, W / 4, OUT_PIXEL_SHUFFLE, sc.bufB, 2 * d, 0, s));
+    {
+      ConvOp g;
+      g.a0 = sc.bufB; g.c0 = 2 * d; g.ld0 = 2 * d; g.a1 = x2; g.c1 = 2 * d; g.ld1 = 2 * d;
+      g.nimg = n; g.H = H / 2; g.W = W / 2; g.w = w.reduce2; g.w_ld = 4 * d; g.w_tap_ld = 4 * d;
+      g.epi.out = d2; g.epi.out_ld = 2 * d; g.epi.N = 2 * d; g.epi.H = H / 2; g.epi.W = W / 2;
+      KD_TRY(conv_gemm<T>(g, s));
+    }
+    KD_TRY(run_blocks<T>(w.dec2, lnb, d2, 2 * d, d2, 2 * d, n, H / 2, W / 2, sc, s));
+    // 5. up2_1 writes channels [0, d) of d1 (the skip already sits in [d, 2d)); no reduce conv at level 1 (:245)
+    KD_TRY(conv3x3<T>(d2, 2 * d, 2 * d, w.up2, 4 * d, n, H / 2, W / 2, OUT_PIXEL_SHUFFLE, d1, 2 * d, 0, s));
+    KD_TRY(run_blocks<T>(w.dec1, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
+    KD_TRY(run_blocks<T>(w.refine, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
+    // 6. output 3x3 2d -> oc ; denoise-rate tail (:314-321)
+    SmallConvOut fo;
+    fo.in = d1; fo.in_ld = 2 * d; fo.cin = 2 * d; fo.nimg = n; fo.H = H; fo.W = W; fo.k = 3; fo.w = w.output; fo.cout = oc;
+    if (c.params_cat) {
+      fo.out = o1; fo.out_img = oc * HW; fo.out_ch = HW;
+      KD_TRY(conv_few_out<T>(fo, s));
+      fi = SmallConv();
+      fi.in0 = o1; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc;
+      fi.in1 = rate_b; fi.in1_img = HW; fi.in1_ch = HW; fi.cin1 = 1;
+      fi.nimg = n; fi.H = H; fi.W = W; fi.dil = 2; fi.w = w.output_param; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
+      KD_TRY(conv_few_in<T>(fi, s));
+      KD_TRY(run_blocks<T>(w.refine_out, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
+      fo.w = w.output2;
+    }
+    fo.res = img_b; fo.res_img = ic * HW; fo.res_ch = HW;   // out_hq = out + inp_img (:321)
+    fo.out = hq_b; fo.out_img = oc * HW; fo.out_ch = HW;
+    KD_CHECK(ic == oc, "KDLAE_teacher: out + inp_img needs inp_channels == out_channels");
+    KD_TRY(conv_few_out<T>(fo, s));
+    // 7. SR head (:324-329): cen -> upen (PixelShuffle) -> enhance -> outputen
+    if (c.sr_head) {
+      fi = SmallConv();
+      fi.in0 = hq_b; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc; fi.nimg = n; fi.H = H; fi.W = W;
+      fi.w = w.cen; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
+      KD_TRY(conv_few_in<T>(fi, s));
+      KD_TRY(conv3x3<T>(d1, 2 * d, 2 * d, w.upen, 4 * d, n, H, W, OUT_PIXEL_SHUFFLE, s0, d, 0, s));
+      KD_TRY(run_blocks<T>(w.enhance, lnb, s0, d, s0, d, n, 2 * H, 2 * W, sc, s));
+      fo = SmallConvOut();
+      fo.in = s0; fo.in_ld = d; fo.cin = d; fo.nimg = n; fo.H = 2 * H; fo.W = 2 * W; fo.k = 3; fo.w = w.outputen; fo.cout = oc;
+      fo.out = sr_b; fo.out_img = oc * HW * 4; fo.out_ch = HW * 4;
+      KD_TRY(conv_few_out<T>(fo, s));
+    }
+  }
+  return 0;
+}
+
+#define INST(T)                                                                                                              \
+  template size_t teacher_packed_bytes<T>(const kdlae_teacher_cfg&);                                                         \
+  template int teacher_pack<T>(const kdlae_teacher_cfg&, const float* const*, int, void*, size_t, cudaStream_t);              \
+  template size_t teacher_workspace_bytes<T>(const kdlae_teacher_cfg&, int, int, int);                                       \
+  template int teacher_forward<T>(const kdlae_teacher_cfg&, const void*, const float*, const float*, float*, float*, int,    \
+                                  int, int, int, void*, size_t, cudaStream_t);
+INST(float)
+INST(bf16)
+#undef INST
+
+}  // namespace kd

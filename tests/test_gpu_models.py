@@ -1,0 +1,152 @@
+"""GPU parity tests proper: the CUDA path (through the drop-in modules -> C ABI) against the golden
+fixtures frozen from the reference and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): fp32 path <= 1e-4 max-abs on outputs in [0,1]; bf16 path >= 50 dB PSNR;
+ASDQE scores within 1e-3 (fp32 path; bf16 path reported and held to 1e-2).
+"""
+import pytest
+import torch
+
+import oracle
+from oracle import synth
+import rethink_acoustic_image_enhancement_b200 as pk
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-4
+BF16_PSNR = 50.0
+
+
+def _teacher(kw, seed, temp_scale, precision):
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(synth.teacher_state_dict(seed=seed, temp_scale=temp_scale, **kw), strict=True)
+    return m.to(DEV).eval().set_precision(precision)
+
+
+TEACHER = ["teacher_c1_biasfree_64", "teacher_c3_withbias_32x48", "teacher_c1_nosr_40x24"]
+
+
+@pytest.mark.parametrize("name", TEACHER)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_matches_reference_fixture(name, precision, manifest):
+    case, g = manifest[name], load_golden(name)
+    kw = case["kwargs"]
+    m = _teacher(kw, case["seed"], case["temp_scale"], precision)
+    b, h, w = case["shape"]
+    rate = g["rate"].view(b, 1, 1, 1).expand(b, 1, h, w).to(DEV)
+    with torch.no_grad():
+        out = m({"img": g["img"].to(DEV), "denoise_rate": rate})
+    torch.cuda.synchronize()
+    assert (out["sr"] is None) == ("sr" not in g)
+    for key in ("hq", "sr"):
+        if key not in g:
+            continue
+        got = out[key].cpu()
+        assert got.shape == g[key].shape and torch.isfinite(got).all()
+        err = (got - g[key]).abs().max().item()
+        p = synth.psnr(got, g[key])
+        print(f"{name} {precision} {key}: max|d|={err:.3e} psnr={p:.2f} dB")
+        if precision == "fp32":
+            assert err <= FP32_TOL, f"{key}: {err}"
+        else:
+            assert p >= BF16_PSNR, f"{key}: {p} dB"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_128_against_oracle_and_batch_invariance(precision):
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+    sd = synth.teacher_state_dict(seed=7, temp_scale=5.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision(precision)
+    img = synth.seeded_tensor("t128.img", (3, 1, 128, 128), 7, "sonar")
+    rate = torch.tensor([0.6, 0.1, 0.9]).view(3, 1, 1, 1).expand(3, 1, 128, 128).contiguous()
+    with torch.no_grad():
+        hq_ref, sr_ref = oracle.teacher_forward(sd, img[:1], rate[:1])
+        m.micro_batch = 2  # 3 images as micro-batches of 2 + 1
+        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+        m.micro_batch = 1
+        one = m({"img": img[2:3].to(DEV), "denoise_rate": rate[2:3].to(DEV)})
+    torch.cuda.synchronize()
+    hq, sr = out["hq"].cpu(), out["sr"].cpu()
+    e1, e2 = (hq[:1] - hq_ref).abs().max().item(), (sr[:1] - sr_ref).abs().max().item()
+    p1, p2 = synth.psnr(hq[:1], hq_ref), synth.psnr(sr[:1], sr_ref)
+    print(f"teacher128 {precision}: hq max|d|={e1:.3e} psnr={p1:.2f}; sr max|d|={e2:.3e} psnr={p2:.2f}")
+    if precision == "fp32":
+        assert e1 <= FP32_TOL and e2 <= FP32_TOL
+    else:
+        assert p1 >= BF16_PSNR and p2 >= BF16_PSNR
+    # images are independent: result must not depend on batch position or micro-batch size (bit-exact)
+    assert torch.equal(out["hq"][2:3], one["hq"]) and torch.equal(out["sr"][2:3], one["sr"])
+
+
+def test_teacher_repack_after_weight_update():
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no")
+    m = _teacher(kw, 3, 1.0, "bf16")
+    x = {"img": torch.rand(1, 1, 32, 32, device=DEV), "denoise_rate": torch.full((1, 1, 32, 32), 0.5, device=DEV)}
+    with torch.no_grad():
+        a = m(x)["hq"].clone()
+        m.output2.weight.mul_(0.0)     # in-place update bumps the tensor version -> packed weights are rebuilt
+        b = m(x)["hq"]
+    assert m(x)["sr"] is None
+    assert not torch.equal(a, b)
+    assert torch.allclose(b, x["img"], atol=1e-6)  # output2 == 0  =>  hq == inp_img (KDLAE_model.py:321)
+
+
+def test_teacher_rejects_bad_sizes():
+    m = _teacher(dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no"), 0, 1.0, "bf16")
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        m({"img": torch.rand(1, 1, 36, 64, device=DEV), "denoise_rate": torch.rand(1, 1, 36, 64, device=DEV)})
+
+
+STUDENT = ["student_f5_32x40", "student_f7_16x16", "student_f1_nores_8x12"]
+
+
+@pytest.mark.parametrize("name", STUDENT)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_student_matches_reference_fixture(name, precision, manifest):
+    case, g = manifest[name], load_golden(name)
+    m = pk.KDLAE_student(residual=case["residual"])
+    m.load_state_dict(synth.student_state_dict(seed=case["seed"]), strict=True)
+    m = m.to(DEV).eval().set_precision(precision)
+    with torch.no_grad():
+        y = m(g["x"].to(DEV)).cpu()
+    err, p = (y - g["y"]).abs().max().item(), synth.psnr(y, g["y"])
+    print(f"{name} {precision}: max|d|={err:.3e} psnr={p:.2f} dB")
+    assert y.shape == g["y"].shape
+    if precision == "fp32":
+        assert err <= FP32_TOL
+    else:
+        assert p >= BF16_PSNR
+
+
+def test_student_rejects_bad_sizes():
+    m = pk.KDLAE_student(residual=True).to(DEV)
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        m(torch.rand(1, 5, 18, 16, device=DEV))
+
+
+ASDQE = ["asdqe_48x40", "asdqe_32x32"]
+
+
+@pytest.mark.parametrize("name", ASDQE)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_asdqe_matches_reference_fixture(name, precision, manifest):
+    case, g = manifest[name], load_golden(name)
+    m = pk.DenoiseRatePredictor()
+    m.load_state_dict(synth.asdqe_state_dict(seed=case["seed"]), strict=False)
+    m = m.to(DEV).eval().set_precision(precision)
+    with torch.no_grad():
+        score, feat = m.forward_with_features(g["lq"].to(DEV), g["gt"].to(DEV))
+        score2 = m(g["lq"].to(DEV), g["gt"].to(DEV))
+    score, feat = score.cpu(), feat.cpu()
+    es = (score - g["score"]).abs().max().item()
+    ef = (feat - g["feat"]).abs().max().item()
+    rel = ef / g["feat"].abs().max().item()
+    print(f"{name} {precision}: score max|d|={es:.3e}; trunk feature max|d|={ef:.3e} (rel {rel:.3e})")
+    assert score.shape == g["score"].shape and torch.equal(score2.cpu(), score)
+    if precision == "fp32":
+        assert es <= 1e-3 and ef <= 1e-3 * max(1.0, g["feat"].abs().max().item())
+    else:
+        assert es <= 1e-2 and rel <= 5e-2

@@ -1,0 +1,114 @@
+"""CPU: host-side mirror of the reference interface + the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import pytest
+import torch
+
+import rethink_acoustic_image_enhancement_b200 as pk
+from rethink_acoustic_image_enhancement_b200 import _lib
+from oracle import synth
+from conftest import ROOT
+
+
+def test_header_symbols_are_all_exported_and_bound(lib):
+    hdr = open(os.path.join(ROOT, "include", "kdlae_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(kdlae_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libkdlae_b200.so"
+    assert lib.kdlae_abi_version() == 1
+
+
+def test_teacher_state_dict_layout_matches_reference_layout():
+    # oracle.synth's key order/shape is asserted equal to the reference's by oracle/make_golden.py
+    for kw in (dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train"),
+               dict(inp_channels=3, out_channels=3, LayerNorm_type="WithBias", static="train"),
+               dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no")):
+        m = pk.KDLAE_teacher(**kw)
+        sd = synth.teacher_state_dict(**kw)
+        msd = m.state_dict()
+        assert list(msd.keys()) == list(sd.keys())
+        assert all(msd[k].shape == sd[k].shape for k in sd)
+        m.load_state_dict(sd, strict=True)
+        assert _lib.load().kdlae_teacher_num_tensors(m._cfg) == len(sd)
+    assert len(pk.KDLAE_teacher(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree").state_dict()) == 483
+    assert sum(p.numel() for p in pk.KDLAE_teacher(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree").parameters()) == 26874300
+
+
+def test_restormer_alias_and_attributes():
+    assert pk.RestormerSuperResolutionParam2 is pk.KDLAE_teacher
+    m = pk.KDLAE_teacher(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree")
+    for attr in ("static", "patch_embed", "cen", "upen", "enhance", "outputen", "params"):  # Train/basicsr/train.py:33-49
+        assert hasattr(m, attr)
+    assert all(isinstance(p, torch.nn.Parameter) for p in m.parameters())
+    m.eval(); m.train()
+
+
+def test_student_and_asdqe_state_dict_layout():
+    s = pk.KDLAE_student(residual=True)
+    ss = synth.student_state_dict()
+    assert list(s.state_dict().keys()) == list(ss.keys()) and len(ss) == 26
+    assert all(s.state_dict()[k].shape == ss[k].shape for k in ss)
+    assert sum(p.numel() for p in s.parameters()) == 294449
+    a = pk.DenoiseRatePredictor()
+    sa = synth.asdqe_state_dict()
+    assert list(a.state_dict().keys()) == list(sa.keys()) and len(sa) == 148
+    assert all(a.state_dict()[k].shape == sa[k].shape for k in sa)
+    a.load_state_dict(sa, strict=False)
+    assert float(pk.DenoiseRatePredictor().regressor[-1].bias.abs().sum()) == 0.0  # ASDQE_model.py:156
+
+
+def test_define_network_shim_exports_the_reference_class_names():
+    from rethink_acoustic_image_enhancement_b200.archs import kdlae_b200_arch as arch
+    opt = dict(type="RestormerSuperResolutionParam2", inp_channels=1, out_channels=1, dim=48, num_blocks=[4, 6, 6, 8],
+               num_refinement_blocks=4, heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="BiasFree",
+               dual_pixel_task=False, static="train", params="cat")
+    cls = getattr(arch, opt.pop("type"))  # what basicsr's dynamic_instantiation does
+    assert isinstance(cls(**opt), pk.KDLAE_teacher)
+    assert arch.KDLAE_student is pk.KDLAE_student
+
+
+def test_no_cpu_fallback_and_argument_errors():
+    m = pk.KDLAE_teacher(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m({"img": torch.zeros(1, 1, 64, 64), "denoise_rate": torch.zeros(1, 1, 64, 64)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pk.KDLAE_student()(torch.zeros(1, 5, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pk.DenoiseRatePredictor()(torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 16, 16))
+    with pytest.raises(NotImplementedError):
+        pk.KDLAE_teacher(bias=True)
+    with pytest.raises(NotImplementedError):
+        pk.KDLAE_teacher(dual_pixel_task=True)
+    with pytest.raises(ValueError):
+        m.set_precision("fp8")
+
+
+def test_size_queries_scale_and_reject_bad_shapes(lib):
+    m = pk.KDLAE_teacher(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree")
+    for prec in (0, 1):
+        one = lib.kdlae_teacher_workspace_bytes(m._cfg, 1, 64, 64, prec)
+        two = lib.kdlae_teacher_workspace_bytes(m._cfg, 2, 64, 64, prec)
+        assert 0 < one < two <= 2 * one + 4096
+        assert lib.kdlae_teacher_packed_bytes(m._cfg, prec) > 26874300 * (2 if prec else 4)
+    assert lib.kdlae_teacher_workspace_bytes(m._cfg, 1, 4, 4, 1) == 0
+    # forward argument validation happens before any CUDA call, so it is testable without a GPU
+    import ctypes as C
+    buf = C.create_string_buffer(64)
+    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, buf, buf, 1, 36, 64, 1, buf, 64, 1, None)
+    assert st != 0 and b"multiples of 8" in lib.kdlae_last_error()
+    s = pk.KDLAE_student()
+    st = lib.kdlae_student_forward(s._cfg, buf, buf, buf, 1, 5, 18, 16, 1, buf, 64, 1, None)
+    assert st != 0 and b"multiples of 4" in lib.kdlae_last_error()
+    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, buf, buf, 1, 64, 64, 1, buf, 64, 7, None)
+    assert st != 0 and b"precision" in lib.kdlae_last_error()
+
+
+def test_device_check_fails_cleanly_without_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.kdlae_device_check(0) != 0
+    assert len(lib.kdlae_last_error()) > 0
