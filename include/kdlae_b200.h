@@ -34,6 +34,15 @@ int kdlae_device_check(int device);
 /* number of kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
 unsigned long long kdlae_launch_count(void);
 
+/* ---- per-kernel-class profiler (CUDA events on the launching stream; used by bench.py's roofline) ------ */
+int kdlae_profile_num_classes(void);
+const char* kdlae_profile_class_name(int cls);
+/* start recording one cudaEvent pair around every kernel launched by this library (adds a few us per launch) */
+int kdlae_profile_begin(void);
+/* stop, synchronise the device and return per class: summed kernel milliseconds, algorithmic FLOPs, algorithmic
+ * bytes (inputs + outputs + weights of each launch) and the launch count. Arrays have kdlae_profile_num_classes() entries. */
+int kdlae_profile_end(int n_classes, double* ms, double* flops, double* bytes, long long* launches);
+
 /* ---- KDLAE-T : KDLAE_teacher (KDLAE/KDLAE_model.py:204-336), alias RestormerSuperResolutionParam2 ------ */
 typedef struct kdlae_teacher_cfg {
   int inp_channels;          /* KDLAE_model.py:206 */

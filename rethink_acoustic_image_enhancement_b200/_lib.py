@@ -41,6 +41,11 @@ SIGNATURES = {
     "kdlae_last_error": (C.c_char_p, []),
     "kdlae_device_check": (C.c_int, [C.c_int]),
     "kdlae_launch_count": (C.c_ulonglong, []),
+    "kdlae_profile_num_classes": (C.c_int, []),
+    "kdlae_profile_class_name": (C.c_char_p, [C.c_int]),
+    "kdlae_profile_begin": (C.c_int, []),
+    "kdlae_profile_end": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_longlong)]),
     "kdlae_teacher_num_tensors": (C.c_int, [C.POINTER(TeacherCfg)]),
     "kdlae_teacher_packed_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int]),
     "kdlae_teacher_pack": (C.c_int, [C.POINTER(TeacherCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
@@ -95,3 +100,21 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().kdlae_launch_count())
+
+
+def profile_begin() -> None:
+    check(load().kdlae_profile_begin(), "kdlae_profile_begin")
+
+
+def profile_end() -> dict:
+    """{class name: dict(ms, flops, bytes, launches)} for every kernel class that launched since profile_begin()."""
+    lib = load()
+    n = lib.kdlae_profile_num_classes()
+    ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+    ln = (C.c_longlong * n)()
+    check(lib.kdlae_profile_end(n, ms, fl, by, ln), "kdlae_profile_end")
+    out = {}
+    for i in range(n):
+        if ln[i]:
+            out[lib.kdlae_profile_class_name(i).decode()] = dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(ln[i]))
+    return out

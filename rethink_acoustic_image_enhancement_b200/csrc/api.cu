@@ -1,4 +1,5 @@
 // extern "C" boundary (include/kdlae_b200.h): argument checking, precision dispatch, error text.
+#include <vector>
 #include "models.cuh"
 
 namespace kd {
@@ -13,6 +14,36 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// ---- profiler ----------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static size_t g_pool_used = 0;
+static const char* kProfNames[PC_COUNT] = {"conv_gemm_tcgen05", "conv_gemm_simt", "dwconv3x3", "ln_stats", "mdta_gram",
+                                           "mdta_softmax_fold", "small_channel_conv", "pool_resample", "gap_mlp_head"};
+
+static cudaEvent_t prof_event() {
+  if (g_pool_used == g_event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_event_pool.push_back(e);
+  }
+  return g_event_pool[g_pool_used++];
+}
+ProfScope::ProfScope(int cls, cudaStream_t s, double flops, double bytes) : stream(s) {
+  if (!g_prof_on) return;
+  active = true;
+  ProfRec r;
+  r.a = prof_event(); r.b = prof_event(); r.cls = cls; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.a, s);
+  slot = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (active) cudaEventRecord(g_recs[slot].b, stream);
+}
 
 }  // namespace kd
 
@@ -41,6 +72,32 @@ int kdlae_device_check(int device) {
   KD_CUDA(cudaGetDeviceProperties(&prop, device));
   KD_CHECK(prop.major == 10, "device %d (%s, sm_%d%d) is not an sm_100 (B200) GPU; this library only carries sm_100a code",
            device, prop.name, prop.major, prop.minor);
+  return 0;
+}
+
+// ---------------- profiler ----------------
+int kdlae_profile_num_classes(void) { return kd::PC_COUNT; }
+const char* kdlae_profile_class_name(int cls) { return (cls >= 0 && cls < kd::PC_COUNT) ? kd::kProfNames[cls] : ""; }
+int kdlae_profile_begin(void) {
+  API_BEGIN();
+  kd::g_recs.clear();
+  kd::g_pool_used = 0;
+  kd::g_prof_on = true;
+  return 0;
+}
+int kdlae_profile_end(int n_classes, double* ms, double* flops, double* bytes, long long* launches) {
+  API_BEGIN();
+  kd::g_prof_on = false;
+  KD_CHECK(n_classes == kd::PC_COUNT && ms && flops && bytes && launches, "kdlae_profile_end: bad arguments");
+  for (int i = 0; i < kd::PC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  KD_CUDA(cudaDeviceSynchronize());
+  for (const auto& r : kd::g_recs) {
+    float t = 0.f;
+    KD_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+  }
+  kd::g_recs.clear();
+  kd::g_pool_used = 0;
   return 0;
 }
 

@@ -45,6 +45,19 @@ const char* get_error();
 extern unsigned long long g_launch_count;
 inline void count_launch() { ++g_launch_count; }
 
+// ---- optional per-kernel-class CUDA-event profiler (bench.py roofline; off by default) ----------
+enum ProfClass {
+  PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_DWCONV, PC_LN_STATS, PC_MDTA_GRAM, PC_MDTA_FOLD, PC_SMALL_CONV, PC_POOL_RESAMPLE, PC_HEAD,
+  PC_COUNT
+};
+struct ProfScope {
+  bool active = false;
+  int slot = -1;
+  cudaStream_t stream;
+  ProfScope(int cls, cudaStream_t s, double flops, double bytes);
+  ~ProfScope();
+};
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

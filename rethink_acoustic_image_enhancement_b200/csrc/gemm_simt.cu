@@ -125,6 +125,8 @@ int conv_gemm_simt(const ConvOp& op, cudaStream_t s) {
   if (op.epi.mode == OUT_PIXEL_SHUFFLE) KD_CHECK(op.epi.cq % 8 == 0 && op.epi.N == 4 * op.epi.cq, "pixel-shuffle needs cq%%8==0");
   dim3 grid(cdiv(p.rows_per_group, BM), cdiv(op.epi.N, BN), op.groups);
   KD_CHECK(grid.y <= 65535 && grid.z <= 65535, "conv_gemm_simt: grid too large");
+  ProfScope prof(PC_GEMM_SIMT, s, 2.0 * rows * op.epi.N * p.ktot,
+                 sizeof(T) * ((double)rows * (p.ctot + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * p.ktot));
   k_conv_gemm_simt<T><<<grid, NT, 0, s>>>(p);
   count_launch();
   KD_LAUNCH_CHECK();

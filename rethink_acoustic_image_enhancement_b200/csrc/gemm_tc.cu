@@ -435,6 +435,9 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   }
   p.items = tiles_m * p.n_chunks;
   const int grid = (int)(p.items < (long)g_num_sms ? p.items : (long)g_num_sms);
+  const double ktot = (double)p.taps * (op.c0 + op.c1);
+  ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * op.epi.N * ktot,
+                 2.0 * ((double)rows * (op.c0 + op.c1 + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * ktot));
   k_conv_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
   count_launch();
   KD_LAUNCH_CHECK();

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) k_ln_stats(const T* __restrict__ x, long 
 template <typename T>
 int ln_stats(const T* x, long ld, int C, long rows, float* rstd, float* mu, cudaStream_t s) {
   KD_CHECK(C % 8 == 0 && ld % 8 == 0, "ln_stats: C=%d ld=%ld must be multiples of 8", C, ld);
+  ProfScope prof(PC_LN_STATS, s, 4.0 * rows * C, (double)rows * (C * sizeof(T) + 4.0 * (mu ? 2 : 1)));
   k_ln_stats<T><<<cdiv(rows, 256), 256, 0, s>>>(x, ld, C, rows, rstd, mu);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -126,6 +127,7 @@ int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const fl
               int gate, cudaStream_t s) {
   KD_CHECK(C % (gate ? 16 : 8) == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dwconv3x3: C=%d ldx=%ld ldo=%ld alignment", C, ldx, ldo);
   const long total = (long)nimg * H * ((W + 3) / 4) * ((gate ? C / 2 : C) / 8);
+  ProfScope prof(PC_DWCONV, s, 18.0 * nimg * H * W * C, (double)nimg * H * W * (C + (gate ? C / 2 : C)) * sizeof(T) + 36.0 * C);
   if (gate) k_dwconv3x3<T, 1><<<cdiv(total, 128), 128, 0, s>>>(x, ldx, out, ldo, w9c, bias, nimg, H, W, C);
   else k_dwconv3x3<T, 0><<<cdiv(total, 128), 128, 0, s>>>(x, ldx, out, ldo, w9c, bias, nimg, H, W, C);
   count_launch();
@@ -236,6 +238,8 @@ int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int spli
     attr = true;
   }
   dim3 grid(splits, heads, nimg);
+  ProfScope prof(PC_MDTA_GRAM, s, 2.0 * nimg * HW * C * ch + 4.0 * nimg * HW * C,
+                 (double)nimg * HW * 2 * C * sizeof(T) + 4.0 * nimg * heads * splits * (ch * ch + 2 * ch));
   k_mdta_gram<T><<<grid, 256, smem, s>>>(qk, ld, HW, C, heads, splits, part);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -301,6 +305,7 @@ int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const f
     KD_CUDA(cudaFuncSetAttribute(k_mdta_fold<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
+  ProfScope prof(PC_MDTA_FOLD, s, 2.0 * nimg * C * C * ch, 4.0 * nimg * heads * splits * (ch * ch + 2 * ch) + (double)nimg * C * C * (4 + sizeof(T)));
   k_mdta_fold<T><<<dim3(heads, nimg), 256, smem, s>>>(part, C, heads, splits, temperature, wproj, mb, mb_ld, mb_img_stride);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -373,6 +378,9 @@ template <typename T>
 int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
   const long total = (long)op.nimg * op.H * op.W * (op.cout / 8);
+  const double fi_pix = (double)op.nimg * op.H * op.W;
+  ProfScope prof(PC_SMALL_CONV, s, 2.0 * fi_pix * op.cout * (op.cin0 + op.cin1) * 9 * op.kd,
+                 fi_pix * (4.0 * (op.cin0 + op.cin1) * (op.sub0 ? 2 : 1) + (double)op.cout * sizeof(T)));
   k_conv_few_in<T><<<cdiv(total, 128), 128, 0, s>>>(op, Hin, Win);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -437,6 +445,8 @@ int conv_few_out(const SmallConvOut& op, cudaStream_t s) {
   const size_t smem = sizeof(float) * (size_t)op.cout * op.k * op.k * op.cin;
   KD_CHECK(smem <= 48 * 1024, "conv_few_out: weights do not fit shared memory");
   const long total = (long)op.nimg * op.H * op.W;
+  ProfScope prof(PC_SMALL_CONV, s, 2.0 * total * op.cout * op.cin * op.k * op.k,
+                 (double)total * (op.cin * sizeof(T) + 4.0 * op.cout * (op.res ? 2 : 1)));
   k_conv_few_out<T><<<cdiv(total, 128), 128, smem, s>>>(op);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -476,6 +486,7 @@ template <typename T>
 int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s) {
   KD_CHECK(C % 8 == 0, "maxpool2x2: C=%d", C);
   const long total = (long)nimg * (H / 2) * (W / 2) * (C / 8);
+  ProfScope prof(PC_POOL_RESAMPLE, s, 0.0, (double)nimg * H * W * C * sizeof(T) * 1.25);
   k_maxpool2x2<T><<<cdiv(total, 256), 256, 0, s>>>(x, out, nimg, H, W, C);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -517,6 +528,7 @@ template <typename T>
 int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s) {
   KD_CHECK(C % 8 == 0, "upsample: C=%d", C);
   const long total = (long)nimg * OH * OW * (C / 8);
+  ProfScope prof(PC_POOL_RESAMPLE, s, 0.0, (double)nimg * C * sizeof(T) * ((double)H * W + (double)OH * OW));
   k_upsample2x<T><<<cdiv(total, 256), 256, 0, s>>>(x, out, nimg, H, W, C, OH, OW);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -582,6 +594,7 @@ int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* w1, const 
                  const float* w3, const float* b3, float* score, float* scratch, cudaStream_t s) {
   KD_CHECK(C <= 64, "gap_mlp_tanh: C=%d > 64", C);
   const int chunks = 64;
+  ProfScope prof(PC_HEAD, s, 0.0, (double)nimg * HW * C * sizeof(T));
   k_gap_partial<T><<<dim3(chunks, nimg), 256, 0, s>>>(feat, HW, C, chunks, scratch);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -607,6 +620,7 @@ __global__ void __launch_bounds__(256) k_nhwc_to_planar(const T* __restrict__ x,
 template <typename T>
 int nhwc_to_planar(const T* x, long ld, float* out, int nimg, int HW, int C, cudaStream_t s) {
   const long total = (long)nimg * HW * C;
+  ProfScope prof(PC_HEAD, s, 0.0, (double)total * (sizeof(T) + 4.0));
   k_nhwc_to_planar<T><<<cdiv(total, 256), 256, 0, s>>>(x, ld, out, HW, C, total);
   count_launch();
   KD_LAUNCH_CHECK();

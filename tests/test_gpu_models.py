@@ -96,7 +96,7 @@ def test_teacher_repack_after_weight_update():
 
 def test_teacher_rejects_bad_sizes():
     m = _teacher(dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no"), 0, 1.0, "bf16")
-    with pytest.raises(RuntimeError, match="multiples of 8"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 8"):
         m({"img": torch.rand(1, 1, 36, 64, device=DEV), "denoise_rate": torch.rand(1, 1, 36, 64, device=DEV)})
 
 
@@ -122,9 +122,15 @@ def test_student_matches_reference_fixture(name, precision, manifest):
 
 
 def test_student_rejects_bad_sizes():
-    m = pk.KDLAE_student(residual=True).to(DEV)
-    with pytest.raises(RuntimeError, match="multiples of 4"):
+    m = pk.KDLAE_student(residual=True).to(DEV).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 4"):
         m(torch.rand(1, 5, 18, 16, device=DEV))
+
+
+def test_training_mode_forward_is_refused_loudly():
+    m = pk.KDLAE_student(residual=True).to(DEV).train()
+    with pytest.raises(NotImplementedError, match="no backward"):
+        m(torch.rand(1, 5, 16, 16, device=DEV))
 
 
 ASDQE = ["asdqe_48x40", "asdqe_32x32"]
