@@ -110,6 +110,12 @@ int kdlae_asdqe_forward(const kdlae_asdqe_cfg* cfg, const void* packed, const fl
  * `a`,`w`,`res`,`out` are bf16 (precision 1) or fp32 (precision 0); w is [N][kh*kw][C] K-major. */
 int kdlae_conv_gemm(const void* a, int C, const void* w, int N, int nimg, int H, int W, int ksize, const float* row_scale,
                     const float* col_bias, int relu, const void* res, void* out, int precision, int force_simt, void* stream);
+/* MDTA reductions over all pixels of each image (KDLAE_model.py:134-137): for every (image, head)
+ * gram[ch*ch + 2*ch] = { q k^T [ch][ch], |q_i|^2 [ch], |k_j|^2 [ch] }.  qk: [nimg*HW][ld] with q at channel 0 and k at
+ * channel C.  scratch: kdlae_mdta_gram_scratch_floats() floats. bf16 path = tcgen05 with MN-major operands. */
+size_t kdlae_mdta_gram_scratch_floats(int nimg, int HW, int C, int heads);
+int kdlae_mdta_gram(const void* qk, long ld, int nimg, int HW, int C, int heads, float* gram, float* scratch, int precision,
+                    void* stream);
 /* Per-pixel channel LayerNorm statistics (KDLAE_model.py:50-52,:67-70). x: [rows][C]. */
 int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int precision, void* stream);
 /* Depthwise 3x3 (+ optional GELU gate) (KDLAE_model.py:97,103-104,119). w9c fp32 [9][C]. */

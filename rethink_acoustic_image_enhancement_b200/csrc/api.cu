@@ -213,6 +213,38 @@ int kdlae_conv_gemm(const void* a, int C, const void* w, int N, int nimg, int H,
   return kd::conv_gemm_tc(g, s);
 }
 
+namespace kd {
+__global__ void k_sum_splits(const float* __restrict__ part, int splits, long psz, long total, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long g = i / psz, e = i % psz;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(g * splits + sp) * psz + e];
+  out[i] = s;
+}
+}  // namespace kd
+
+size_t kdlae_mdta_gram_scratch_floats(int nimg, int HW, int C, int heads) {
+  const int ch = heads > 0 ? C / heads : 0;
+  return (size_t)nimg * heads * kd::mdta_gram_splits(HW, nimg * heads) * ((size_t)ch * ch + 2 * ch);
+}
+
+int kdlae_mdta_gram(const void* qk, long ld, int nimg, int HW, int C, int heads, float* gram, float* scratch, int precision,
+                    void* stream) {
+  API_BEGIN();
+  KD_CHECK(qk && gram && scratch && heads > 0 && C % heads == 0, "kdlae_mdta_gram: bad argument");
+  CHECK_PREC(precision);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int splits = kd::mdta_gram_splits(HW, nimg * heads);
+  if (precision == KDLAE_PREC_BF16) KD_TRY(kd::mdta_gram<bf16>(reinterpret_cast<const bf16*>(qk), ld, nimg, HW, C, heads, splits, scratch, s));
+  else KD_TRY(kd::mdta_gram<float>(reinterpret_cast<const float*>(qk), ld, nimg, HW, C, heads, splits, scratch, s));
+  const int ch = C / heads;
+  const long psz = (long)ch * ch + 2 * ch, total = (long)nimg * heads * psz;
+  kd::k_sum_splits<<<kd::cdiv(total, 256), 256, 0, s>>>(scratch, splits, psz, total, gram);
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
 int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int precision, void* stream) {
   API_BEGIN();
   KD_CHECK(x && rstd, "kdlae_ln_stats: NULL argument");

@@ -14,8 +14,7 @@
 //   fused epilogue (LayerNorm row scale, bias, ReLU, residual, PixelShuffle/Unshuffle addressing).
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 //   allocator, warps 2..9 epilogue.  4-stage smem ring, mbarrier full/empty pipelines.
-#include <cuda.h>
-#include "ops.cuh"
+#include "sm100.cuh"
 
 namespace kd {
 
@@ -50,100 +49,11 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 200000000u) {
-      printf("kdlae gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
-// 8-row x 128-byte swizzle atoms, atoms stacked every 1024 bytes along M/N (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
-  return d;
-}
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------
+// FAST = 1: identity addressing, N % 8 == 0, 16-byte aligned out/residual rows, no WithBias terms (the hot 1x1 /
+// 3x3 shapes); FAST = 0: generic epilogue_store8 (PixelShuffle/Unshuffle, ragged N, WithBias LayerNorm).
+template <int FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -272,22 +182,82 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         valid = rr < p.rows_per_group;
         prow = (long)g * p.rows_per_group + rr;
       }
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + acc * TC_NC_MAX + ((uint32_t)(quarter * 32) << 16);
       const int ngroups = (p.nc + 31) / 32;
-      for (int cgp = half; cgp < ngroups; cgp += 2) {
-        uint32_t v[32];
-        tmem_ld32(t_row + cgp * 32, v);
-        if (valid) {
+      const int nbase = nchunk * p.nc;
+      if (FAST) {
+        // per-row scalars and the first residual vectors are fetched while the MMAs of this tile still run
+        const float rs = (valid && p.epi.row_scale) ? __ldg(p.epi.row_scale + prow) : 1.0f;
+        const bf16* resp = reinterpret_cast<const bf16*>(p.epi.res);
+        const bf16* rrow = resp ? resp + prow * p.epi.res_ld + nbase : nullptr;
+        bf16* orow = reinterpret_cast<bf16*>(p.epi.out) + prow * p.epi.out_ld + p.epi.out_coff + nbase;
+        uint4 rv[4];
+        auto fetch_res = [&](int cgp) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = cgp * 32 + j * 8;
-            if (col < p.nc) {
-              float f[8];
+            rv[j] = make_uint4(0, 0, 0, 0);
+            if (valid && rrow && col < p.nc && nbase + col < p.epi.N) rv[j] = __ldg(reinterpret_cast<const uint4*>(rrow + col));
+          }
+        };
+        if (half < ngroups) fetch_res(half);
+        mbar_wait(tfull_bar(acc), aph);
+        tc_fence_after();
+        for (int cgp = half; cgp < ngroups; cgp += 2) {
+          uint32_t v[32];
+          tmem_ld32_issue(t_row + cgp * 32, v);
+          uint4 rc[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
-              epilogue_store8<bf16>(p.epi, prow, img, y, x, nchunk * p.nc + col, f);
+          for (int j = 0; j < 4; ++j) rc[j] = rv[j];
+          if (cgp + 2 < ngroups) fetch_res(cgp + 2);     // next group's residual in flight during this group's math
+          tmem_ld32_wait(v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = cgp * 32 + j * 8;
+              const int n = nbase + col;
+              if (col < p.nc && n < p.epi.N) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) * rs;
+                if (p.epi.col_bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n + 4));
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (rrow) {
+                  const uint32_t w4[4] = {rc[j].x, rc[j].y, rc[j].z, rc[j].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    f[2 * i] += __uint_as_float(w4[i] << 16);
+                    f[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
+                  }
+                }
+                if (p.epi.relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                store8<bf16>(orow + col, f);
+              }
+            }
+          }
+        }
+      } else {
+        mbar_wait(tfull_bar(acc), aph);
+        tc_fence_after();
+        for (int cgp = half; cgp < ngroups; cgp += 2) {
+          uint32_t v[32];
+          tmem_ld32(t_row + cgp * 32, v);
+          if (valid) {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              const int col = cgp * 32 + j * 8;
+              if (col < p.nc) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
+                epilogue_store8<bf16>(p.epi, prow, img, y, x, nbase + col, f);
+              }
             }
           }
         }
@@ -309,35 +279,6 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // ---------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
-  EncodeTiledFn fn = get_encode_fn();
-  KD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  KD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)", (int)r, rank,
-           (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0));
-  return 0;
-}
-
 int pick_nc(int N, int* n_chunks) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= TC_NC_MAX) { *n_chunks = 1; return n16; }
@@ -370,7 +311,8 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    KD_CUDA(cudaFuncSetAttribute(k_conv_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    KD_CUDA(cudaFuncSetAttribute(k_conv_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    KD_CUDA(cudaFuncSetAttribute(k_conv_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -438,7 +380,13 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   const double ktot = (double)p.taps * (op.c0 + op.c1);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * op.epi.N * ktot,
                  2.0 * ((double)rows * (op.c0 + op.c1 + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * ktot));
-  k_conv_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
+  const Epilogue& e = op.epi;
+  const bool fast = e.mode == OUT_IDENTITY && e.N % 8 == 0 && e.row_mu == nullptr && e.out_ld % 8 == 0 && e.out_coff % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+                    (e.res == nullptr || (e.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(e.res) & 15) == 0)) &&
+                    (e.col_bias == nullptr || (reinterpret_cast<uintptr_t>(e.col_bias) & 15) == 0);
+  if (fast) k_conv_gemm_tc<1><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
+  else k_conv_gemm_tc<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -1,6 +1,7 @@
 // Memory-bound glue kernels (NHWC, vectorised 8 channels per access, fp32 math):
 // LayerNorm statistics, depthwise 3x3 (+GELU gate), MDTA Gram/norm reduction and softmax fold,
 // tiny-channel direct convolutions, pooling, bilinear up-sampling, GAP+MLP head, layout conversion.
+#include <type_traits>
 #include "ops.cuh"
 
 namespace kd {
@@ -122,9 +123,16 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const T* __restrict__ x, long
   }
 }
 
+int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
+                  cudaStream_t s);
+
 template <typename T>
 int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias, int nimg, int H, int W, int C,
               int gate, cudaStream_t s) {
+  if (std::is_same<T, bf16>::value && bias == nullptr) {   // TMA-staged tile kernel (bf16 throughput path)
+    const int r = dwconv3x3_tma(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, w9c, nimg, H, W, C, gate, s);
+    if (r >= 0) return r;
+  }
   KD_CHECK(C % (gate ? 16 : 8) == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dwconv3x3: C=%d ldx=%ld ldo=%ld alignment", C, ldx, ldo);
   const long total = (long)nimg * H * ((W + 3) / 4) * ((gate ? C / 2 : C) / 8);
   ProfScope prof(PC_DWCONV, s, 18.0 * nimg * H * W * C, (double)nimg * H * W * (C + (gate ? C / 2 : C)) * sizeof(T) + 36.0 * C);
@@ -221,14 +229,22 @@ __global__ void __launch_bounds__(256) k_mdta_gram(const T* __restrict__ qk, lon
   if (tid < 2 * ch) dst[ch * ch + tid] = nrm;
 }
 
-int mdta_gram_splits(int HW) {
-  int s = HW / 1024;
-  return s < 1 ? 1 : (s > 256 ? 256 : s);
+// Pixel splits per (image, head).  Depends on the image size only, so the reduction order - and therefore the
+// result - of an image does not depend on the batch or micro-batch it is processed in.
+int mdta_gram_splits(int HW, int /*nimg_heads*/) {
+  int s = HW / 2048;
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
+
+int mdta_gram_tc(const bf16* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s);
 
 template <typename T>
 int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s) {
   const int ch = C / heads;
+  if (std::is_same<T, bf16>::value) {   // tcgen05 Gram (MN-major operands straight from the dwconv output)
+    const int r = mdta_gram_tc(reinterpret_cast<const bf16*>(qk), ld, nimg, HW, C, heads, splits, part, s);
+    if (r >= 0) return r;
+  }
   KD_CHECK(C % heads == 0 && ch % 8 == 0 && ch <= 128 && 2 * ch <= 256, "mdta_gram: unsupported channels/head %d", ch);
   const size_t smem = sizeof(float) * (size_t)max(2 * GRAM_PT * ch, ch * ch);
   static bool attr_f = false, attr_b = false;

@@ -39,7 +39,7 @@ template <typename T> int dwconv3x3(const T* x, long ldx, T* out, long ldo, cons
 // MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
 // qk: [nimg*HW, ld] with q at channel 0 and k at channel C.  part: [nimg][heads][splits][ch*ch + 2*ch] fp32
 template <typename T> int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s);
-int mdta_gram_splits(int HW);
+int mdta_gram_splits(int HW, int nimg_heads);
 // softmax(normalised Gram * temperature) folded into project_out: Mb[img][n][head*ch + j] = sum_i Wp[n][head*ch+i]*attn[i][j]
 template <typename T> int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const float* temperature,
                                     const float* wproj /*[C][C] fp32*/, T* mb, long mb_ld, long mb_img_stride, cudaStream_t s);

@@ -166,7 +166,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
   KD_TRY(conv_gemm<T>(g, s));
   KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s));
-  const int splits = mdta_gram_splits(HW);
+  const int splits = mdta_gram_splits(HW, nimg * w.heads);
   KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
   KD_TRY(mdta_fold<T>(sc.gram, nimg, C, w.heads, splits, w.temp, w.wproj, sc.mb, C, (long)C * C, s));
   g = ConvOp();
@@ -253,7 +253,7 @@ WsLayout ws_layout(const kdlae_teacher_cfg& c, int mb, int H, int W) {
   size_t gmax = 0;
   auto gr = [&](size_t hw, size_t C, size_t heads) {
     const size_t ch = C / heads;
-    gmax = std::max(gmax, (size_t)mb * heads * mdta_gram_splits((int)hw) * (ch * ch + 2 * ch));
+    gmax = std::max(gmax, (size_t)mb * heads * mdta_gram_splits((int)hw, 1) * (ch * ch + 2 * ch));
   };
   const size_t HW = (size_t)H * W;
   gr(HW, d, c.heads[0]); gr(HW / 4, 2 * d, c.heads[1]); gr(HW / 16, 4 * d, c.heads[2]); gr(HW / 64, 8 * d, c.heads[3]);

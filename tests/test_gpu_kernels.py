@@ -120,3 +120,48 @@ def test_dwconv3x3(lib, prec, dtype, tol, gate):
         y = F.gelu(y[:, :Co]) * y[:, Co:]
     ref = y.permute(0, 2, 3, 1)
     assert (out.double().cpu() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 72, 144, 0), (2, 16, 33, 288, 0), (1, 24, 64, 256, 1), (1, 8, 8, 1024, 1), (3, 9, 5, 48, 0)])
+def test_dwconv3x3_bf16_tma_tiles(lib, shape):
+    """TMA-staged tile kernel: several tiles, ragged edges, partial 64-channel blocks, gate halves."""
+    n, H, W, C, gate = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, H, W, C, generator=g).to(DEV).bfloat16()
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    w9c = w.view(C, 9).t().contiguous().to(DEV)
+    Co = C // 2 if gate else C
+    out = torch.full((n, H, W, Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.kdlae_dwconv3x3(x.data_ptr(), out.data_ptr(), w9c.data_ptr(), n, H, W, C, gate, 1, _stream()), "dwconv")
+    torch.cuda.synchronize()
+    y = F.conv2d(x.double().cpu().permute(0, 3, 1, 2), w.double(), padding=1, groups=C)
+    if gate:
+        y = F.gelu(y[:, :Co]) * y[:, Co:]
+    ref = y.permute(0, 2, 3, 1)
+    assert torch.isfinite(out).all()
+    assert (out.double().cpu() - ref).abs().max().item() < 1.2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("prec,dtype", [(0, torch.float32), (1, torch.bfloat16)])
+@pytest.mark.parametrize("shape", [(2, 64 * 64, 48, 1), (1, 48 * 40, 96, 2), (1, 4096 + 64, 96, 1), (2, 30 * 30, 384, 8)])
+def test_mdta_gram(lib, prec, dtype, shape):
+    """q k^T and squared norms over all pixels; bf16 = tcgen05 MN-major kernel, fp32 = CUDA-core kernel."""
+    nimg, HW, C, heads = shape
+    ch = C // heads
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(nimg, HW, 3 * C, generator=g).to(DEV).to(dtype)
+    psz = ch * ch + 2 * ch
+    gram = torch.empty(nimg, heads, psz, device=DEV)
+    scratch = torch.empty(lib.kdlae_mdta_gram_scratch_floats(nimg, HW, C, heads), device=DEV)
+    _lib.check(lib.kdlae_mdta_gram(qkv.data_ptr(), 3 * C, nimg, HW, C, heads, gram.data_ptr(), scratch.data_ptr(), prec, _stream()),
+               "mdta_gram")
+    torch.cuda.synchronize()
+    x = qkv.double().cpu()
+    q = x[..., :C].view(nimg, HW, heads, ch).permute(0, 2, 3, 1)          # [n, h, ch, HW]
+    k = x[..., C:2 * C].view(nimg, HW, heads, ch).permute(0, 2, 3, 1)
+    G = q @ k.transpose(-1, -2)
+    got = gram.double().cpu()
+    tol = 1e-4 * HW ** 0.5 if prec == 0 else 1e-3 * HW ** 0.5
+    assert (got[..., :ch * ch].view(nimg, heads, ch, ch) - G).abs().max().item() < tol
+    assert (got[..., ch * ch:ch * ch + ch] - (q * q).sum(-1)).abs().max().item() < tol * 4
+    assert (got[..., ch * ch + ch:] - (k * k).sum(-1)).abs().max().item() < tol * 4
