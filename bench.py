@@ -184,12 +184,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from rethink_acoustic_image_enhancement_b200.sharding import max_over_ranks as _mor
+
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _mor(ms, dev)
 
     def step_device():
         with torch.no_grad():

@@ -10,10 +10,15 @@
 // * W tiles ([n-chunk <= 256] x 64, K-major) come from a 3-D map (k, n, group); group = image for
 //   the per-image attention matrices (MDTA folded into project_out).
 // * One elected thread issues tcgen05.mma (M=128, N=n-chunk, K=16) into one of two TMEM accumulator
-//   buffers (2 x 256 columns); 8 epilogue warps drain the other buffer with tcgen05.ld and apply the
-//   fused epilogue (LayerNorm row scale, bias, ReLU, residual, PixelShuffle/Unshuffle addressing).
+//   buffers (2 x 256 columns); 8 epilogue warps drain the other buffer with tcgen05.ld.
+// * FAST epilogue (identity addressing: every 1x1 and the ASDQE 3x3 convs): the output tile leaves through a
+//   ring of four 128 x 64 bf16 shared-memory slabs (128B swizzle) and TMA bulk stores, and the residual tile
+//   arrives in the same slab by TMA load and is updated in place - so every byte that crosses HBM moves in
+//   full 128-byte lines and the epilogue warps never form a global address.
+//   Generic epilogue (PixelShuffle / PixelUnshuffle scatter, ragged N, WithBias LayerNorm): direct stores.
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM
-//   allocator, warps 2..9 epilogue.  4-stage smem ring, mbarrier full/empty pipelines.
+//   allocator, warps 2..9 epilogue, warp 10 residual-slab producer, warp 11 slab store issuer.
+//   mbarrier pipelines: smem ring full/empty, TMEM full/empty, slab full/empty (+ named barriers per slab).
 #include "sm100.cuh"
 
 namespace kd {
@@ -23,14 +28,17 @@ namespace {
 constexpr int TC_BM = 128;         // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;          // K elements per stage (one 128B swizzle atom of bf16)
 constexpr int TC_NC_MAX = 256;     // max N per accumulator (UMMA N)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;
+constexpr int TC_NSLAB = 4;        // output slabs of 128 rows x 64 columns
 constexpr int TC_TW = 16, TC_TH = 8;   // spatial tile of the 3x3 path
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS + 2) * 32;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_NC_MAX * TC_BK * 2;
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_SLAB_BYTES = TC_BM * 64 * 2;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_STORE_BAR_THREADS = TC_EPI_WARPS * 32 + 32;
 
 struct TcParams {
   int spatial;          // 0: linear rows (1x1), 1: 16x8 patches with 3x3 taps
@@ -45,29 +53,66 @@ struct TcParams {
   int tiles_per_group;
   // spatial mode
   int H, W, tiles_x, tiles_y;
+  int has_res;
   Epilogue epi;
 };
+
+struct TileCoord { int g, r0, tx0, ty0, img, nchunk; };
+
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long item) {
+  TileCoord t;
+  const long mt = item / p.n_chunks;
+  t.nchunk = (int)(item % p.n_chunks);
+  t.g = 0; t.r0 = 0; t.tx0 = 0; t.ty0 = 0; t.img = 0;
+  if (p.spatial) {
+    const int txi = (int)(mt % p.tiles_x);
+    const int tyi = (int)((mt / p.tiles_x) % p.tiles_y);
+    t.img = (int)(mt / ((long)p.tiles_x * p.tiles_y));
+    t.tx0 = txi * TC_TW; t.ty0 = tyi * TC_TH;
+  } else {
+    t.g = (int)(mt / p.tiles_per_group);
+    t.r0 = (int)(mt % p.tiles_per_group) * TC_BM;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------
-// FAST = 1: identity addressing, N % 8 == 0, 16-byte aligned out/residual rows, no WithBias terms (the hot 1x1 /
-// 3x3 shapes); FAST = 0: generic epilogue_store8 (PixelShuffle/Unshuffle, ragged N, WithBias LayerNorm).
 template <int FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+               const __grid_constant__ CUtensorMap map_res, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+  const uint32_t slab_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t bar_base = slab_base + TC_NSLAB * TC_SLAB_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + b); };
+  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + TC_NSLAB + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 2 * TC_NSLAB);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* slab_gen = smem_raw + (slab_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -75,8 +120,10 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     prefetch_tmap(&map_a0);
     if (p.kc1 > 0) prefetch_tmap(&map_a1);
     prefetch_tmap(&map_w);
+    if (FAST) { prefetch_tmap(&map_out); if (p.has_res) prefetch_tmap(&map_res); }
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    for (int b = 0; b < TC_NSLAB; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -91,24 +138,14 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int kchunks = p.kc0 + p.kc1;
   const int kblocks = p.taps * kchunks;
   const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.nc * TC_BK * 2;
+  const int nslabs = (p.nc + 63) / 64;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (A and W tiles) =====================
     if (lane == 0) {
       uint32_t kidx = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const long mt = item / p.n_chunks;
-        const int nchunk = (int)(item % p.n_chunks);
-        int g = 0, r0 = 0, tx0 = 0, ty0 = 0, img = 0;
-        if (p.spatial) {
-          const int txi = (int)(mt % p.tiles_x);
-          const int tyi = (int)((mt / p.tiles_x) % p.tiles_y);
-          img = (int)(mt / ((long)p.tiles_x * p.tiles_y));
-          tx0 = txi * TC_TW; ty0 = tyi * TC_TH;
-        } else {
-          g = (int)(mt / p.tiles_per_group);
-          r0 = (int)(mt % p.tiles_per_group) * TC_BM;
-        }
+        const TileCoord t = tile_coord(p, item);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dx = (tap % p.kw - p.kw / 2) * p.dil, dy = (tap / p.kw - p.kw / 2) * p.dil;
           for (int kc = 0; kc < kchunks; ++kc, ++kidx) {
@@ -121,10 +158,10 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const bool src1 = kc >= p.kc0;
             const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
             const int cc = (src1 ? kc - p.kc0 : kc) * TC_BK;
-            if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, tx0 + dx, ty0 + dy, img);
-            else tma_load_3d(a_dst, ma, full_bar(s), cc, r0, g);
+            if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, t.img);
+            else tma_load_3d(a_dst, ma, full_bar(s), cc, t.r0, t.g);
             const int wk = (int)(tap * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
-            tma_load_3d(b_dst, &map_w, full_bar(s), wk, nchunk * p.nc, g);
+            tma_load_3d(b_dst, &map_w, full_bar(s), wk, t.nchunk * p.nc, t.g);
           }
         }
       }
@@ -157,76 +194,60 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         umma_commit(tfull_bar(acc));      // accumulator complete
       }
     }
-  } else {
+  } else if (warp < 2 + TC_EPI_WARPS) {
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
-    const int half = ew >> 2;             // which half of the 32-column groups
+    const int half = ew >> 2;             // which 32-column half of a 64-column slab / which column groups
     const int r = quarter * 32 + lane;    // accumulator row (pixel within the tile)
-    uint32_t it = 0;
+    uint32_t it = 0, slab_ctr = 0;
     for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const long mt = item / p.n_chunks;
-      const int nchunk = (int)(item % p.n_chunks);
+      const TileCoord t = tile_coord(p, item);
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-      long prow; int img = 0, y = 0, x = 0; bool valid;
+      long prow; int y = 0, x = 0; bool valid;
       if (p.spatial) {
-        const int txi = (int)(mt % p.tiles_x);
-        const int tyi = (int)((mt / p.tiles_x) % p.tiles_y);
-        img = (int)(mt / ((long)p.tiles_x * p.tiles_y));
-        x = txi * TC_TW + (r % TC_TW); y = tyi * TC_TH + (r / TC_TW);
+        x = t.tx0 + (r % TC_TW); y = t.ty0 + (r / TC_TW);
         valid = (x < p.W) && (y < p.H);
-        prow = ((long)img * p.H + y) * p.W + x;
+        prow = ((long)t.img * p.H + y) * p.W + x;
       } else {
-        const int g = (int)(mt / p.tiles_per_group);
-        const long rr = (long)(mt % p.tiles_per_group) * TC_BM + r;
+        const long rr = (long)t.r0 + r;
         valid = rr < p.rows_per_group;
-        prow = (long)g * p.rows_per_group + rr;
+        prow = (long)t.g * p.rows_per_group + rr;
       }
       const uint32_t t_row = tmem_base + acc * TC_NC_MAX + ((uint32_t)(quarter * 32) << 16);
-      const int ngroups = (p.nc + 31) / 32;
-      const int nbase = nchunk * p.nc;
+      const int nbase = t.nchunk * p.nc;
       if (FAST) {
-        // per-row scalars and the first residual vectors are fetched while the MMAs of this tile still run
         const float rs = (valid && p.epi.row_scale) ? __ldg(p.epi.row_scale + prow) : 1.0f;
-        const bf16* resp = reinterpret_cast<const bf16*>(p.epi.res);
-        const bf16* rrow = resp ? resp + prow * p.epi.res_ld + nbase : nullptr;
-        bf16* orow = reinterpret_cast<bf16*>(p.epi.out) + prow * p.epi.out_ld + p.epi.out_coff + nbase;
-        uint4 rv[4];
-        auto fetch_res = [&](int cgp) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = cgp * 32 + j * 8;
-            rv[j] = make_uint4(0, 0, 0, 0);
-            if (valid && rrow && col < p.nc && nbase + col < p.epi.N) rv[j] = __ldg(reinterpret_cast<const uint4*>(rrow + col));
-          }
-        };
-        if (half < ngroups) fetch_res(half);
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
-        for (int cgp = half; cgp < ngroups; cgp += 2) {
-          uint32_t v[32];
-          tmem_ld32_issue(t_row + cgp * 32, v);
-          uint4 rc[4];
+        for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
+          const int b = slab_ctr % TC_NSLAB;
+          const uint32_t sph = (slab_ctr / TC_NSLAB) & 1;
+          // the slab holds the residual tile (TMA-loaded) or is simply free again (its last store has been read out)
+          if (p.has_res) mbar_wait(sfull_bar(b), sph);
+          else mbar_wait(sempty_bar(b), sph ^ 1);
+          const int col0 = j * 64 + half * 32;
+          if (col0 < p.nc) {
+            uint32_t v[32];
+            tmem_ld32(t_row + col0, v);
+            uint8_t* srow = slab_gen + b * TC_SLAB_BYTES + r * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rc[j] = rv[j];
-          if (cgp + 2 < ngroups) fetch_res(cgp + 2);     // next group's residual in flight during this group's math
-          tmem_ld32_wait(v);
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = cgp * 32 + j * 8;
-              const int n = nbase + col;
-              if (col < p.nc && n < p.epi.N) {
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int chunk = half * 4 + q4;                 // 16-byte chunk of the 128-byte slab row
+              const int n = nbase + j * 64 + chunk * 8;
+              uint4* sp = reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4));   // 128B swizzle
+              if (n < p.epi.N) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) * rs;
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q4 * 8 + i]) * rs;
                 if (p.epi.col_bias) {
                   const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n));
                   const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n + 4));
                   f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
-                if (rrow) {
-                  const uint32_t w4[4] = {rc[j].x, rc[j].y, rc[j].z, rc[j].w};
+                if (p.has_res) {
+                  const uint4 rr4 = *sp;
+                  const uint32_t w4[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     f[2 * i] += __uint_as_float(w4[i] << 16);
@@ -237,34 +258,83 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                 }
-                store8<bf16>(orow + col, f);
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                *sp = o;
               }
             }
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+          if (j == nslabs - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));                 // TMEM buffer drained
+          }
+          named_bar_arrive(1 + b, TC_STORE_BAR_THREADS);                 // slab written (store warp syncs on it)
         }
       } else {
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
+        const int ngroups = (p.nc + 31) / 32;
         for (int cgp = half; cgp < ngroups; cgp += 2) {
           uint32_t v[32];
           tmem_ld32(t_row + cgp * 32, v);
           if (valid) {
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-              const int col = cgp * 32 + j * 8;
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int col = cgp * 32 + q4 * 8;
               if (col < p.nc) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
-                epilogue_store8<bf16>(p.epi, prow, img, y, x, nbase + col, f);
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q4 * 8 + i]);
+                epilogue_store8<bf16>(p.epi, prow, t.img, y, x, nbase + col, f);
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  } else if (warp == 2 + TC_EPI_WARPS) {
+    // ===================== residual-slab producer =====================
+    if (FAST && p.has_res && lane == 0) {
+      uint32_t slab_ctr = 0;
+      for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const TileCoord t = tile_coord(p, item);
+        for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
+          const int b = slab_ctr % TC_NSLAB;
+          mbar_wait(sempty_bar(b), ((slab_ctr / TC_NSLAB) & 1) ^ 1);
+          mbar_expect_tx(sfull_bar(b), TC_SLAB_BYTES);
+          const int n0 = t.nchunk * p.nc + j * 64;
+          if (p.spatial) tma_load_4d(slab_base + b * TC_SLAB_BYTES, &map_res, sfull_bar(b), n0, t.tx0, t.ty0, t.img);
+          else tma_load_3d(slab_base + b * TC_SLAB_BYTES, &map_res, sfull_bar(b), n0, t.r0, t.g);
+        }
+      }
+    }
+  } else {
+    // ===================== slab store issuer =====================
+    if (FAST) {
+      uint32_t slab_ctr = 0;
+      for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const TileCoord t = tile_coord(p, item);
+        for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
+          const int b = slab_ctr % TC_NSLAB;
+          named_bar_sync(1 + b, TC_STORE_BAR_THREADS);                   // all 256 epilogue threads have written slab b
+          if (lane == 0) {
+            const int n0 = t.nchunk * p.nc + j * 64;
+            if (p.spatial) tma_store_4d(&map_out, slab_base + b * TC_SLAB_BYTES, n0, t.tx0, t.ty0, t.img);
+            else tma_store_3d(&map_out, slab_base + b * TC_SLAB_BYTES, n0, t.r0, t.g);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");    // stores <= slab_ctr-2 have left smem
+            if (slab_ctr >= 2) mbar_arrive(sempty_bar((slab_ctr - 2) % TC_NSLAB));
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
 
@@ -279,13 +349,19 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // ---------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------
+// N is split in chunks of at most 256 accumulator columns; with several chunks the chunk width is a multiple of 64 so
+// that no 64-column output slab straddles two chunks.
 int pick_nc(int N, int* n_chunks) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= TC_NC_MAX) { *n_chunks = 1; return n16; }
-  const int chunks = (n16 + TC_NC_MAX - 1) / TC_NC_MAX;
-  int nc = ((n16 + chunks - 1) / chunks + 15) / 16 * 16;
-  *n_chunks = (N + nc - 1) / nc;
-  return nc;
+  int best_nc = 256, best_cost = 1 << 30;
+  for (int nc = 256; nc >= 128; nc -= 64) {
+    const int chunks = (N + nc - 1) / nc;
+    const int cost = chunks * nc;
+    if (cost < best_cost) { best_cost = cost; best_nc = nc; }
+  }
+  *n_chunks = (N + best_nc - 1) / best_nc;
+  return best_nc;
 }
 
 int g_num_sms = 0;
@@ -327,45 +403,48 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   p.nc = pick_nc(op.epi.N, &p.n_chunks);
   p.H = op.H; p.W = op.W;
   p.epi = op.epi;
+  const Epilogue& e = op.epi;
+  p.has_res = e.res != nullptr;
+  const bool fast = e.mode == OUT_IDENTITY && e.N % 8 == 0 && e.row_mu == nullptr && e.out_ld % 8 == 0 && e.out_coff % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+                    (e.res == nullptr || (e.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(e.res) & 15) == 0)) &&
+                    (e.col_bias == nullptr || (reinterpret_cast<uintptr_t>(e.col_bias) & 15) == 0);
 
-  CUtensorMap ma0, ma1, mw;
+  CUtensorMap ma0, ma1, mw, mout, mres;
   const long rows = (long)op.nimg * op.H * op.W;
   long tiles_m;
+  // activation-like maps (A sources, output, residual): {channels, pixels...}
+  auto act_map = [&](CUtensorMap* m, const void* base, int ch, long ld, int box_ch) -> int {
+    if (p.spatial) {
+      const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.nimg};
+      const cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * op.W, (cuuint64_t)ld * 2 * op.W * op.H};
+      const cuuint32_t box[4] = {(cuuint32_t)box_ch, TC_TW, TC_TH, 1};
+      return make_map(m, base, 4, dims, str, box);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)ch, (cuuint64_t)p.rows_per_group, (cuuint64_t)op.groups};
+    const cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * p.rows_per_group};
+    const cuuint32_t box[3] = {(cuuint32_t)box_ch, TC_BM, 1};
+    return make_map(m, base, 3, dims, str, box);
+  };
   if (p.spatial) {
     p.tiles_x = cdiv(op.W, TC_TW);
     p.tiles_y = cdiv(op.H, TC_TH);
     tiles_m = (long)op.nimg * p.tiles_x * p.tiles_y;
-    const cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
-    {
-      const cuuint64_t dims[4] = {(cuuint64_t)op.c0, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.nimg};
-      const cuuint64_t str[3] = {(cuuint64_t)op.ld0 * 2, (cuuint64_t)op.ld0 * 2 * op.W, (cuuint64_t)op.ld0 * 2 * op.W * op.H};
-      KD_TRY(make_map(&ma0, op.a0, 4, dims, str, box));
-    }
-    if (op.c1 > 0) {
-      const cuuint64_t dims[4] = {(cuuint64_t)op.c1, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.nimg};
-      const cuuint64_t str[3] = {(cuuint64_t)op.ld1 * 2, (cuuint64_t)op.ld1 * 2 * op.W, (cuuint64_t)op.ld1 * 2 * op.W * op.H};
-      KD_TRY(make_map(&ma1, op.a1, 4, dims, str, box));
-    } else {
-      ma1 = ma0;
-    }
   } else {
     KD_CHECK(rows % op.groups == 0, "conv_gemm_tc: rows %ld not divisible by groups %d", rows, op.groups);
     p.rows_per_group = rows / op.groups;
     p.tiles_per_group = cdiv(p.rows_per_group, TC_BM);
     tiles_m = (long)p.tiles_per_group * op.groups;
-    const cuuint32_t box[3] = {TC_BK, TC_BM, 1};
-    {
-      const cuuint64_t dims[3] = {(cuuint64_t)op.c0, (cuuint64_t)p.rows_per_group, (cuuint64_t)op.groups};
-      const cuuint64_t str[2] = {(cuuint64_t)op.ld0 * 2, (cuuint64_t)op.ld0 * 2 * p.rows_per_group};
-      KD_TRY(make_map(&ma0, op.a0, 3, dims, str, box));
-    }
-    if (op.c1 > 0) {
-      const cuuint64_t dims[3] = {(cuuint64_t)op.c1, (cuuint64_t)p.rows_per_group, (cuuint64_t)op.groups};
-      const cuuint64_t str[2] = {(cuuint64_t)op.ld1 * 2, (cuuint64_t)op.ld1 * 2 * p.rows_per_group};
-      KD_TRY(make_map(&ma1, op.a1, 3, dims, str, box));
-    } else {
-      ma1 = ma0;
-    }
+  }
+  KD_TRY(act_map(&ma0, op.a0, op.c0, op.ld0, TC_BK));
+  if (op.c1 > 0) KD_TRY(act_map(&ma1, op.a1, op.c1, op.ld1, TC_BK));
+  else ma1 = ma0;
+  if (fast) {
+    KD_TRY(act_map(&mout, reinterpret_cast<const bf16*>(e.out) + e.out_coff, e.N, e.out_ld, 64));
+    if (e.res) KD_TRY(act_map(&mres, e.res, e.N, e.res_ld, 64));
+    else mres = mout;
+  } else {
+    mout = ma0; mres = ma0;
   }
   {
     const long w_row = (p.taps > 1) ? (long)p.taps * op.w_tap_ld : (long)(op.c0 + op.c1);
@@ -380,13 +459,8 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   const double ktot = (double)p.taps * (op.c0 + op.c1);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * op.epi.N * ktot,
                  2.0 * ((double)rows * (op.c0 + op.c1 + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * ktot));
-  const Epilogue& e = op.epi;
-  const bool fast = e.mode == OUT_IDENTITY && e.N % 8 == 0 && e.row_mu == nullptr && e.out_ld % 8 == 0 && e.out_coff % 8 == 0 &&
-                    (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
-                    (e.res == nullptr || (e.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(e.res) & 15) == 0)) &&
-                    (e.col_bias == nullptr || (reinterpret_cast<uintptr_t>(e.col_bias) & 15) == 0);
-  if (fast) k_conv_gemm_tc<1><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
-  else k_conv_gemm_tc<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, p);
+  if (fast) k_conv_gemm_tc<1><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p);
+  else k_conv_gemm_tc<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
