@@ -130,6 +130,10 @@ struct Epilogue {
   int cq = 0;                        // PIXEL_SHUFFLE: channels per sub-pixel (N = 4*cq, packed sub-pixel major)
   int H = 0, W = 0;                  // conv-output pixel grid (per image/frame)
   int N = 0;                         // valid output channels
+  // optional: LayerNorm statistics of the produced rows (over the N channels) for the next fused LN
+  // (tcgen05 FAST epilogue only, N in a single chunk): rstd = 1/sqrt(var + 1e-5), mu = mean
+  float* stat_rstd = nullptr;
+  float* stat_mu = nullptr;
 };
 
 // Store 8 consecutive columns n0..n0+7 (n0 % 8 == 0) of one row. `img` = b*D+d, `prow` = linear row.

@@ -7,20 +7,27 @@
 // (2 CTAs/SM so one CTA's TMA load overlaps the other's math).  The gate variant loads the matching 64
 // channels of the second chunk(2) half with a second box and emits gelu(dw(x1)) * dw(x2).
 #include <algorithm>
+#include <cstdlib>
 #include "sm100.cuh"
 
 namespace kd {
 
 namespace {
 
-constexpr int DW_TW = 32, DW_TH = 8, DW_CB = 64;
-constexpr int DW_IN_W = DW_TW + 2, DW_IN_H = DW_TH + 2;
-constexpr uint32_t DW_TILE_BYTES = DW_IN_W * DW_IN_H * DW_CB * 2;   // 43520
+constexpr int DW_TH = 8, DW_CB = 64;
+constexpr int DW_IN_H = DW_TH + 2;
+// PX = consecutive output pixels per thread; the tile is 4*PX pixels wide (PX=8: 32x8 tile, PX=4: 16x8 tile)
+template <int PX> struct DwCfg {
+  static constexpr int TW = 4 * PX, IN_W = TW + 2;
+  static constexpr uint32_t TILE_BYTES = IN_W * DW_IN_H * DW_CB * 2;
+};
 
-template <int GATE>
-__global__ void __launch_bounds__(256, GATE ? 1 : 2)
+template <int GATE, int PX>
+__global__ void __launch_bounds__(256, PX == 8 ? (GATE ? 1 : 2) : (GATE ? 2 : 3))
 k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, long ldo, const float* __restrict__ w9c,
              int H, int W, int C, int Cout, int tiles_x, int tiles_y, int cblocks, int total_tiles) {
+  constexpr int DW_TW = DwCfg<PX>::TW, DW_IN_W = DwCfg<PX>::IN_W;
+  constexpr uint32_t DW_TILE_BYTES = DwCfg<PX>::TILE_BYTES;
   constexpr uint32_t STAGE = (GATE ? 2 : 1) * DW_TILE_BYTES;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -50,7 +57,7 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
 
   const int cg = threadIdx.x & 7;
   const int pg = threadIdx.x >> 3;
-  const int row = pg >> 2, xs = (pg & 3) * 8;
+  const int row = pg >> 2, xs = (pg & 3) * PX;
 
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -67,12 +74,12 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
 
     mbar_wait(bar0 + 8u * stage, (it >> 1) & 1);
 
-    float res[8][8];
+    float res[PX][8];
 #pragma unroll
     for (int half = 0; half < (GATE ? 2 : 1); ++half) {
-      float acc[8][8];
+      float acc[PX][8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p)
+      for (int p = 0; p < PX; ++p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
       const bf16* tl = reinterpret_cast<const bf16*>(sgen + stage * STAGE + half * DW_TILE_BYTES);
@@ -94,13 +101,13 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
         }
         const bf16* rp = tl + ((row + dy) * DW_IN_W + xs) * DW_CB + cg * 8;
 #pragma unroll
-        for (int cx = 0; cx < 10; ++cx) {
+        for (int cx = 0; cx < PX + 2; ++cx) {
           float v[8];
           load8<bf16>(rp + cx * DW_CB, v);
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
             const int p = cx - t;   // output pixel fed by this input column through filter column t
-            if (p >= 0 && p < 8) {
+            if (p >= 0 && p < PX) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(v[i], wt[t][i], acc[p][i]);
             }
@@ -109,12 +116,12 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
       }
       if (half == 0) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
+        for (int p = 0; p < PX; ++p)
 #pragma unroll
           for (int i = 0; i < 8; ++i) res[p][i] = acc[p][i];
       } else {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
+        for (int p = 0; p < PX; ++p)
 #pragma unroll
           for (int i = 0; i < 8; ++i) res[p][i] = gelu_erf(res[p][i]) * acc[p][i];
       }
@@ -123,7 +130,7 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
     if (ch_ok && y < H) {
       bf16* op = out + (((long)img * H + y) * W + x0 + xs) * ldo + ch;
 #pragma unroll
-      for (int p = 0; p < 8; ++p)
+      for (int p = 0; p < PX; ++p)
         if (x0 + xs + p < W) store8<bf16>(op + (long)p * ldo, res[p]);
     }
     __syncthreads();   // everyone is done reading this stage before it is refilled two iterations later
@@ -133,40 +140,51 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
 }  // namespace
 
 static int g_dw_sms = 148;
+static int g_dw_px = 8;
 
-// bf16 specialisation entry used by dwconv3x3<bf16>; returns -1 when the shape is not eligible
-int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
-                  cudaStream_t s) {
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || ldx % 8 || ldo % 8 || C % (gate ? 16 : 8)) return -1;
+template <int GATE, int PX>
+static int launch_dw(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, cudaStream_t s) {
+  constexpr uint32_t smem = 2 * (GATE ? 2 : 1) * DwCfg<PX>::TILE_BYTES + 256;
   static bool attr = false;
   if (!attr) {
-    KD_CUDA(cudaFuncSetAttribute(k_dwconv_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DW_TILE_BYTES + 256));
-    KD_CUDA(cudaFuncSetAttribute(k_dwconv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * DW_TILE_BYTES + 256));
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_dw_sms, cudaDevAttrMultiProcessorCount, dev));
+    KD_CUDA(cudaFuncSetAttribute(k_dwconv_tma<GATE, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
   const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
-  const cuuint32_t box[4] = {DW_CB, DW_IN_W, DW_IN_H, 1};
+  const cuuint32_t box[4] = {DW_CB, (cuuint32_t)DwCfg<PX>::IN_W, DW_IN_H, 1};
   KD_TRY(make_map(&map, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
-  const int Cout = gate ? C / 2 : C;
-  const int tiles_x = cdiv(W, DW_TW), tiles_y = cdiv(H, DW_TH), cblocks = cdiv(Cout, DW_CB);
+  const int Cout = GATE ? C / 2 : C;
+  const int tiles_x = cdiv(W, DwCfg<PX>::TW), tiles_y = cdiv(H, DW_TH), cblocks = cdiv(Cout, DW_CB);
   const long total = (long)nimg * tiles_x * tiles_y * cblocks;
   KD_CHECK(total < (1L << 31), "dwconv3x3: too many tiles");
-  const long grid = std::min<long>(total, (long)g_dw_sms * (gate ? 1 : 2));
+  const int per_sm = PX == 8 ? (GATE ? 1 : 2) : (GATE ? 2 : 3);
+  const long grid = std::min<long>(total, (long)g_dw_sms * per_sm);
   ProfScope prof(PC_DWCONV, s, 18.0 * nimg * H * W * C, (double)nimg * H * W * (C + Cout) * 2.0 + 36.0 * C);
-  if (gate)
-    k_dwconv_tma<1><<<(unsigned)grid, 256, 4 * DW_TILE_BYTES + 256, s>>>(map, out, ldo, w9c, H, W, C, Cout, tiles_x, tiles_y, cblocks,
-                                                                        (int)total);
-  else
-    k_dwconv_tma<0><<<(unsigned)grid, 256, 2 * DW_TILE_BYTES + 256, s>>>(map, out, ldo, w9c, H, W, C, Cout, tiles_x, tiles_y, cblocks,
-                                                                        (int)total);
+  k_dwconv_tma<GATE, PX><<<(unsigned)grid, 256, smem, s>>>(map, out, ldo, w9c, H, W, C, Cout, tiles_x, tiles_y, cblocks, (int)total);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
+}
+
+// bf16 specialisation entry used by dwconv3x3<bf16>; returns -1 when the shape is not eligible
+int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
+                  cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || ldx % 8 || ldo % 8 || C % (gate ? 16 : 8)) return -1;
+  static bool init = false;
+  if (!init) {
+    int dev = 0;
+    KD_CUDA(cudaGetDevice(&dev));
+    KD_CUDA(cudaDeviceGetAttribute(&g_dw_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("KDLAE_DW_PX");
+    if (e && atoi(e) == 4) g_dw_px = 4;
+    if (e && atoi(e) == 8) g_dw_px = 8;
+    init = true;
+  }
+  if (g_dw_px == 4)
+    return gate ? launch_dw<1, 4>(x, ldx, out, ldo, w9c, nimg, H, W, C, s) : launch_dw<0, 4>(x, ldx, out, ldo, w9c, nimg, H, W, C, s);
+  return gate ? launch_dw<1, 8>(x, ldx, out, ldo, w9c, nimg, H, W, C, s) : launch_dw<0, 8>(x, ldx, out, ldo, w9c, nimg, H, W, C, s);
 }
 
 }  // namespace kd

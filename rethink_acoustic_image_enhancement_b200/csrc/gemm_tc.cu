@@ -37,7 +37,8 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_NC_MAX * TC_BK * 2;
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_SLAB_BYTES = TC_BM * 64 * 2;
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_STAT_BYTES = TC_NSLAB * 2 * TC_BM * 2 * 4;   // [slab buffer][half][row]{mean, M2}
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SLAB_BYTES + TC_STAT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_STORE_BAR_THREADS = TC_EPI_WARPS * 32 + 32;
 
 struct TcParams {
@@ -94,7 +95,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 // ---------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------
-template <int FAST>
+// FAST epilogue feature mask (compile-time so the per-vector inner loop has no runtime branches)
+enum { EF_ROW_SCALE = 1, EF_BIAS = 2, EF_RES = 4, EF_RELU = 8, EF_STATS = 16, EF_RUNTIME = 32 };
+
+// FAST = 0: generic epilogue. FAST = 1: slab/TMA epilogue specialised on MASK (EF_RUNTIME: flags read at run time).
+template <int FAST, int MASK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
@@ -102,7 +107,8 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slab_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  const uint32_t bar_base = slab_base + TC_NSLAB * TC_SLAB_BYTES;
+  const uint32_t stat_base = slab_base + TC_NSLAB * TC_SLAB_BYTES;
+  const uint32_t bar_base = stat_base + TC_STAT_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
@@ -113,6 +119,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* slab_gen = smem_raw + (slab_base - smem_u32(smem_raw));
+  float2* stat_gen = reinterpret_cast<float2*>(smem_raw + (stat_base - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -217,17 +224,26 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t t_row = tmem_base + acc * TC_NC_MAX + ((uint32_t)(quarter * 32) << 16);
       const int nbase = t.nchunk * p.nc;
       if (FAST) {
-        const float rs = (valid && p.epi.row_scale) ? __ldg(p.epi.row_scale + prow) : 1.0f;
+        const bool rt = (MASK & EF_RUNTIME) != 0;
+        const bool f_rs = rt ? (p.epi.row_scale != nullptr) : (MASK & EF_ROW_SCALE) != 0;
+        const bool f_bias = rt ? (p.epi.col_bias != nullptr) : (MASK & EF_BIAS) != 0;
+        const bool f_res = rt ? (p.has_res != 0) : (MASK & EF_RES) != 0;
+        const bool f_relu = rt ? (p.epi.relu != 0) : (MASK & EF_RELU) != 0;
+        const bool f_stats = rt ? (p.epi.stat_rstd != nullptr) : (MASK & EF_STATS) != 0;
+        const float* __restrict__ bias_p = p.epi.col_bias;
+        const int n_valid = p.epi.N, nc_ = p.nc;
+        const float rs = (f_rs && valid) ? __ldg(p.epi.row_scale + prow) : 1.0f;
+        float st_mean = 0.f, st_m2 = 0.f;   // running sum / sum of squares of this thread's part of the row
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
           const int b = slab_ctr % TC_NSLAB;
           const uint32_t sph = (slab_ctr / TC_NSLAB) & 1;
           // the slab holds the residual tile (TMA-loaded) or is simply free again (its last store has been read out)
-          if (p.has_res) mbar_wait(sfull_bar(b), sph);
+          if (f_res) mbar_wait(sfull_bar(b), sph);
           else mbar_wait(sempty_bar(b), sph ^ 1);
           const int col0 = j * 64 + half * 32;
-          if (col0 < p.nc) {
+          if (col0 < nc_) {
             uint32_t v[32];
             tmem_ld32(t_row + col0, v);
             uint8_t* srow = slab_gen + b * TC_SLAB_BYTES + r * 128;
@@ -236,16 +252,16 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               const int chunk = half * 4 + q4;                 // 16-byte chunk of the 128-byte slab row
               const int n = nbase + j * 64 + chunk * 8;
               uint4* sp = reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4));   // 128B swizzle
-              if (n < p.epi.N) {
+              if (n < n_valid) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q4 * 8 + i]) * rs;
-                if (p.epi.col_bias) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.epi.col_bias + n + 4));
+                for (int i = 0; i < 8; ++i) f[i] = f_rs ? __uint_as_float(v[q4 * 8 + i]) * rs : __uint_as_float(v[q4 * 8 + i]);
+                if (f_bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_p + n));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_p + n + 4));
                   f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
-                if (p.has_res) {
+                if (f_res) {
                   const uint4 rr4 = *sp;
                   const uint32_t w4[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
 #pragma unroll
@@ -254,9 +270,13 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     f[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
                   }
                 }
-                if (p.epi.relu) {
+                if (f_relu) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                if (f_stats) {   // plain sums; the residual stream is roughly centred, fp32 is ample for C <= 256
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { st_mean += f[i]; st_m2 = fmaf(f[i], f[i], st_m2); }
                 }
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -265,6 +285,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             }
           }
+          if (f_stats && j == nslabs - 1) stat_gen[(b * 2 + half) * TC_BM + r] = make_float2(st_mean, st_m2);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
           if (j == nslabs - 1) {
             tc_fence_before();
@@ -323,6 +344,23 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
           const int b = slab_ctr % TC_NSLAB;
           named_bar_sync(1 + b, TC_STORE_BAR_THREADS);                   // all 256 epilogue threads have written slab b
+          if (p.epi.stat_rstd && j == nslabs - 1) {
+            // add the two column halves of every row and publish rstd / mean for the next LayerNorm
+            const float inv_n = 1.0f / (float)p.epi.N;
+#pragma unroll
+            for (int k = 0; k < TC_BM / 32; ++k) {
+              const int row = k * 32 + lane;
+              const long rr = (long)t.r0 + row;
+              if (rr < p.rows_per_group) {
+                const float2 a = stat_gen[(b * 2 + 0) * TC_BM + row], c2 = stat_gen[(b * 2 + 1) * TC_BM + row];
+                const float mean = (a.x + c2.x) * inv_n;
+                const float var = fmaxf((a.y + c2.y) * inv_n - mean * mean, 0.f);
+                const long prow = (long)t.g * p.rows_per_group + rr;
+                p.epi.stat_rstd[prow] = rsqrtf(var + 1e-5f);
+                if (p.epi.stat_mu) p.epi.stat_mu[prow] = mean;
+              }
+            }
+          }
           if (lane == 0) {
             const int n0 = t.nchunk * p.nc + j * 64;
             if (p.spatial) tma_store_4d(&map_out, slab_base + b * TC_SLAB_BYTES, n0, t.tx0, t.ty0, t.img);
@@ -366,6 +404,15 @@ int pick_nc(int N, int* n_chunks) {
 
 int g_num_sms = 0;
 
+cudaError_t set_smem_attr() {
+  cudaError_t e = cudaSuccess;
+#define KD_TC_ATTR(F, M) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_gemm_tc<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  KD_TC_ATTR(0, 0) KD_TC_ATTR(1, 0) KD_TC_ATTR(1, EF_ROW_SCALE) KD_TC_ATTR(1, EF_RES) KD_TC_ATTR(1, EF_RES | EF_STATS)
+  KD_TC_ATTR(1, EF_BIAS) KD_TC_ATTR(1, EF_BIAS | EF_RELU) KD_TC_ATTR(1, EF_RUNTIME)
+#undef KD_TC_ATTR
+  return e;
+}
+
 }  // namespace
 
 bool conv_gemm_tc_eligible(const ConvOp& op) {
@@ -387,8 +434,7 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    KD_CUDA(cudaFuncSetAttribute(k_conv_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    KD_CUDA(cudaFuncSetAttribute(k_conv_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    KD_CUDA(set_smem_attr());
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -410,6 +456,8 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
                     (e.res == nullptr || (e.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(e.res) & 15) == 0)) &&
                     (e.col_bias == nullptr || (reinterpret_cast<uintptr_t>(e.col_bias) & 15) == 0);
 
+  KD_CHECK(e.stat_rstd == nullptr || (fast && p.n_chunks == 1 && !p.spatial),
+           "conv_gemm_tc: LayerNorm statistics need the FAST 1x1 epilogue with N in one chunk (N=%d)", e.N);
   CUtensorMap ma0, ma1, mw, mout, mres;
   const long rows = (long)op.nimg * op.H * op.W;
   long tiles_m;
@@ -459,8 +507,23 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   const double ktot = (double)p.taps * (op.c0 + op.c1);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * op.epi.N * ktot,
                  2.0 * ((double)rows * (op.c0 + op.c1 + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * ktot));
-  if (fast) k_conv_gemm_tc<1><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p);
-  else k_conv_gemm_tc<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p);
+  if (!fast) {
+    k_conv_gemm_tc<0, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p);
+  } else {
+    const int mask = (e.row_scale ? EF_ROW_SCALE : 0) | (e.col_bias ? EF_BIAS : 0) | (e.res ? EF_RES : 0) | (e.relu ? EF_RELU : 0) |
+                     (e.stat_rstd ? EF_STATS : 0);
+#define KD_TC_CASE(M) case M: k_conv_gemm_tc<1, M><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p); break;
+    switch (mask) {
+      KD_TC_CASE(0)                                  // reduce_chan
+      KD_TC_CASE(EF_ROW_SCALE)                       // qkv, project_in (LayerNorm folded)
+      KD_TC_CASE(EF_RES)                             // attention apply / project_out + residual
+      KD_TC_CASE(EF_RES | EF_STATS)                  //   ... + statistics for the next LayerNorm
+      KD_TC_CASE(EF_BIAS)                            // ASDQE outc
+      KD_TC_CASE(EF_BIAS | EF_RELU)                  // ASDQE conv + BN + ReLU
+      default: k_conv_gemm_tc<1, EF_RUNTIME><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mout, mres, p); break;
+    }
+#undef KD_TC_CASE
+  }
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

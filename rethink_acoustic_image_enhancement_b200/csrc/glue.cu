@@ -300,9 +300,12 @@ __global__ void __launch_bounds__(256) k_mdta_fold(const float* __restrict__ par
     for (int j = 0; j < ch; ++j) G[i * ch + j] *= inv;
   }
   __syncthreads();
+  // each CTA of the z-dimension produces a block of output rows n (the softmax above is recomputed per block: cheap)
   T* dst = mb + (long)img * mb_img_stride + head * ch;
-  for (int e = tid; e < C * ch; e += 256) {
-    const int n = e / ch, j = e % ch;
+  const int rows_per_blk = (C + gridDim.z - 1) / gridDim.z;
+  const int n_begin = blockIdx.z * rows_per_blk, n_end = min(C, n_begin + rows_per_blk);
+  for (int e = tid; e < (n_end - n_begin) * ch; e += 256) {
+    const int n = n_begin + e / ch, j = e % ch;
     const float* wrow = wproj + (long)n * C + head * ch;
     float s = 0.f;
     for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], G[i * ch + j], s);
@@ -322,7 +325,7 @@ int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const f
     attr = true;
   }
   ProfScope prof(PC_MDTA_FOLD, s, 2.0 * nimg * C * C * ch, 4.0 * nimg * heads * splits * (ch * ch + 2 * ch) + (double)nimg * C * C * (4 + sizeof(T)));
-  k_mdta_fold<T><<<dim3(heads, nimg), 256, smem, s>>>(part, C, heads, splits, temperature, wproj, mb, mb_ld, mb_img_stride);
+  k_mdta_fold<T><<<dim3(heads, nimg, cdiv(C, 16)), 256, smem, s>>>(part, C, heads, splits, temperature, wproj, mb, mb_ld, mb_img_stride);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
@@ -336,14 +339,13 @@ template int mdta_fold<bf16>(const float*, int, int, int, int, const float*, con
 // =====================================================================================
 template <typename T>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
-  const int cgroups = op.cout / 8;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)op.nimg * op.H * op.W * cgroups;
-  if (idx >= total) return;
+  const unsigned cgroups = op.cout / 8;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index math: one image per blockIdx.y
+  if (idx >= (unsigned)op.H * op.W * cgroups) return;
   const int cg = (int)(idx % cgroups); idx /= cgroups;
-  const int x = (int)(idx % op.W); idx /= op.W;
-  const int y = (int)(idx % op.H); idx /= op.H;
-  const int img = (int)idx;
+  const int x = (int)(idx % (unsigned)op.W);
+  const int y = (int)(idx / (unsigned)op.W);
+  const int img = blockIdx.y;
   const int d = img % op.D, b = img / op.D;
   const int cin = op.cin0 + op.cin1;
   float acc[8];
@@ -393,11 +395,12 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
 template <typename T>
 int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
-  const long total = (long)op.nimg * op.H * op.W * (op.cout / 8);
+  const long total = (long)op.H * op.W * (op.cout / 8);
+  KD_CHECK(total < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
   const double fi_pix = (double)op.nimg * op.H * op.W;
   ProfScope prof(PC_SMALL_CONV, s, 2.0 * fi_pix * op.cout * (op.cin0 + op.cin1) * 9 * op.kd,
                  fi_pix * (4.0 * (op.cin0 + op.cin1) * (op.sub0 ? 2 : 1) + (double)op.cout * sizeof(T)));
-  k_conv_few_in<T><<<cdiv(total, 128), 128, 0, s>>>(op, Hin, Win);
+  k_conv_few_in<T><<<dim3(cdiv(total, 128), op.nimg), 128, 0, s>>>(op, Hin, Win);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
@@ -411,17 +414,16 @@ template int conv_few_in_sized<bf16>(const SmallConv&, int, int, cudaStream_t);
 // Few output channels (output, output2, outputen, student out_conv): thread = pixel, weights in smem.
 template <typename T>
 __global__ void __launch_bounds__(128) k_conv_few_out(const SmallConvOut op) {
-  extern __shared__ float wsm[];  // [cout][taps][cin]
+  extern __shared__ __align__(16) float wsm[];  // [cout][taps][cin]
   const int taps = op.k * op.k;
   const int wn = op.cout * taps * op.cin;
   for (int e = threadIdx.x; e < wn; e += blockDim.x) wsm[e] = op.w[e];
   __syncthreads();
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)op.nimg * op.H * op.W;
-  if (idx >= total) return;
-  const int x = (int)(idx % op.W);
-  const int y = (int)((idx / op.W) % op.H);
-  const int img = (int)(idx / ((long)op.W * op.H));
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math: one image per blockIdx.y
+  if (idx >= (unsigned)op.H * op.W) return;
+  const int x = (int)(idx % (unsigned)op.W);
+  const int y = (int)(idx / (unsigned)op.W);
+  const int img = blockIdx.y;
   const T* in = reinterpret_cast<const T*>(op.in);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int hk = op.k / 2;
@@ -439,9 +441,12 @@ __global__ void __launch_bounds__(128) k_conv_few_out(const SmallConvOut op) {
 #pragma unroll
         for (int co = 0; co < 4; ++co) {
           if (co < op.cout) {
-            const float* wc = wt + (long)co * taps * op.cin + c;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[co] = fmaf(v[i], wc[i], acc[co]);
+            const float* wc = wt + co * taps * op.cin + c;     // 32-byte aligned: cin % 8 == 0
+            const float4 w0 = *reinterpret_cast<const float4*>(wc), w1 = *reinterpret_cast<const float4*>(wc + 4);
+            acc[co] = fmaf(v[0], w0.x, acc[co]); acc[co] = fmaf(v[1], w0.y, acc[co]);
+            acc[co] = fmaf(v[2], w0.z, acc[co]); acc[co] = fmaf(v[3], w0.w, acc[co]);
+            acc[co] = fmaf(v[4], w1.x, acc[co]); acc[co] = fmaf(v[5], w1.y, acc[co]);
+            acc[co] = fmaf(v[6], w1.z, acc[co]); acc[co] = fmaf(v[7], w1.w, acc[co]);
           }
         }
       }
@@ -461,9 +466,10 @@ int conv_few_out(const SmallConvOut& op, cudaStream_t s) {
   const size_t smem = sizeof(float) * (size_t)op.cout * op.k * op.k * op.cin;
   KD_CHECK(smem <= 48 * 1024, "conv_few_out: weights do not fit shared memory");
   const long total = (long)op.nimg * op.H * op.W;
+  KD_CHECK((long)op.H * op.W < (1L << 31) && op.nimg <= 65535, "conv_few_out: image too large");
   ProfScope prof(PC_SMALL_CONV, s, 2.0 * total * op.cout * op.cin * op.k * op.k,
                  (double)total * (op.cin * sizeof(T) + 4.0 * op.cout * (op.res ? 2 : 1)));
-  k_conv_few_out<T><<<cdiv(total, 128), 128, smem, s>>>(op);
+  k_conv_few_out<T><<<dim3(cdiv((long)op.H * op.W, 128), op.nimg), 128, smem, s>>>(op);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -31,15 +31,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// mbarrier wait.  Build with -DKDLAE_MBAR_WATCHDOG=1 to bound the wait: a pipeline-protocol bug then traps with a
+// message instead of hanging the GPU (used while bringing kernels up; off by default because the counter and the
+// compare double the instruction count of every spin iteration).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if defined(KDLAE_MBAR_WATCHDOG) && KDLAE_MBAR_WATCHDOG
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > 200000000u) {
-      printf("kdlae gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      printf("kdlae: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(

@@ -5,6 +5,7 @@
 //   ln_stats -> [1x1 qkv GEMM, LN folded: weight into W, rstd as epilogue row scale] -> dw3x3
 //   -> Gram/norm reduction -> softmax folded into project_out (per-image CxC) -> [1x1 GEMM on v + residual]
 //   ln_stats -> [1x1 project_in GEMM, LN folded] -> dw3x3 + GELU gate -> [1x1 project_out GEMM + residual]
+#include <type_traits>
 #include <vector>
 #include "models.cuh"
 
@@ -152,13 +153,19 @@ struct Scratch {
 
 // One TransformerBlock (KDLAE_model.py:159-163) over `nimg` images of H x W pixels, C channels.
 // x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
+// In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
+// rows (C <= 256, one accumulator chunk), so only the first norm1 of a stage needs the stand-alone ln_stats pass.
+template <typename T>
+bool epilogue_emits_stats(int C) { return std::is_same<T, bf16>::value && C % 8 == 0 && C <= 256; }
+
 template <typename T>
 int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, int nimg, int H, int W, Scratch<T>& sc,
-              cudaStream_t s) {
+              bool have_stats, bool emit_next_stats, cudaStream_t s) {
   const int C = w.C, HW = H * W;
   const long rows = (long)nimg * HW;
+  const bool fused_stats = epilogue_emits_stats<T>(C);
   // ---- x = x + project_out(attn(norm1(x))) ----
-  KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  if (!(have_stats && fused_stats)) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   ConvOp g;
   g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
@@ -173,9 +180,10 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   g.a0 = sc.bufB + 2 * C; g.c0 = C; g.ld0 = 3 * C; g.nimg = nimg; g.H = H; g.W = W;
   g.w = sc.mb; g.w_ld = C; g.w_tap_ld = C; g.groups = nimg; g.w_group_stride = (long)C * C;
   g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = x; g.epi.out_ld = ldx; g.epi.N = C; g.epi.H = H; g.epi.W = W;
+  if (fused_stats) { g.epi.stat_rstd = sc.rstd; g.epi.stat_mu = lnb ? sc.mu : nullptr; }
   KD_TRY(conv_gemm<T>(g, s));
   // ---- x = x + ffn(norm2(x)) ----
-  KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   g = ConvOp();
   g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w.win; g.w_ld = C; g.w_tap_ld = C;
@@ -187,6 +195,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w.wout; g.w_ld = w.hp; g.w_tap_ld = w.hp;
   g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = xout; g.epi.out_ld = ldo; g.epi.N = C; g.epi.H = H; g.epi.W = W;
+  if (fused_stats && emit_next_stats) { g.epi.stat_rstd = sc.rstd; g.epi.stat_mu = lnb ? sc.mu : nullptr; }
   KD_TRY(conv_gemm<T>(g, s));
   return 0;
 }
@@ -196,7 +205,9 @@ int run_blocks(const std::vector<BlockW<T>>& v, bool lnb, T* x, long ldx, T* las
                Scratch<T>& sc, cudaStream_t s) {
   for (size_t i = 0; i < v.size(); ++i) {
     const bool last = (i + 1 == v.size());
-    KD_TRY(run_block<T>(v[i], lnb, x, ldx, last ? last_out : x, last ? last_ld : ldx, nimg, H, W, sc, s));
+    // stats for block i+1's norm1 come from block i's project_out epilogue (same stage, same pixel rows)
+    KD_TRY(run_block<T>(v[i], lnb, x, ldx, last ? last_out : x, last ? last_ld : ldx, nimg, H, W, sc, /*have_stats=*/i > 0,
+                        /*emit_next_stats=*/!last, s));
   }
   return 0;
 }
