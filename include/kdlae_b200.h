@@ -122,6 +122,12 @@ int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int 
 int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H, int W, int C, int gate, int precision,
                     void* stream);
 
+/* Tensor-core depthwise 3x3 (bf16): the conv as 9 tcgen05.mma per 16-channel group with diagonal weight blocks.
+ * wtc_scratch: kdlae_dwconv_tc_weight_bytes(C, gate) bytes of device memory (filled here from w9c, then used). */
+size_t kdlae_dwconv_tc_weight_bytes(int C, int gate);
+int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scratch, int nimg, int H, int W, int C, int gate,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

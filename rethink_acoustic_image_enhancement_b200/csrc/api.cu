@@ -268,4 +268,17 @@ int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H,
                                     W, C, gate, s);
 }
 
+size_t kdlae_dwconv_tc_weight_bytes(int C, int gate) { return kd::dwconv_tc_weight_bytes(C, gate); }
+
+int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scratch, int nimg, int H, int W, int C, int gate,
+                       void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && out && w9c && wtc_scratch, "kdlae_dwconv3x3_tc: NULL argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  KD_TRY(kd::pack_dw_tc(w9c, C, gate, wtc_scratch, s));
+  const long ldo = gate ? C / 2 : C;
+  return kd::dwconv3x3<bf16>(reinterpret_cast<const bf16*>(x), C, reinterpret_cast<bf16*>(out), ldo, w9c, nullptr, nimg, H, W, C,
+                             gate, s, wtc_scratch);
+}
+
 }  // extern "C"

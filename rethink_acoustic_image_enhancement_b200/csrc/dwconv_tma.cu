@@ -47,11 +47,22 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
     if (GATE) tma_load_4d(dst + DW_TILE_BYTES, &map, bar, hp + cb * DW_CB, txi * DW_TW - 1, tyi * DW_TH - 1, img);
   };
 
+  auto prefetch_l2 = [&](int tile) {   // bring a later tile's boxes into L2 (2-3 tiles ahead of the smem load)
+    int b = tile;
+    const int cb = b % cblocks; b /= cblocks;
+    const int txi = b % tiles_x; b /= tiles_x;
+    const int tyi = b % tiles_y;
+    const int img = b / tiles_y;
+    tma_prefetch_4d(&map, cb * DW_CB, txi * DW_TW - 1, tyi * DW_TH - 1, img);
+    if (GATE) tma_prefetch_4d(&map, hp + cb * DW_CB, txi * DW_TW - 1, tyi * DW_TH - 1, img);
+  };
+
   if (threadIdx.x == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    if ((long)blockIdx.x + 2L * gridDim.x < total_tiles) prefetch_l2(blockIdx.x + 2 * gridDim.x);
   }
   __syncthreads();
 
@@ -62,7 +73,10 @@ k_dwconv_tma(const __grid_constant__ CUtensorMap map, bf16* __restrict__ out, lo
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
-    if (threadIdx.x == 0 && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+    if (threadIdx.x == 0) {
+      if (tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+      if ((long)tile + 3L * gridDim.x < total_tiles) prefetch_l2(tile + 3 * gridDim.x);
+    }
     int b = tile;
     const int cb = b % cblocks; b /= cblocks;
     const int txi = b % tiles_x; b /= tiles_x;

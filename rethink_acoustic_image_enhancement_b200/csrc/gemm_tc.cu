@@ -158,7 +158,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int kc = 0; kc < kchunks; ++kc, ++kidx) {
             const int s = kidx % TC_STAGES;
             const uint32_t ph = (kidx / TC_STAGES) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_wait_relaxed(empty_bar(s), ph ^ 1);
             const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
             const uint32_t b_dst = a_dst + TC_A_BYTES;
             mbar_expect_tx(full_bar(s), stage_tx);
@@ -234,14 +234,14 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int n_valid = p.epi.N, nc_ = p.nc;
         const float rs = (f_rs && valid) ? __ldg(p.epi.row_scale + prow) : 1.0f;
         float st_mean = 0.f, st_m2 = 0.f;   // running sum / sum of squares of this thread's part of the row
-        mbar_wait(tfull_bar(acc), aph);
+        mbar_wait_relaxed(tfull_bar(acc), aph);
         tc_fence_after();
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
           const int b = slab_ctr % TC_NSLAB;
           const uint32_t sph = (slab_ctr / TC_NSLAB) & 1;
           // the slab holds the residual tile (TMA-loaded) or is simply free again (its last store has been read out)
-          if (f_res) mbar_wait(sfull_bar(b), sph);
-          else mbar_wait(sempty_bar(b), sph ^ 1);
+          if (f_res) mbar_wait_relaxed(sfull_bar(b), sph);
+          else mbar_wait_relaxed(sempty_bar(b), sph ^ 1);
           const int col0 = j * 64 + half * 32;
           if (col0 < nc_) {
             uint32_t v[32];
@@ -327,7 +327,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const TileCoord t = tile_coord(p, item);
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
           const int b = slab_ctr % TC_NSLAB;
-          mbar_wait(sempty_bar(b), ((slab_ctr / TC_NSLAB) & 1) ^ 1);
+          mbar_wait_relaxed(sempty_bar(b), ((slab_ctr / TC_NSLAB) & 1) ^ 1);
           mbar_expect_tx(sfull_bar(b), TC_SLAB_BYTES);
           const int n0 = t.nchunk * p.nc + j * 64;
           if (p.spatial) tma_load_4d(slab_base + b * TC_SLAB_BYTES, &map_res, sfull_bar(b), n0, t.tx0, t.ty0, t.img);

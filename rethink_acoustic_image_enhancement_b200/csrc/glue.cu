@@ -126,10 +126,17 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const T* __restrict__ x, long
 int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
                   cudaStream_t s);
 
+int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, int nimg, int H, int W, int C, int gate,
+                 cudaStream_t s);
+
 template <typename T>
 int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias, int nimg, int H, int W, int C,
-              int gate, cudaStream_t s) {
-  if (std::is_same<T, bf16>::value && bias == nullptr) {   // TMA-staged tile kernel (bf16 throughput path)
+              int gate, cudaStream_t s, const void* wtc) {
+  if (std::is_same<T, bf16>::value && bias == nullptr && wtc != nullptr) {   // tensor-core kernel (diagonal-weight implicit GEMM)
+    const int r = dwconv3x3_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, wtc, nimg, H, W, C, gate, s);
+    if (r >= 0) return r;
+  }
+  if (std::is_same<T, bf16>::value && bias == nullptr) {   // TMA-staged CUDA-core tile kernel
     const int r = dwconv3x3_tma(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, w9c, nimg, H, W, C, gate, s);
     if (r >= 0) return r;
   }
@@ -142,8 +149,8 @@ int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const fl
   KD_LAUNCH_CHECK();
   return 0;
 }
-template int dwconv3x3<float>(const float*, long, float*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
-template int dwconv3x3<bf16>(const bf16*, long, bf16*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
+template int dwconv3x3<float>(const float*, long, float*, long, const float*, const float*, int, int, int, int, int, cudaStream_t, const void*);
+template int dwconv3x3<bf16>(const bf16*, long, bf16*, long, const float*, const float*, int, int, int, int, int, cudaStream_t, const void*);
 
 // =====================================================================================
 // MDTA reductions (KDLAE_model.py:134-137): partial Gram q k^T + squared L2 norms over pixels

@@ -33,8 +33,11 @@ template <typename T> int ln_stats(const T* x, long ld, int C, long rows, float*
 
 // depthwise 3x3 (pad 1) NHWC; w packed [9][C] (fp32).  gate=0: out[...,C]; gate=1: C = 2*hp,
 // out[..., j] = gelu(dw(x)[j]) * dw(x)[hp + j], j < hp
+// wtc (bf16 path only, optional): diagonal weight blocks from pack_dw_tc -> tensor-core kernel (dwconv_tc.cu)
 template <typename T> int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias,
-                                    int nimg, int H, int W, int C, int gate, cudaStream_t s);
+                                    int nimg, int H, int W, int C, int gate, cudaStream_t s, const void* wtc = nullptr);
+size_t dwconv_tc_weight_bytes(int C, int gate);
+int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
 
 // MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
 // qk: [nimg*HW, ld] with q at channel 0 and k at channel C.  part: [nimg][heads][splits][ch*ch + 2*ch] fp32

@@ -18,6 +18,7 @@ struct BlockW {
   int C, heads, h, hp;
   T* wqkv; float* qkv_s1; float* qkv_s2;   // [3C][C] (+ WithBias column vectors)
   float* wdw_qkv;                          // [9][3C]
+  uint8_t* wdw_qkv_tc; uint8_t* wdw_ffn_tc; // bf16 path: diagonal weight blocks for the tensor-core depthwise kernel
   float* wproj;                            // [C][C] fp32 (consumed by mdta_fold)
   float* temp;                             // [heads]
   T* win; float* in_s1; float* in_s2;      // [2hp][C]
@@ -42,12 +43,15 @@ void layout_block(Bump& b, BlockW<T>& w, int C, int heads, int hidden, bool lnb)
   w.qkv_s1 = lnb ? b.take<float>(3 * C) : nullptr;
   w.qkv_s2 = lnb ? b.take<float>(3 * C) : nullptr;
   w.wdw_qkv = b.take<float>((size_t)9 * 3 * C);
+  const bool tc = std::is_same<T, bf16>::value;
+  w.wdw_qkv_tc = tc ? b.take<uint8_t>(dwconv_tc_weight_bytes(3 * C, 0)) : nullptr;
   w.wproj = b.take<float>((size_t)C * C);
   w.temp = b.take<float>(heads);
   w.win = b.take<T>((size_t)2 * w.hp * C);
   w.in_s1 = lnb ? b.take<float>(2 * w.hp) : nullptr;
   w.in_s2 = lnb ? b.take<float>(2 * w.hp) : nullptr;
   w.wdw_ffn = b.take<float>((size_t)9 * 2 * w.hp);
+  w.wdw_ffn_tc = tc ? b.take<uint8_t>(dwconv_tc_weight_bytes(2 * w.hp, 1)) : nullptr;
   w.wout = b.take<T>((size_t)C * w.hp);
 }
 
@@ -109,6 +113,7 @@ int pack_block(const BlockW<T>& w, Cursor& cur, bool lnb, cudaStream_t s) {
   KD_TRY(pack_weights<T>(p, s));
   if (lnb) KD_TRY(pack_ln_cols<T>(p, ln1b, w.qkv_s1, w.qkv_s2, s));
   KD_TRY(pack_dw(qkv_dw, 3 * C, 0, 0, w.wdw_qkv, 3 * C, s));
+  if (w.wdw_qkv_tc) KD_TRY(pack_dw_tc(w.wdw_qkv, 3 * C, 0, w.wdw_qkv_tc, s));
   KD_TRY(copy_f32(proj, w.wproj, (long)C * C, s));
   KD_TRY(copy_f32(temp, w.temp, w.heads, s));
   // project_in: the two chunk(2) halves of h rows are each padded to hp (127 -> 128 ...) so both start 8-aligned
@@ -118,6 +123,7 @@ int pack_block(const BlockW<T>& w, Cursor& cur, bool lnb, cudaStream_t s) {
   KD_TRY(pack_weights<T>(p, s));
   if (lnb) KD_TRY(pack_ln_cols<T>(p, ln2b, w.in_s1, w.in_s2, s));
   KD_TRY(pack_dw(dw, 2 * w.h, w.h, w.hp, w.wdw_ffn, 2 * w.hp, s));
+  if (w.wdw_ffn_tc) KD_TRY(pack_dw_tc(w.wdw_ffn, 2 * w.hp, 1, w.wdw_ffn_tc, s));
   p = PackOp();
   p.src = pout; p.n_src = C; p.c_src = w.h; p.taps = 1; p.mode = PACK_HALVES; p.halves_on_k = 1; p.h = w.h; p.hp = w.hp;
   p.dst = w.wout; p.n_dst = C; p.c_dst = w.hp;
@@ -172,7 +178,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.qkv_s1; g.epi.col_bias = w.qkv_s2;
   g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
   KD_TRY(conv_gemm<T>(g, s));
-  KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s));
+  KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s, w.wdw_qkv_tc));
   const int splits = mdta_gram_splits(HW, nimg * w.heads);
   KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
   KD_TRY(mdta_fold<T>(sc.gram, nimg, C, w.heads, splits, w.temp, w.wproj, sc.mb, C, (long)C * C, s));
@@ -190,7 +196,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.in_s1; g.epi.col_bias = w.in_s2;
   g.epi.out = sc.bufA; g.epi.out_ld = 2 * w.hp; g.epi.N = 2 * w.hp; g.epi.H = H; g.epi.W = W;
   KD_TRY(conv_gemm<T>(g, s));
-  KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s));
+  KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s, w.wdw_ffn_tc));
   g = ConvOp();
   g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w.wout; g.w_ld = w.hp; g.w_tap_ld = w.hp;

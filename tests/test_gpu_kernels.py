@@ -165,3 +165,28 @@ def test_mdta_gram(lib, prec, dtype, shape):
     assert (got[..., :ch * ch].view(nimg, heads, ch, ch) - G).abs().max().item() < tol
     assert (got[..., ch * ch:ch * ch + ch] - (q * q).sum(-1)).abs().max().item() < tol * 4
     assert (got[..., ch * ch + ch:] - (k * k).sum(-1)).abs().max().item() < tol * 4
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 72, 144, 0), (2, 16, 33, 288, 0), (1, 24, 64, 256, 1), (1, 8, 8, 1024, 1), (3, 9, 5, 48, 0),
+                                   (1, 64, 64, 512, 1)])
+def test_dwconv3x3_tensor_core(lib, shape):
+    """tcgen05 depthwise conv (diagonal-weight implicit GEMM with shifted smem descriptors) vs float64 conv."""
+    n, H, W, C, gate = shape
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(n, H, W, C, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).bfloat16().float()   # bf16-representable weights: isolates the kernel
+    w9c = w.view(C, 9).t().contiguous().to(DEV)
+    Co = C // 2 if gate else C
+    out = torch.full((n, H, W, Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    scratch = torch.empty(lib.kdlae_dwconv_tc_weight_bytes(C, gate), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.kdlae_dwconv3x3_tc(x.data_ptr(), out.data_ptr(), w9c.data_ptr(), scratch.data_ptr(), n, H, W, C, gate, _stream()),
+               "dwconv_tc")
+    torch.cuda.synchronize()
+    y = F.conv2d(x.double().cpu().permute(0, 3, 1, 2), w.double(), padding=1, groups=C)
+    if gate:
+        y = F.gelu(y[:, :Co]) * y[:, Co:]
+    ref = y.permute(0, 2, 3, 1)
+    assert torch.isfinite(out).all()
+    err = (out.double().cpu() - ref).abs().max().item()
+    print(f"dwconv_tc {shape}: max err {err:.3e} (ref max {ref.abs().max().item():.2f})")
+    assert err < 1.2e-2 * max(1.0, ref.abs().max().item())
