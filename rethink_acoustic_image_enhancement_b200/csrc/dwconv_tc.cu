@@ -26,13 +26,15 @@ constexpr int DT_TW = 32, DT_OW = 30, DT_OH = 4, DT_IH = 6, DT_CB = 64;
 constexpr uint32_t DT_TILE_BYTES = DT_TW * DT_IH * DT_CB * 2;   // 24576
 constexpr uint32_t DT_TILE_SLOT = DT_TILE_BYTES + 1024;         // + slack: shifted reads run 2 pixels past the tile
 constexpr uint32_t DT_B_BYTES = 4 * 3 * 2048;                   // per 64-channel block and half: 4 groups x 3 atoms
-constexpr int DT_STAGES = 3;
 constexpr int DT_EPI_WARPS = 8;
 // warp 0: TMA producer; warps 1..NI: MMA issuers (2 per chunk(2) half, two 16-channel groups each); then 8 epilogue warps
 template <int GATE> struct DtCfg {
   static constexpr int NH = GATE ? 2 : 1, NI = 2 * NH, EPI0 = 1 + NI, THREADS = (1 + NI + DT_EPI_WARPS) * 32;
+  static constexpr int STAGES = GATE ? 3 : 6;      // smem tile ring (50 KB / 25 KB per stage)
+  static constexpr int NACC = 4;                   // TMEM accumulator ring: 4 x 128 / 4 x 64 columns
+  static constexpr int TMEM_COLS = GATE ? 512 : 256;
+  static constexpr uint32_t SMEM = 1024 + NH * DT_B_BYTES + STAGES * NH * DT_TILE_SLOT + 256;
 };
-
 __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr, uint32_t base_offset) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -86,12 +88,15 @@ struct DtParams {
   int base_offset_mode;     // 0 (default, verified on B200): the 128B swizzle is a function of the absolute smem address, so a
                             // row-shifted start needs base_offset = 0; 1 sets base_offset = dx (kept as a bring-up switch)
   long ldo;
+  float inv_tiles_x, inv_tiles_y;
 };
 
 template <int GATE>
 __global__ void __launch_bounds__(DtCfg<GATE>::THREADS, 1)
-k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__ wtc, bf16* __restrict__ out, const DtParams p) {
+k_dwconv_tc(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out, const uint8_t* __restrict__ wtc,
+            const DtParams p) {
   constexpr int NH = DtCfg<GATE>::NH, NI = DtCfg<GATE>::NI, EPI0 = DtCfg<GATE>::EPI0;
+  constexpr int DT_STAGES = DtCfg<GATE>::STAGES, NACC = DtCfg<GATE>::NACC;
   constexpr uint32_t STAGE = NH * DT_TILE_SLOT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -101,9 +106,9 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (DT_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * DT_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * DT_STAGES + 2 + a); };
-  const uint32_t wbar = bar_base + 8u * (2 * DT_STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * DT_STAGES + 5);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * DT_STAGES + NACC + a); };
+  const uint32_t wbar = bar_base + 8u * (2 * DT_STAGES + 2 * NACC);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * DT_STAGES + 2 * NACC + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,13 +122,14 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map);
-    for (int s = 0; s < DT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NI); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), NI); mbar_init(tempty_bar(a), DT_EPI_WARPS); }
+    prefetch_tmap(&map_out);
+    for (int s = 0; s < DT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), NI); mbar_init(tempty_bar(a), DT_EPI_WARPS); }
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(DtCfg<GATE>::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -131,10 +137,12 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  auto tile_xy = [&](long t, int& img, int& y0, int& x0) {
-    const int txi = (int)(t % p.tiles_x);
-    const int tyi = (int)((t / p.tiles_x) % p.tiles_y);
-    img = (int)(t / ((long)p.tiles_x * p.tiles_y));
+  auto tile_xy = [&](long t64, int& img, int& y0, int& x0) {
+    const int t = (int)t64;
+    const int rowt = fast_div(t, p.tiles_x, p.inv_tiles_x);
+    const int txi = t - rowt * p.tiles_x;
+    img = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
+    const int tyi = rowt - img * p.tiles_y;
     x0 = txi * DT_OW; y0 = tyi * DT_OH;
   };
 
@@ -168,7 +176,7 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
       uint32_t it = 0;
       for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
         const int s = it % DT_STAGES;
-        const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        const uint32_t acc = it % NACC, aph = (it / NACC) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
         mbar_wait(full_bar(s), (it / DT_STAGES) & 1);
         tc_fence_after();
@@ -188,8 +196,7 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
             }
           }
         }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(acc));
+        umma_commit(tfull_bar(acc));     // accumulator ready; the smem slot is released by the epilogue after its store
       }
     }
   } else {
@@ -199,53 +206,68 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__
     const int chalf = ew >> 2;               // channels [chalf*32, +32) of the 64-channel block
     const int r = quarter * 32 + lane;       // accumulator row = pixel of the tile
     const int ty_l = r / DT_TW, tx_l = r % DT_TW;
+    // Output staging: the tile's own (already consumed) input slot, packed [4 rows][30 px][64 ch] with the 128B swizzle,
+    // leaves through one TMA store box {64 ch, 30 px, 4 rows}: full-line writes, clipped at the image / channel edge.
+    const int opix = ty_l * DT_OW + tx_l;
+    const bool in_box = tx_l < DT_OW;
+    uint8_t* sgen = smem_raw + (a_base - smem_u32(smem_raw));
     uint32_t it = 0;
     for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
-      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-      int img, y0, x0;
-      tile_xy(t, img, y0, x0);
-      const int y = y0 + ty_l, x = x0 + tx_l;
-      const bool valid = (tx_l < DT_OW) && (y < p.H) && (x < p.W);
-      bf16* op = out + (((long)img * p.H + y) * p.W + x) * p.ldo + cb * DT_CB + chalf * 32;
-      mbar_wait_relaxed(tfull_bar(acc), aph);
+      const uint32_t acc = it % NACC, aph = (it / NACC) & 1;
+      const int s = it % DT_STAGES;
+      mbar_wait_relaxed(tfull_bar(acc), aph);   // all MMAs of the tile retired: TMEM valid, smem slot no longer read
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * (NH * DT_CB) + ((uint32_t)(quarter * 32) << 16) + chalf * 32;
+      const bool run0 = chalf * 32 < ch_valid, run1 = chalf * 32 + 16 < ch_valid;   // warp-uniform
+      uint32_t a0[16], a1[16], b0[16], b1[16];
+      if (run0) { tmem_ld16x(t_row, a0); if (GATE) tmem_ld16x(t_row + DT_CB, b0); }
+      if (run1) { tmem_ld16x(t_row + 16, a1); if (GATE) tmem_ld16x(t_row + DT_CB + 16, b1); }
+      uint8_t* srow = sgen + s * STAGE + opix * 128;
+      auto emit = [&](uint32_t (&a)[16], uint32_t (&b)[16], int q) {
+        tmem_wait16(a);
+        if (GATE) tmem_wait16(b);
+        if (in_box) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {          // two runs of 16 channels
-        const int c0 = chalf * 32 + q * 16;
-        if (c0 < ch_valid) {                 // warp-uniform
-          uint32_t a[16], b[16];
-          tmem_ld16x(t_row + q * 16, a);
-          if (GATE) tmem_ld16x(t_row + DT_CB + q * 16, b);
-          tmem_wait16(a);
-          if (GATE) tmem_wait16(b);
-          if (valid) {
+          for (int v8 = 0; v8 < 2; ++v8) {
+            float f[8];
 #pragma unroll
-            for (int v8 = 0; v8 < 2; ++v8) {
-              if (c0 + v8 * 8 < ch_valid) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float x1 = __uint_as_float(a[v8 * 8 + i]);
-                  f[i] = GATE ? gelu_as(x1) * __uint_as_float(b[v8 * 8 + i]) : x1;
-                }
-                store8<bf16>(op + q * 16 + v8 * 8, f);
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float x1 = __uint_as_float(a[v8 * 8 + i]);
+              f[i] = GATE ? gelu_as(x1) * __uint_as_float(b[v8 * 8 + i]) : x1;
             }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            const int chunk = chalf * 4 + q * 2 + v8;
+            *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
           }
         }
-      }
+      };
+      if (run0) emit(a0, b0, 0);
+      if (run1) emit(a1, b1, 1);
       tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      asm volatile("bar.sync 1, %0;" ::"n"(DT_EPI_WARPS * 32) : "memory");   // whole tile staged
+      if (ew == 0 && lane == 0) {
+        int img, y0, x0;
+        tile_xy(t, img, y0, x0);
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&map_out), "r"(a_base + s * STAGE), "r"(cb * DT_CB), "r"(x0), "r"(y0), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // smem read out -> slot free for the next load
+        mbar_arrive(empty_bar(s));
+      }
     }
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(DtCfg<GATE>::TMEM_COLS));
   }
 }
 
@@ -296,8 +318,7 @@ int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, 
   if (wtc == nullptr || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || ldx % 8 || ldo % 8 ||
       C % (gate ? 16 : 8) || (reinterpret_cast<uintptr_t>(wtc) & 15))
     return -1;
-  const uint32_t smem0 = 1024 + DT_B_BYTES + DT_STAGES * DT_TILE_SLOT + 256;
-  const uint32_t smem1 = 1024 + 2 * DT_B_BYTES + DT_STAGES * 2 * DT_TILE_SLOT + 256;
+  const uint32_t smem0 = DtCfg<0>::SMEM, smem1 = DtCfg<1>::SMEM;
   if (g_dt_sms == 0) {
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
@@ -313,17 +334,27 @@ int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, 
   p.tiles_per_cb = (long)nimg * p.tiles_x * p.tiles_y;
   p.base_offset_mode = g_dt_base_offset_mode;
   p.ldo = ldo;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x;
+  p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  if (p.tiles_per_cb >= (1L << 24)) return -1;   // fast_div range
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
   const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
   const cuuint32_t box[4] = {DT_CB, DT_TW, DT_IH, 1};
   KD_TRY(make_map(&map, x, 4, dims, str, box));
+  CUtensorMap map_out;
+  {
+    const cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    const cuuint64_t os[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)ldo * 2 * W, (cuuint64_t)ldo * 2 * W * H};
+    const cuuint32_t ob[4] = {DT_CB, DT_OW, DT_OH, 1};
+    KD_TRY(make_map(&map_out, out, 4, od, os, ob));
+  }
   const long want = (long)p.cblocks * p.tiles_per_cb;
   int grid = (int)std::min<long>(want, (long)g_dt_sms);
   if (grid < p.cblocks) grid = p.cblocks;   // every channel block needs at least one CTA
   ProfScope prof(PC_DWCONV, s, 18.0 * nimg * H * W * C, (double)nimg * H * W * (C + p.Cout) * 2.0 + 36.0 * C);
-  if (gate) k_dwconv_tc<1><<<grid, DtCfg<1>::THREADS, smem1, s>>>(map, reinterpret_cast<const uint8_t*>(wtc), out, p);
-  else k_dwconv_tc<0><<<grid, DtCfg<0>::THREADS, smem0, s>>>(map, reinterpret_cast<const uint8_t*>(wtc), out, p);
+  if (gate) k_dwconv_tc<1><<<grid, DtCfg<1>::THREADS, smem1, s>>>(map, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
+  else k_dwconv_tc<0><<<grid, DtCfg<0>::THREADS, smem0, s>>>(map, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -55,24 +55,27 @@ struct TcParams {
   // spatial mode
   int H, W, tiles_x, tiles_y;
   int has_res;
+  float inv_n_chunks, inv_tiles_per_group, inv_tiles_x, inv_tiles_y;   // fast_div reciprocals (items < 2^24)
   Epilogue epi;
 };
 
 struct TileCoord { int g, r0, tx0, ty0, img, nchunk; };
 
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long item) {
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long item64) {
   TileCoord t;
-  const long mt = item / p.n_chunks;
-  t.nchunk = (int)(item % p.n_chunks);
+  const int item = (int)item64;
+  const int mt = fast_div(item, p.n_chunks, p.inv_n_chunks);
+  t.nchunk = item - mt * p.n_chunks;
   t.g = 0; t.r0 = 0; t.tx0 = 0; t.ty0 = 0; t.img = 0;
   if (p.spatial) {
-    const int txi = (int)(mt % p.tiles_x);
-    const int tyi = (int)((mt / p.tiles_x) % p.tiles_y);
-    t.img = (int)(mt / ((long)p.tiles_x * p.tiles_y));
+    const int rowt = fast_div(mt, p.tiles_x, p.inv_tiles_x);
+    const int txi = mt - rowt * p.tiles_x;
+    t.img = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
+    const int tyi = rowt - t.img * p.tiles_y;
     t.tx0 = txi * TC_TW; t.ty0 = tyi * TC_TH;
   } else {
-    t.g = (int)(mt / p.tiles_per_group);
-    t.r0 = (int)(mt % p.tiles_per_group) * TC_BM;
+    t.g = fast_div(mt, p.tiles_per_group, p.inv_tiles_per_group);
+    t.r0 = (mt - t.g * p.tiles_per_group) * TC_BM;
   }
   return t;
 }
@@ -503,6 +506,11 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     KD_TRY(make_map(&mw, op.w, 3, dims, str, box));
   }
   p.items = tiles_m * p.n_chunks;
+  KD_CHECK(p.items < (1L << 24), "conv_gemm_tc: too many tiles (%ld)", p.items);
+  p.inv_n_chunks = 1.0f / (float)p.n_chunks;
+  p.inv_tiles_per_group = p.tiles_per_group ? 1.0f / (float)p.tiles_per_group : 0.f;
+  p.inv_tiles_x = p.tiles_x ? 1.0f / (float)p.tiles_x : 0.f;
+  p.inv_tiles_y = p.tiles_y ? 1.0f / (float)p.tiles_y : 0.f;
   const int grid = (int)(p.items < (long)g_num_sms ? p.items : (long)g_num_sms);
   const double ktot = (double)p.taps * (op.c0 + op.c1);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * op.epi.N * ktot,

@@ -9,6 +9,14 @@ namespace kd {
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------
+// exact floor(t / d) for 0 <= t < 2^24 via one float multiply and a fix-up (integer division costs ~50 instructions,
+// and every role of a persistent kernel decodes a tile index per tile)
+__device__ __forceinline__ int fast_div(int t, int d, float inv_d) {
+  int q = (int)((float)t * inv_d);
+  if (q * d > t) --q;
+  if ((q + 1) * d <= t) ++q;
+  return q;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
