@@ -113,7 +113,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- epilogue shared by the SIMT and the tcgen05 implicit-GEMM kernels --------------------
 // Row = one output pixel of the conv (b*D+d, y, x) in a D x H x W grid, column n = output channel.
-enum OutMode { OUT_IDENTITY = 0, OUT_PIXEL_SHUFFLE = 1, OUT_PIXEL_UNSHUFFLE = 2 };
+enum OutMode { OUT_IDENTITY = 0, OUT_PIXEL_SHUFFLE = 1, OUT_PIXEL_UNSHUFFLE = 2, OUT_PLANAR_F32 = 3 };
 
 struct Epilogue {
   const float* row_scale = nullptr;  // [rows]  LayerNorm rstd folded behind the GEMM
@@ -134,6 +134,9 @@ struct Epilogue {
   // (tcgen05 FAST epilogue only, N in a single chunk): rstd = 1/sqrt(var + 1e-5), mu = mean
   float* stat_rstd = nullptr;
   float* stat_mu = nullptr;
+  // OUT_PLANAR_F32: fp32 NCHW output (+ fp32 NCHW residual), element (img, n, y, x) at img*img_stride + n*ch_stride + y*W + x
+  float* planar_out = nullptr; long planar_img = 0, planar_ch = 0;
+  const float* planar_res = nullptr; long planar_res_img = 0, planar_res_ch = 0;
 };
 
 // Store 8 consecutive columns n0..n0+7 (n0 % 8 == 0) of one row. `img` = b*D+d, `prow` = linear row.
@@ -151,6 +154,20 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, long prow, in
       if (e.col_bias) t += e.col_bias[n];
     }
     v[i] = t;
+  }
+  if (e.mode == OUT_PLANAR_F32) {
+    const long sp = (long)y * e.W + x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      if (n < e.N) {
+        float t = v[i];
+        if (e.planar_res) t += e.planar_res[(long)img * e.planar_res_img + (long)n * e.planar_res_ch + sp];
+        if (e.relu) t = fmaxf(t, 0.f);
+        e.planar_out[(long)img * e.planar_img + (long)n * e.planar_ch + sp] = t;
+      }
+    }
+    return;
   }
   T* out = reinterpret_cast<T*>(e.out);
   const T* res = reinterpret_cast<const T*>(e.res);

@@ -121,7 +121,7 @@ int conv_gemm_simt(const ConvOp& op, cudaStream_t s) {
   const long rows = (long)op.nimg * op.H * op.W;
   KD_CHECK(op.groups >= 1 && rows % op.groups == 0, "conv_gemm_simt: rows %ld not divisible by groups %d", rows, op.groups);
   p.rows_per_group = rows / op.groups;
-  KD_CHECK(op.epi.N > 0 && op.epi.out != nullptr, "conv_gemm_simt: bad epilogue");
+  KD_CHECK(op.epi.N > 0 && (op.epi.out != nullptr || op.epi.planar_out != nullptr), "conv_gemm_simt: bad epilogue");
   if (op.epi.mode == OUT_PIXEL_SHUFFLE) KD_CHECK(op.epi.cq % 8 == 0 && op.epi.N == 4 * op.epi.cq, "pixel-shuffle needs cq%%8==0");
   dim3 grid(cdiv(p.rows_per_group, BM), cdiv(op.epi.N, BN), op.groups);
   KD_CHECK(grid.y <= 65535 && grid.z <= 65535, "conv_gemm_simt: grid too large");

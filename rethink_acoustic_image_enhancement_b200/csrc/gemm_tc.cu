@@ -31,13 +31,13 @@ constexpr int TC_NC_MAX = 256;     // max N per accumulator (UMMA N)
 constexpr int TC_STAGES = 3;
 constexpr int TC_NSLAB = 4;        // output slabs of 128 rows x 64 columns
 constexpr int TC_TW = 16, TC_TH = 8;   // spatial tile of the 3x3 path
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column quarters of a 64-column slab
 constexpr int TC_THREADS = (2 + TC_EPI_WARPS + 2) * 32;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t TC_B_BYTES = TC_NC_MAX * TC_BK * 2;
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_SLAB_BYTES = TC_BM * 64 * 2;
-constexpr uint32_t TC_STAT_BYTES = TC_NSLAB * 2 * TC_BM * 2 * 4;   // [slab buffer][half][row]{mean, M2}
+constexpr uint32_t TC_STAT_BYTES = TC_NSLAB * 4 * TC_BM * 2 * 4;   // [slab buffer][column quarter][row]{sum, sum of squares}
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SLAB_BYTES + TC_STAT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_STORE_BAR_THREADS = TC_EPI_WARPS * 32 + 32;
 
@@ -208,7 +208,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
-    const int half = ew >> 2;             // which 32-column half of a 64-column slab / which column groups
+    const int cq = ew >> 2;               // which 16-column quarter of a 64-column slab / which column groups
     const int r = quarter * 32 + lane;    // accumulator row (pixel within the tile)
     uint32_t it = 0, slab_ctr = 0;
     for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -245,14 +245,15 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // the slab holds the residual tile (TMA-loaded) or is simply free again (its last store has been read out)
           if (f_res) mbar_wait_relaxed(sfull_bar(b), sph);
           else mbar_wait_relaxed(sempty_bar(b), sph ^ 1);
-          const int col0 = j * 64 + half * 32;
+          const int col0 = j * 64 + cq * 16;
           if (col0 < nc_) {
-            uint32_t v[32];
-            tmem_ld32(t_row + col0, v);
+            uint32_t v[16];
+            tmem_ld16_issue(t_row + col0, v);
+            tmem_ld16_wait(v);
             uint8_t* srow = slab_gen + b * TC_SLAB_BYTES + r * 128;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int chunk = half * 4 + q4;                 // 16-byte chunk of the 128-byte slab row
+            for (int q4 = 0; q4 < 2; ++q4) {
+              const int chunk = cq * 2 + q4;                   // 16-byte chunk of the 128-byte slab row
               const int n = nbase + j * 64 + chunk * 8;
               uint4* sp = reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4));   // 128B swizzle
               if (n < n_valid) {
@@ -288,7 +289,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             }
           }
-          if (f_stats && j == nslabs - 1) stat_gen[(b * 2 + half) * TC_BM + r] = make_float2(st_mean, st_m2);
+          if (f_stats && j == nslabs - 1) stat_gen[(b * 4 + cq) * TC_BM + r] = make_float2(st_mean, st_m2);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
           if (j == nslabs - 1) {
             tc_fence_before();
@@ -301,7 +302,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
         const int ngroups = (p.nc + 31) / 32;
-        for (int cgp = half; cgp < ngroups; cgp += 2) {
+        for (int cgp = cq; cgp < ngroups; cgp += 4) {
           uint32_t v[32];
           tmem_ld32(t_row + cgp * 32, v);
           if (valid) {
@@ -355,9 +356,11 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               const int row = k * 32 + lane;
               const long rr = (long)t.r0 + row;
               if (rr < p.rows_per_group) {
-                const float2 a = stat_gen[(b * 2 + 0) * TC_BM + row], c2 = stat_gen[(b * 2 + 1) * TC_BM + row];
-                const float mean = (a.x + c2.x) * inv_n;
-                const float var = fmaxf((a.y + c2.y) * inv_n - mean * mean, 0.f);
+                float sx = 0.f, sq = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) { const float2 a = stat_gen[(b * 4 + c4) * TC_BM + row]; sx += a.x; sq += a.y; }
+                const float mean = sx * inv_n;
+                const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
                 const long prow = (long)t.g * p.rows_per_group + rr;
                 p.epi.stat_rstd[prow] = rsqrtf(var + 1e-5f);
                 if (p.epi.stat_mu) p.epi.stat_mu[prow] = mean;

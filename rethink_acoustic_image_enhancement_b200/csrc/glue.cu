@@ -273,79 +273,108 @@ template int mdta_gram<bf16>(const bf16*, long, int, int, int, int, int, float*,
 
 // softmax(cosine-Gram * temperature) (KDLAE_model.py:134-138) folded into project_out (:140,:144):
 //   project_out(attn @ v) = (Wp . blockdiag(attn)) @ v   ->  per-image C x C matrix Mb
-template <typename T>
-__global__ void __launch_bounds__(256) k_mdta_fold(const float* __restrict__ part, int C, int heads, int splits,
-                                                   const float* __restrict__ temperature, const float* __restrict__ wproj,
-                                                   T* __restrict__ mb, long mb_ld, long mb_img_stride) {
+// Kernel 1: grid (ch/8, heads, nimg) - reduce the split partials of 8 Gram rows (fixed order: deterministic), normalise
+//           by max(|q_i|,eps) max(|k_j|,eps), scale by the temperature, softmax; the rows are written in place over
+//           split 0 of the partial buffer (each CTA only overwrites the rows that it alone reads).
+__global__ void __launch_bounds__(256) k_mdta_softmax(float* __restrict__ part, int C, int heads, int splits,
+                                                      const float* __restrict__ temperature) {
   extern __shared__ float sm[];
   const int ch = C / heads;
-  const int head = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
-  float* G = sm;                 // [ch][ch]
-  float* nq = sm + ch * ch;      // [ch]
-  float* nk = nq + ch;           // [ch]
+  const int i0 = blockIdx.x * 8, head = blockIdx.y, img = blockIdx.z, tid = threadIdx.x;
+  float* G = sm;                 // [8][ch]
+  float* nq = sm + 8 * ch;       // [8]
+  float* nk = nq + 8;            // [ch]
+  const long psz = (long)ch * ch + 2 * ch;
+  float* src = part + ((long)img * heads + head) * splits * psz;
+  const int nrow = min(8, ch - i0);
+  for (int e = tid; e < nrow * ch + nrow + ch; e += 256) {
+    long off;
+    if (e < nrow * ch) off = (long)(i0 + e / ch) * ch + e % ch;
+    else if (e < nrow * ch + nrow) off = (long)ch * ch + i0 + (e - nrow * ch);
+    else off = (long)ch * ch + ch + (e - nrow * ch - nrow);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += src[(long)sp * psz + off];
+    if (e < nrow * ch) G[e] = s;
+    else if (e < nrow * ch + nrow) nq[e - nrow * ch] = fmaxf(sqrtf(s), 1e-12f);   // F.normalize eps
+    else nk[e - nrow * ch - nrow] = fmaxf(sqrtf(s), 1e-12f);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < nrow) {   // one warp per softmax row
+    const float temp = temperature[head];
+    float* g = G + warp * ch;
+    float mx = -INFINITY;
+    for (int j = lane; j < ch; j += 32) { const float l = g[j] / (nq[warp] * nk[j]) * temp; g[j] = l; mx = fmaxf(mx, l); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < ch; j += 32) { const float e = expf(g[j] - mx); g[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float* dst = src + (long)(i0 + warp) * ch;    // split 0, rows of this CTA
+    for (int j = lane; j < ch; j += 32) dst[j] = g[j] * inv;
+  }
+}
+// Kernel 2: grid (C/16, heads, nimg) - Mb[n][head*ch + j] = sum_i Wp[n][head*ch + i] * attn[i][j] for 16 rows n.
+template <typename T>
+__global__ void __launch_bounds__(256) k_mdta_project(const float* __restrict__ part, int C, int heads, int splits,
+                                                      const float* __restrict__ wproj, T* __restrict__ mb, long mb_ld,
+                                                      long mb_img_stride) {
+  extern __shared__ float sm[];
+  const int ch = C / heads;
+  const int n0 = blockIdx.x * 16, head = blockIdx.y, img = blockIdx.z, tid = threadIdx.x;
+  float* A = sm;                 // attn [ch][ch]
+  float* Wr = sm + ch * ch;      // [16][ch]
   const long psz = (long)ch * ch + 2 * ch;
   const float* src = part + ((long)img * heads + head) * splits * psz;
-  for (int e = tid; e < psz; e += 256) {
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += src[(long)sp * psz + e];
-    sm[e] = s;
-  }
+  for (int e = tid; e < ch * ch; e += 256) A[e] = src[e];
+  const int nrow = min(16, C - n0);
+  for (int e = tid; e < nrow * ch; e += 256) Wr[e] = wproj[(long)(n0 + e / ch) * C + head * ch + e % ch];
   __syncthreads();
-  if (tid < 2 * ch) nq[tid] = fmaxf(sqrtf(nq[tid]), 1e-12f);  // F.normalize eps
-  __syncthreads();
-  const float temp = temperature[head];
-  for (int i = tid; i < ch; i += 256) {  // one softmax row per thread
-    float mx = -INFINITY;
-    for (int j = 0; j < ch; ++j) {
-      const float l = G[i * ch + j] / (nq[i] * nk[j]) * temp;
-      G[i * ch + j] = l;
-      mx = fmaxf(mx, l);
-    }
-    float sum = 0.f;
-    for (int j = 0; j < ch; ++j) { const float e = expf(G[i * ch + j] - mx); G[i * ch + j] = e; sum += e; }
-    const float inv = 1.f / sum;
-    for (int j = 0; j < ch; ++j) G[i * ch + j] *= inv;
-  }
-  __syncthreads();
-  // each CTA of the z-dimension produces a block of output rows n (the softmax above is recomputed per block: cheap)
   T* dst = mb + (long)img * mb_img_stride + head * ch;
-  const int rows_per_blk = (C + gridDim.z - 1) / gridDim.z;
-  const int n_begin = blockIdx.z * rows_per_blk, n_end = min(C, n_begin + rows_per_blk);
-  for (int e = tid; e < (n_end - n_begin) * ch; e += 256) {
-    const int n = n_begin + e / ch, j = e % ch;
-    const float* wrow = wproj + (long)n * C + head * ch;
+  for (int e = tid; e < nrow * ch; e += 256) {
+    const int r = e / ch, j = e % ch;
     float s = 0.f;
-    for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], G[i * ch + j], s);
-    dst[(long)n * mb_ld + j] = from_f<T>(s);
+    for (int i = 0; i < ch; ++i) s = fmaf(Wr[r * ch + i], A[i * ch + j], s);
+    dst[(long)(n0 + r) * mb_ld + j] = from_f<T>(s);
   }
 }
 
 template <typename T>
-int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const float* temperature, const float* wproj, T* mb,
+int mdta_fold(float* part, int nimg, int C, int heads, int splits, const float* temperature, const float* wproj, T* mb,
               long mb_ld, long mb_img_stride, cudaStream_t s) {
   const int ch = C / heads;
-  const size_t smem = sizeof(float) * ((size_t)ch * ch + 2 * ch);
   static bool attr_f = false, attr_b = false;
   bool& attr = std::is_same<T, float>::value ? attr_f : attr_b;
   if (!attr) {
-    KD_CUDA(cudaFuncSetAttribute(k_mdta_fold<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    KD_CUDA(cudaFuncSetAttribute(k_mdta_project<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
   ProfScope prof(PC_MDTA_FOLD, s, 2.0 * nimg * C * C * ch, 4.0 * nimg * heads * splits * (ch * ch + 2 * ch) + (double)nimg * C * C * (4 + sizeof(T)));
-  k_mdta_fold<T><<<dim3(heads, nimg, cdiv(C, 16)), 256, smem, s>>>(part, C, heads, splits, temperature, wproj, mb, mb_ld, mb_img_stride);
+  k_mdta_softmax<<<dim3(cdiv(ch, 8), heads, nimg), 256, sizeof(float) * (9 * ch + 8), s>>>(part, C, heads, splits, temperature);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_mdta_project<T><<<dim3(cdiv(C, 16), heads, nimg), 256, sizeof(float) * ((size_t)ch * ch + 16 * ch), s>>>(part, C, heads, splits, wproj, mb,
+                                                                                                       mb_ld, mb_img_stride);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
 }
-template int mdta_fold<float>(const float*, int, int, int, int, const float*, const float*, float*, long, long, cudaStream_t);
-template int mdta_fold<bf16>(const float*, int, int, int, int, const float*, const float*, bf16*, long, long, cudaStream_t);
+template int mdta_fold<float>(float*, int, int, int, int, const float*, const float*, float*, long, long, cudaStream_t);
+template int mdta_fold<bf16>(float*, int, int, int, int, const float*, const float*, bf16*, long, long, cudaStream_t);
 
 // =====================================================================================
 // Direct convolutions with very few input channels (patch_embed, output_param, cen, student conv 1,
 // ASDQE stems).  thread = (pixel, 8 output channels); planar fp32 inputs.
 // =====================================================================================
-template <typename T>
+// CIN = total input planes (1..4), KD = temporal taps (1 or 3).  All tap inputs are gathered first (independent,
+// predicated loads), the [taps*CIN][cout] weights sit in shared memory.
+template <typename T, int CIN, int KD>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
+  extern __shared__ __align__(16) float wsm_in[];   // [KD*9*CIN][cout]
+  constexpr int TAPS = KD * 9;
+  for (int e = threadIdx.x; e < TAPS * CIN * op.cout; e += blockDim.x) wsm_in[e] = op.w[e];
+  __syncthreads();
   const unsigned cgroups = op.cout / 8;
   unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index math: one image per blockIdx.y
   if (idx >= (unsigned)op.H * op.W * cgroups) return;
@@ -354,42 +383,50 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
   const int y = (int)(idx / (unsigned)op.W);
   const int img = blockIdx.y;
   const int d = img % op.D, b = img / op.D;
-  const int cin = op.cin0 + op.cin1;
-  float acc[8];
+  float in[TAPS * CIN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
-  const int hd = op.kd / 2;
-  for (int td = 0; td < op.kd; ++td) {
-    const int dd = d + td - hd;
-    if (dd < 0 || dd >= op.D) continue;
+  for (int td = 0; td < KD; ++td) {
+    const int dd = d + td - KD / 2;
+    const bool d_ok = dd >= 0 && dd < op.D;
     const long im = (long)b * op.D + dd;
+#pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
       const int yy = y + (ty - 1) * op.dil;
-      if (yy < 0 || yy >= Hin) continue;
+#pragma unroll
       for (int tx = 0; tx < 3; ++tx) {
         const int xx = x + (tx - 1) * op.dil;
-        if (xx < 0 || xx >= Win) continue;
-        const int tap = (td * 3 + ty) * 3 + tx;
+        const bool ok = d_ok && yy >= 0 && yy < Hin && xx >= 0 && xx < Win;
         const long sp = (long)yy * Win + xx;
-        for (int c = 0; c < cin; ++c) {
-          float v;
-          if (c < op.cin0) {
-            const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
-            v = op.in0[o];
-            if (op.sub0) v -= op.sub0[o];
-          } else {
-            v = op.in1[im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          float v = 0.f;
+          if (ok) {
+            if (c < op.cin0) {
+              const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
+              v = __ldg(op.in0 + o);
+              if (op.sub0) v -= __ldg(op.sub0 + o);
+            } else {
+              v = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp);
+            }
           }
-          const float* wp = op.w + ((long)tap * cin + c) * op.cout + cg * 8;
-          const float4 wa = *reinterpret_cast<const float4*>(wp);
-          const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
-          acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]);
-          acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
-          acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]);
-          acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+          in[((td * 3 + ty) * 3 + tx) * CIN + c] = v;
         }
       }
     }
+  }
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
+#pragma unroll
+  for (int k = 0; k < TAPS * CIN; ++k) {
+    const float* wp = wsm_in + k * op.cout + cg * 8;
+    const float4 wa = *reinterpret_cast<const float4*>(wp);
+    const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+    const float v = in[k];
+    acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]);
+    acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
+    acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]);
+    acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
   }
   if (op.relu) {
 #pragma unroll
@@ -402,12 +439,21 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
 template <typename T>
 int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
+  const int cin = op.cin0 + op.cin1;
+  KD_CHECK(cin >= 1 && cin <= 4 && (op.kd == 1 || (op.kd == 3 && cin == 1)), "conv_few_in: unsupported cin=%d kd=%d", cin, op.kd);
   const long total = (long)op.H * op.W * (op.cout / 8);
   KD_CHECK(total < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
   const double fi_pix = (double)op.nimg * op.H * op.W;
-  ProfScope prof(PC_SMALL_CONV, s, 2.0 * fi_pix * op.cout * (op.cin0 + op.cin1) * 9 * op.kd,
-                 fi_pix * (4.0 * (op.cin0 + op.cin1) * (op.sub0 ? 2 : 1) + (double)op.cout * sizeof(T)));
-  k_conv_few_in<T><<<dim3(cdiv(total, 128), op.nimg), 128, 0, s>>>(op, Hin, Win);
+  ProfScope prof(PC_SMALL_CONV, s, 2.0 * fi_pix * op.cout * cin * 9 * op.kd,
+                 fi_pix * (4.0 * cin * (op.sub0 ? 2 : 1) + (double)op.cout * sizeof(T)));
+  const dim3 grid(cdiv(total, 128), op.nimg);
+  const size_t smem = sizeof(float) * (size_t)op.kd * 9 * cin * op.cout;
+  KD_CHECK(smem <= 48 * 1024, "conv_few_in: weights do not fit shared memory");
+  if (op.kd == 3) k_conv_few_in<T, 1, 3><<<grid, 128, smem, s>>>(op, Hin, Win);
+  else if (cin == 1) k_conv_few_in<T, 1, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
+  else if (cin == 2) k_conv_few_in<T, 2, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
+  else if (cin == 3) k_conv_few_in<T, 3, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
+  else k_conv_few_in<T, 4, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

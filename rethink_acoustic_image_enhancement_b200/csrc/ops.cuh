@@ -44,7 +44,7 @@ int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
 template <typename T> int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s);
 int mdta_gram_splits(int HW, int nimg_heads);
 // softmax(normalised Gram * temperature) folded into project_out: Mb[img][n][head*ch + j] = sum_i Wp[n][head*ch+i]*attn[i][j]
-template <typename T> int mdta_fold(const float* part, int nimg, int C, int heads, int splits, const float* temperature,
+template <typename T> int mdta_fold(float* part /* split 0 is overwritten with the softmax */, int nimg, int C, int heads, int splits, const float* temperature,
                                     const float* wproj /*[C][C] fp32*/, T* mb, long mb_ld, long mb_img_stride, cudaStream_t s);
 
 // direct convolutions for very small channel counts (CUDA cores, HBM-bound)

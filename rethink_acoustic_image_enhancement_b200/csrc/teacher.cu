@@ -34,6 +34,7 @@ struct TeacherW {
   T *up4, *up3, *up2, *upen;          // [2C][9][C], rows packed sub-pixel major
   T *reduce3, *reduce2;               // 1x1 over the [upsampled, skip] concat
   float *output, *output_param, *output2, *cen, *outputen;
+  T *output_tc, *output2_tc, *outputen_tc;   // bf16 path: [oc][9][C] for the tcgen05 3x3 kernel with the planar-fp32 epilogue
 };
 
 template <typename T>
@@ -80,10 +81,14 @@ void layout_teacher(const kdlae_teacher_cfg& c, Bump& b, TeacherW<T>& w) {
   w.up2 = b.take<T>((size_t)(4 * d) * 9 * 2 * d);
   blocks(w.dec1, c.num_blocks[0], 1, 0);            // dim*2 channels with heads[0] (KDLAE_model.py:246)
   blocks(w.refine, c.num_refinement_blocks, 1, 0);
+  const bool tc = std::is_same<T, bf16>::value;
   w.output = b.take<float>((size_t)oc * 9 * 2 * d);
+  w.output_tc = tc ? b.take<T>((size_t)oc * 9 * 2 * d) : nullptr;
   w.output_param = b.take<float>((size_t)9 * (oc + 1) * 2 * d);
   blocks(w.refine_out, c.num_refinement_blocks, 1, 0);
   w.output2 = b.take<float>((size_t)oc * 9 * 2 * d);
+  w.output2_tc = tc ? b.take<T>((size_t)oc * 9 * 2 * d) : nullptr;
+  w.outputen_tc = nullptr;
   w.cen = w.outputen = nullptr;
   w.upen = nullptr;
   if (c.sr_head) {
@@ -91,6 +96,7 @@ void layout_teacher(const kdlae_teacher_cfg& c, Bump& b, TeacherW<T>& w) {
     w.upen = b.take<T>((size_t)(4 * d) * 9 * 2 * d);
     blocks(w.enhance, c.num_refinement_blocks, 0, 0);
     w.outputen = b.take<float>((size_t)oc * 9 * d);
+    w.outputen_tc = tc ? b.take<T>((size_t)oc * 9 * d) : nullptr;
   }
 }
 
@@ -230,6 +236,26 @@ int conv3x3(const T* a, int cin, long lda, const T* w, int cout, int nimg, int H
   return conv_gemm<T>(g, s);
 }
 
+// 3x3 conv to <= 4 planar fp32 output channels (+ planar residual): tcgen05 implicit GEMM (N padded to 16 inside the MMA)
+// in the bf16 path, CUDA-core direct conv otherwise
+template <typename T>
+int conv_to_planar(const T* in, int cin, long ld, const float* w_few, const T* w_tc, int cout, int nimg, int H, int W,
+                   const float* res, long res_img, long res_ch, float* out, long out_img, long out_ch, cudaStream_t s) {
+  if (w_tc != nullptr) {
+    ConvOp g;
+    g.a0 = in; g.c0 = cin; g.ld0 = ld; g.nimg = nimg; g.H = H; g.W = W; g.kh = 3; g.kw = 3;
+    g.w = w_tc; g.w_ld = 9L * cin; g.w_tap_ld = cin;
+    g.epi.mode = OUT_PLANAR_F32; g.epi.N = cout; g.epi.H = H; g.epi.W = W;
+    g.epi.planar_out = out; g.epi.planar_img = out_img; g.epi.planar_ch = out_ch;
+    g.epi.planar_res = res; g.epi.planar_res_img = res_img; g.epi.planar_res_ch = res_ch;
+    if (conv_gemm_tc_eligible(g)) return conv_gemm_tc(g, s);
+  }
+  SmallConvOut fo;
+  fo.in = in; fo.in_ld = ld; fo.cin = cin; fo.nimg = nimg; fo.H = H; fo.W = W; fo.k = 3; fo.w = w_few; fo.cout = cout;
+  fo.res = res; fo.res_img = res_img; fo.res_ch = res_ch; fo.out = out; fo.out_img = out_img; fo.out_ch = out_ch;
+  return conv_few_out<T>(fo, s);
+}
+
 struct WsLayout {
   size_t x1, d1, x2, x3, x4, d3, d2, s0, bufA, bufB, o1, rstd, mu, gram, mb, total;
 };
@@ -339,15 +365,15 @@ int teacher_pack(const kdlae_teacher_cfg& c, const float* const* tensors, int n_
   KD_TRY(pack_conv3<T>(cur.next(), w.up2, 4 * d, 2 * d, PACK_PIXEL_SHUFFLE, s));
   KD_TRY(blocks(w.dec1));
   KD_TRY(blocks(w.refine));
-  KD_TRY(pack_few_out(cur.next(), oc, 2 * d, 9, w.output, s));
+  { const float* src = cur.next(); KD_TRY(pack_few_out(src, oc, 2 * d, 9, w.output, s)); if (w.output_tc) KD_TRY(pack_conv3<T>(src, w.output_tc, oc, 2 * d, PACK_PLAIN, s)); }
   KD_TRY(pack_few_in(cur.next(), 2 * d, oc + 1, 9, nullptr, w.output_param, s));
   KD_TRY(blocks(w.refine_out));
-  KD_TRY(pack_few_out(cur.next(), oc, 2 * d, 9, w.output2, s));
+  { const float* src = cur.next(); KD_TRY(pack_few_out(src, oc, 2 * d, 9, w.output2, s)); if (w.output2_tc) KD_TRY(pack_conv3<T>(src, w.output2_tc, oc, 2 * d, PACK_PLAIN, s)); }
   if (c.sr_head) {
     KD_TRY(pack_few_in(cur.next(), 2 * d, oc, 9, nullptr, w.cen, s));
     KD_TRY(pack_conv3<T>(cur.next(), w.upen, 4 * d, 2 * d, PACK_PIXEL_SHUFFLE, s));
     KD_TRY(blocks(w.enhance));
-    KD_TRY(pack_few_out(cur.next(), oc, d, 9, w.outputen, s));
+    { const float* src = cur.next(); KD_TRY(pack_few_out(src, oc, d, 9, w.outputen, s)); if (w.outputen_tc) KD_TRY(pack_conv3<T>(src, w.outputen_tc, oc, d, PACK_PLAIN, s)); }
   }
   KD_CHECK(cur.i == n_tensors, "teacher_pack: consumed %d of %d tensors", cur.i, n_tensors);
   return 0;
@@ -434,23 +460,20 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
     KD_TRY(run_blocks<T>(w.dec1, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
     KD_TRY(run_blocks<T>(w.refine, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
     // 6. output 3x3 2d -> oc ; denoise-rate tail (:314-321)
-    SmallConvOut fo;
-    fo.in = d1; fo.in_ld = 2 * d; fo.cin = 2 * d; fo.nimg = n; fo.H = H; fo.W = W; fo.k = 3; fo.w = w.output; fo.cout = oc;
+    KD_CHECK(ic == oc, "KDLAE_teacher: out + inp_img needs inp_channels == out_channels");
+    const float* last_w = w.output; const T* last_w_tc = w.output_tc;
     if (c.params_cat) {
-      fo.out = o1; fo.out_img = oc * HW; fo.out_ch = HW;
-      KD_TRY(conv_few_out<T>(fo, s));
+      KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, w.output, w.output_tc, oc, n, H, W, nullptr, 0, 0, o1, oc * HW, HW, s));
       fi = SmallConv();
       fi.in0 = o1; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc;
       fi.in1 = rate_b; fi.in1_img = HW; fi.in1_ch = HW; fi.cin1 = 1;
       fi.nimg = n; fi.H = H; fi.W = W; fi.dil = 2; fi.w = w.output_param; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
       KD_TRY(conv_few_in<T>(fi, s));
       KD_TRY(run_blocks<T>(w.refine_out, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
-      fo.w = w.output2;
+      last_w = w.output2; last_w_tc = w.output2_tc;
     }
-    fo.res = img_b; fo.res_img = ic * HW; fo.res_ch = HW;   // out_hq = out + inp_img (:321)
-    fo.out = hq_b; fo.out_img = oc * HW; fo.out_ch = HW;
-    KD_CHECK(ic == oc, "KDLAE_teacher: out + inp_img needs inp_channels == out_channels");
-    KD_TRY(conv_few_out<T>(fo, s));
+    // out_hq = out + inp_img (:321)
+    KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, last_w, last_w_tc, oc, n, H, W, img_b, ic * HW, HW, hq_b, oc * HW, HW, s));
     // 7. SR head (:324-329): cen -> upen (PixelShuffle) -> enhance -> outputen
     if (c.sr_head) {
       fi = SmallConv();
@@ -459,10 +482,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       KD_TRY(conv_few_in<T>(fi, s));
       KD_TRY(conv3x3<T>(d1, 2 * d, 2 * d, w.upen, 4 * d, n, H, W, OUT_PIXEL_SHUFFLE, s0, d, 0, s));
       KD_TRY(run_blocks<T>(w.enhance, lnb, s0, d, s0, d, n, 2 * H, 2 * W, sc, s));
-      fo = SmallConvOut();
-      fo.in = s0; fo.in_ld = d; fo.cin = d; fo.nimg = n; fo.H = 2 * H; fo.W = 2 * W; fo.k = 3; fo.w = w.outputen; fo.cout = oc;
-      fo.out = sr_b; fo.out_img = oc * HW * 4; fo.out_ch = HW * 4;
-      KD_TRY(conv_few_out<T>(fo, s));
+      KD_TRY(conv_to_planar<T>(s0, d, d, w.outputen, w.outputen_tc, oc, n, 2 * H, 2 * W, nullptr, 0, 0, sr_b, oc * HW * 4, HW * 4, s));
     }
   }
   return 0;
