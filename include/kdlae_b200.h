@@ -128,6 +128,12 @@ size_t kdlae_dwconv_tc_weight_bytes(int C, int gate);
 int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scratch, int nimg, int H, int W, int C, int gate,
                        void* stream);
 
+/* Fused LayerNorm-folded 1x1 conv -> depthwise 3x3 (-> GELU gate) (KDLAE_model.py:95-104 / :118-119), bf16 tcgen05:
+ * out = dw3x3(rstd[p] * (x . w1^T)) [gate: gelu(.[:Nt/2]) * .[Nt/2:]].  x [nimg,H,W,C] bf16, w1 [Nt][C] bf16,
+ * w9c [9][Nt] fp32, wtc_scratch kdlae_dwconv_tc_weight_bytes(Nt, gate) bytes, out [nimg,H,W,Nt or Nt/2] bf16. */
+int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* wtc_scratch, void* out, int nimg,
+                  int H, int W, int C, int gate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

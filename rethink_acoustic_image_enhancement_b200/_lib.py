@@ -73,6 +73,8 @@ SIGNATURES = {
     "kdlae_dwconv_tc_weight_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "kdlae_dwconv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "kdlae_pwdw_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

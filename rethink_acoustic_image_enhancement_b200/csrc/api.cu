@@ -22,7 +22,8 @@ static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_event_pool;
 static size_t g_pool_used = 0;
 static const char* kProfNames[PC_COUNT] = {"conv_gemm_tcgen05", "conv_gemm_simt", "dwconv3x3", "ln_stats", "mdta_gram",
-                                           "mdta_softmax_fold", "small_channel_conv", "pool_resample", "gap_mlp_head"};
+                                           "mdta_softmax_fold", "small_channel_conv", "pool_resample", "gap_mlp_head",
+                                           "fused_conv1x1_dwconv3x3_tcgen05"};
 
 static cudaEvent_t prof_event() {
   if (g_pool_used == g_event_pool.size()) {
@@ -279,6 +280,16 @@ int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scr
   const long ldo = gate ? C / 2 : C;
   return kd::dwconv3x3<bf16>(reinterpret_cast<const bf16*>(x), C, reinterpret_cast<bf16*>(out), ldo, w9c, nullptr, nimg, H, W, C,
                              gate, s, wtc_scratch);
+}
+
+int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* wtc_scratch, void* out, int nimg,
+                  int H, int W, int C, int gate, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && rstd && w1 && w9c && wtc_scratch && out, "kdlae_pwdw_tc: NULL argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  KD_TRY(kd::pack_dw_tc(w9c, Nt, gate, wtc_scratch, s));
+  return kd::pwdw_tc(reinterpret_cast<const bf16*>(x), C, rstd, reinterpret_cast<const bf16*>(w1), Nt, wtc_scratch,
+                     reinterpret_cast<bf16*>(out), gate ? Nt / 2 : Nt, nimg, H, W, C, gate, s);
 }
 
 }  // extern "C"

@@ -48,6 +48,7 @@ inline void count_launch() { ++g_launch_count; }
 // ---- optional per-kernel-class CUDA-event profiler (bench.py roofline; off by default) ----------
 enum ProfClass {
   PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_DWCONV, PC_LN_STATS, PC_MDTA_GRAM, PC_MDTA_FOLD, PC_SMALL_CONV, PC_POOL_RESAMPLE, PC_HEAD,
+  PC_PWDW,
   PC_COUNT
 };
 struct ProfScope {

@@ -42,8 +42,10 @@ constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SL
 constexpr int TC_STORE_BAR_THREADS = TC_EPI_WARPS * 32 + 32;
 
 struct TcParams {
-  int spatial;          // 0: linear rows (1x1), 1: 16x8 patches with 3x3 taps
+  int spatial;          // 0: linear rows (1x1), 1: 16x8 patches with 3x3 (x3) taps
   int taps, kw, dil;
+  int kd, D;            // 3-D convs (Conv3d 3x3x3): temporal taps and frames per batch element (5-D A tensor map)
+  float inv_D;
   int kc0, kc1;         // 64-wide K chunks per tap from source 0 / 1
   int c0;               // weight column offset of source 1
   long w_tap_ld;
@@ -156,8 +158,11 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       uint32_t kidx = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const TileCoord t = tile_coord(p, item);
+        int fb = 0, fd = 0;                       // 3-D: batch element and frame of this tile's image index
+        if (p.kd == 3) { fb = fast_div(t.img, p.D, p.inv_D); fd = t.img - fb * p.D; }
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int dx = (tap % p.kw - p.kw / 2) * p.dil, dy = (tap / p.kw - p.kw / 2) * p.dil;
+          const int dx = (tap % p.kw - p.kw / 2) * p.dil, dy = ((tap / p.kw) % 3 - p.kw / 2) * p.dil;
+          const int dd = (p.kd == 3) ? tap / 9 - 1 : 0;
           for (int kc = 0; kc < kchunks; ++kc, ++kidx) {
             const int s = kidx % TC_STAGES;
             const uint32_t ph = (kidx / TC_STAGES) & 1;
@@ -168,7 +173,8 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const bool src1 = kc >= p.kc0;
             const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
             const int cc = (src1 ? kc - p.kc0 : kc) * TC_BK;
-            if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, t.img);
+            if (p.kd == 3) tma_load_5d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, fd + dd, fb);
+            else if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, t.img);
             else tma_load_3d(a_dst, ma, full_bar(s), cc, t.r0, t.g);
             const int wk = (int)(tap * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
             tma_load_3d(b_dst, &map_w, full_bar(s), wk, t.nchunk * p.nc, t.g);
@@ -424,11 +430,12 @@ cudaError_t set_smem_attr() {
 bool conv_gemm_tc_eligible(const ConvOp& op) {
   const bool k11 = (op.kd == 1 && op.kh == 1 && op.kw == 1);
   const bool k33 = (op.kd == 1 && op.kh == 3 && op.kw == 3);
-  if (!k11 && !k33) return false;
+  const bool k333 = (op.kd == 3 && op.kh == 3 && op.kw == 3 && op.dil == 1 && op.c1 == 0 && op.D >= 1 && op.nimg % op.D == 0);
+  if (!k11 && !k33 && !k333) return false;
   if (op.c0 % 8 || op.ld0 % 8 || (reinterpret_cast<uintptr_t>(op.a0) & 15)) return false;
   if (op.c1 > 0 && (op.c1 % 8 || op.ld1 % 8 || (reinterpret_cast<uintptr_t>(op.a1) & 15))) return false;
   if (op.w_ld % 8 || op.w_tap_ld % 8 || (reinterpret_cast<uintptr_t>(op.w) & 15) || op.w_group_stride % 8) return false;
-  if (k33 && op.groups != 1) return false;
+  if ((k33 || k333) && op.groups != 1) return false;
   if (k11 && op.epi.mode != OUT_IDENTITY) return false;
   if (op.epi.mode == OUT_PIXEL_SHUFFLE && (op.epi.cq % 8 != 0)) return false;
   return true;
@@ -445,8 +452,9 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.spatial = (op.kh == 3) ? 1 : 0;
-  p.taps = op.kh * op.kw;
+  p.taps = op.kd * op.kh * op.kw;
   p.kw = op.kw;
+  p.kd = op.kd; p.D = op.D; p.inv_D = 1.0f / (float)(op.D > 0 ? op.D : 1);
   p.dil = op.dil;
   p.kc0 = (op.c0 + TC_BK - 1) / TC_BK;
   p.kc1 = (op.c1 + TC_BK - 1) / TC_BK;
@@ -490,7 +498,15 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     p.tiles_per_group = cdiv(p.rows_per_group, TC_BM);
     tiles_m = (long)p.tiles_per_group * op.groups;
   }
-  KD_TRY(act_map(&ma0, op.a0, op.c0, op.ld0, TC_BK));
+  if (op.kd == 3) {   // 5-D {C, W, H, frames, batch}: the temporal zero padding is TMA out-of-bounds fill as well
+    const cuuint64_t dims[5] = {(cuuint64_t)op.c0, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.D, (cuuint64_t)(op.nimg / op.D)};
+    const cuuint64_t f = (cuuint64_t)op.ld0 * 2 * op.W * op.H;
+    const cuuint64_t str[4] = {(cuuint64_t)op.ld0 * 2, (cuuint64_t)op.ld0 * 2 * op.W, f, f * op.D};
+    const cuuint32_t box[5] = {TC_BK, TC_TW, TC_TH, 1, 1};
+    KD_TRY(make_map(&ma0, op.a0, 5, dims, str, box));
+  } else {
+    KD_TRY(act_map(&ma0, op.a0, op.c0, op.ld0, TC_BK));
+  }
   if (op.c1 > 0) KD_TRY(act_map(&ma1, op.a1, op.c1, op.ld1, TC_BK));
   else ma1 = ma0;
   if (fast) {

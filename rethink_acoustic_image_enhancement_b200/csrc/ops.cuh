@@ -38,6 +38,10 @@ template <typename T> int dwconv3x3(const T* x, long ldx, T* out, long ldo, cons
                                     int nimg, int H, int W, int C, int gate, cudaStream_t s, const void* wtc = nullptr);
 size_t dwconv_tc_weight_bytes(int C, int gate);
 int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
+// fused LN-folded 1x1 conv -> depthwise 3x3 (-> GELU gate), bf16 tcgen05 (pwdw_tc.cu)
+bool pwdw_tc_eligible(int C, int Nt, int gate);
+int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const void* wtc, bf16* out, long ldo, int nimg,
+            int H, int W, int C, int gate, cudaStream_t s);
 
 // MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
 // qk: [nimg*HW, ld] with q at channel 0 and k at channel C.  part: [nimg][heads][splits][ch*ch + 2*ch] fp32

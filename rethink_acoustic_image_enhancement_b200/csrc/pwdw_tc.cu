@@ -1,0 +1,366 @@
+// Fused  LayerNorm-folded 1x1 conv  ->  depthwise 3x3  (-> GELU gate)  on tcgen05, bf16 path.
+//   qkv branch  (KDLAE_model.py:118-119):  qkv' = dw3x3(W_qkv . LN(x))
+//   GDFN branch (KDLAE_model.py:95-104):   g    = gelu(dw(t)[:h]) * dw(t)[h:],  t = W_in . LN(x)
+// The 3C / 2h wide intermediate t is the largest tensor of a TransformerBlock; here it only ever exists as a
+// 6 x 32 pixel shared-memory tile.  Per CTA (bound to one 64-channel block of the output), per 4 x 30 pixel tile:
+//   1. TMA: x tile with halo {C, 32 px, 6 rows} (zero fill outside the image = the conv's zero padding)
+//   2. MMA1 (tcgen05, M=128 x2, N=64|128, K=C):  T = X . W1^T  -> TMEM        (halo rows recomputed: 1.5x of a tiny GEMM)
+//   3. epilogue 1: tcgen05.ld, * rstd[pixel] (BiasFree LayerNorm folded: gamma in W1, rstd here), bf16, st.shared into
+//      the 128B-swizzled K-major t tile with a row pitch of 32 pixels
+//   4. MMA2: the depthwise conv as 9 shifted-descriptor MMAs (M=128, N=16, K=16) per 16-channel group against
+//      diagonal weight blocks (see dwconv_tc.cu)                              -> TMEM
+//   5. epilogue 2: (gate) gelu(x1)*x2, bf16, staged [4][30][64] -> one TMA store.
+// Warp roles: 0 TMA producer, 1 MMA issuer (MMA1 + MMA2 of half 0), 2 MMA issuer (MMA2 of half 1, gate only),
+// 3..10 epilogue.  Weights (W1 block, diagonal dw blocks) are resident in smem for the CTA's lifetime.
+#include <algorithm>
+#include "sm100.cuh"
+
+namespace kd {
+
+namespace {
+
+constexpr int PD_TW = 32, PD_OW = 30, PD_OH = 4, PD_IH = 6, PD_CB = 64;
+constexpr uint32_t PD_XCHUNK = PD_TW * PD_IH * 128;          // 24576: one 64-channel K chunk of the x tile
+constexpr uint32_t PD_TSLOT = PD_XCHUNK + 1024;              // t tile of one half (+ slack for shifted reads)
+constexpr uint32_t PD_DWB = 4 * 3 * 2048;                    // diagonal dw blocks per half
+constexpr uint32_t PD_STAGE_OUT = PD_OW * PD_OH * 128;       // 15360: output staging [4][30][64 ch]
+// epilogue warps: the gate variant is bound by CUDA-core epilogue work (192x128 scalings + 120x64 GELUs per tile), so it
+// gets 16 warps on its single CTA per SM; the non-gate variant keeps 8 and runs 2 CTAs per SM
+template <int GATE> struct PdCfg {
+  static constexpr int EPW = GATE ? 16 : 8, THREADS = (3 + EPW) * 32, CW = 64 / (EPW / 4);   // CW: channels per warp per half
+};
+
+struct PdParams {
+  int H, W, C, Nt, Cout, nimg;     // Nt = rows of W1 (3C or 2hp); Cout = output channels (3C or hp)
+  int kc;                          // 64-wide K chunks of C (1 or 2)
+  int tiles_x, tiles_y, cblocks;
+  long tiles_per_cb;
+  float inv_tiles_x, inv_tiles_y;
+  const float* rstd;               // [nimg*H*W]
+};
+
+__device__ __forceinline__ float gelu_as2(float x) {   // exact GELU via A&S 7.1.26 erf (see dwconv_tc.cu)
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  y *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+  const float erf_x = copysignf(fmaf(-y, e, 1.0f), x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_x, hx);
+}
+
+template <int GATE>
+__global__ void __launch_bounds__(PdCfg<GATE>::THREADS, GATE ? 1 : 2)
+k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+          const __grid_constant__ CUtensorMap map_out, const uint8_t* __restrict__ wtc, const PdParams p) {
+  constexpr int NH = GATE ? 2 : 1;
+  constexpr int N1 = 64 * NH;                       // MMA1 N: t channels of this block (both halves for the gate)
+  constexpr int EPW = PdCfg<GATE>::EPW, CW = PdCfg<GATE>::CW;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // smem carve-up (all 1024-aligned): W1 [kc][NH][64 rows][128 B] | dw blocks | x chunks | t tiles | out staging | barriers
+  const uint32_t w1_base = sbase;
+  const uint32_t dwb_base = w1_base + p.kc * NH * 8192;
+  const uint32_t x_base = dwb_base + NH * PD_DWB;
+  const uint32_t t_base = x_base + p.kc * PD_XCHUNK;
+  const uint32_t o_base = t_base + NH * PD_TSLOT;
+  const uint32_t bar_base = o_base + 16384;
+  const uint32_t w_bar = bar_base, x_full = bar_base + 8, x_empty = bar_base + 16, d1_full = bar_base + 24,
+                 t_ready = bar_base + 32, d2_full = bar_base + 40, tmem_slot = bar_base + 48;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* t_gen = smem_raw + (t_base - smem_u32(smem_raw));
+  uint8_t* o_gen = smem_raw + (o_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cb = blockIdx.x % p.cblocks;
+  const int cta_in_cb = blockIdx.x / p.cblocks;
+  const int ctas_in_cb = (gridDim.x - cb + p.cblocks - 1) / p.cblocks;
+  const int hp = p.Nt / 2;
+  const int ch_valid = min(PD_CB, p.Cout - cb * PD_CB);
+  const int ngroups = (ch_valid + 15) / 16;
+  const int ksteps = (p.C + 15) / 16;               // K = 16 MMA steps over the C input channels
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out);
+    mbar_init(w_bar, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(d1_full, 1);
+    mbar_init(t_ready, 1); mbar_init(d2_full, NH);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(GATE ? 512 : 256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t d1_col = 0;                        // D1: 2 M-tiles x N1 columns
+  const uint32_t d2_col = 2 * N1;                   // D2: NH x 64 columns
+
+  auto tile_xy = [&](long t64, int& img, int& y0, int& x0) {
+    const int t = (int)t64;
+    const int rowt = fast_div(t, p.tiles_x, p.inv_tiles_x);
+    const int txi = t - rowt * p.tiles_x;
+    img = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
+    const int tyi = rowt - img * p.tiles_y;
+    x0 = txi * PD_OW; y0 = tyi * PD_OH;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights: W1 rows of this block (per K chunk, per half) and the diagonal depthwise blocks
+      mbar_expect_tx(w_bar, p.kc * NH * 8192 + NH * PD_DWB);
+      for (int k = 0; k < p.kc; ++k)
+        for (int h = 0; h < NH; ++h)
+          tma_load_3d(w1_base + (k * NH + h) * 8192, &map_w1, w_bar, k * 64, (GATE ? h * hp : 0) + cb * PD_CB, 0);
+      for (int h = 0; h < NH; ++h) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dwb_base + h * PD_DWB), "l"(wtc + ((size_t)h * p.cblocks + cb) * PD_DWB), "r"(PD_DWB), "r"(w_bar) : "memory");
+      }
+      uint32_t it = 0;
+      for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
+        mbar_wait_relaxed(x_empty, (it & 1) ^ 1);
+        int img, y0, x0;
+        tile_xy(t, img, y0, x0);
+        mbar_expect_tx(x_full, p.kc * PD_XCHUNK);
+        for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * PD_XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
+      }
+    }
+  } else if (warp == 1 || (GATE && warp == 2)) {
+    // ===================== MMA issuers =====================
+    if (lane == 0) {
+      const int h = warp - 1;
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lo_tag = 1u << 16;
+      mbar_wait(w_bar, 0);
+      auto issue_mma1 = [&](uint32_t it) {          // T = X . W1^T for both M tiles (pixels 0..127, 128..255)
+        mbar_wait(x_full, it & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < 2; ++mt) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int k = ks >> 2, kk = ks & 3;
+            const uint32_t a_lo = (((x_base + k * PD_XCHUNK + mt * 16384 + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+            const uint32_t b_lo = (((w1_base + k * NH * 8192 + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+            umma_bf16_lohi(tmem_base + d1_col + mt * N1, a_lo, b_lo, desc_hi, idesc1, ks != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(x_empty);      // x tile consumed
+        umma_commit(d1_full);      // T accumulators ready for epilogue 1
+      };
+      const uint32_t t_lo0 = (((t_base + h * PD_TSLOT) & 0x3FFFF) >> 4) | lo_tag;
+      const uint32_t b_lo0 = (((dwb_base + h * PD_DWB) & 0x3FFFF) >> 4) | lo_tag;
+      uint32_t it = 0;
+      if (h == 0 && cta_in_cb < p.tiles_per_cb) issue_mma1(0);
+      for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
+        mbar_wait(t_ready, it & 1);                 // epilogue 1 of tile `it` stored the t tile (and drained D1, and D2 is free)
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < ngroups) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap % 3;
+              const uint32_t a_lo = t_lo0 + (uint32_t)((dy * PD_TW + dx) * 8 + g * 2);
+              const uint32_t b_lo = b_lo0 + (uint32_t)((g * 6144 + (tap >> 2) * 2048 + (tap & 3) * 32) >> 4);
+              umma_bf16_lohi(tmem_base + d2_col + h * PD_CB + g * 16, a_lo, b_lo, desc_hi, idesc2, tap != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(d2_full);
+        if (h == 0 && t + ctas_in_cb < p.tiles_per_cb) issue_mma1(it + 1);   // next tile's 1x1 overlaps epilogue 2
+      }
+    }
+  } else if (warp >= 3) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 3;
+    const int quarter = warp & 3;
+    const int cw = ew >> 2;                   // column group: channels [cw*CW, +CW) of each chunk(2) half
+    const int r = quarter * 32 + lane;        // TMEM lane = row of the M tile
+    const int oy_l = r / PD_TW, ox_l = r % PD_TW;
+    const int opix = oy_l * PD_OW + ox_l;
+    const bool in_box = ox_l < PD_OW;
+    uint32_t it = 0;
+    for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
+      int img, y0, x0;
+      tile_xy(t, img, y0, x0);
+      // ---------- epilogue 1: T (fp32, TMEM) * rstd -> bf16 t tile in smem ----------
+      float rs[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int pix = mt * 128 + r;           // pixel of the 6 x 32 halo tile
+        const int y = y0 - 1 + pix / PD_TW, x = x0 - 1 + pix % PD_TW;
+        const bool inimg = pix < PD_TW * PD_IH && y >= 0 && y < p.H && x >= 0 && x < p.W;
+        rs[mt] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;   // 0 outside: conv zero padding of t
+      }
+      mbar_wait_relaxed(d1_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt == 1 && quarter >= 2) continue;  // pixels 192..255 do not exist (warp-uniform)
+        const int pix = mt * 128 + r;
+        const uint32_t t_row = tmem_base + d1_col + mt * N1 + ((uint32_t)(quarter * 32) << 16);
+        uint32_t v[NH * (CW / 16)][16];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int u = 0; u < CW / 16; ++u) tmem_ld16_issue(t_row + h * 64 + cw * CW + u * 16, v[h * (CW / 16) + u]);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          uint8_t* trow = t_gen + h * PD_TSLOT + pix * 128;
+#pragma unroll
+          for (int u = 0; u < CW / 16; ++u) {
+            uint32_t (&vv)[16] = v[h * (CW / 16) + u];
+            tmem_ld16_wait(vv);
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int o = c2 * 8;
+              uint4 w4;
+              w4.x = pack_bf16x2(__uint_as_float(vv[o + 0]) * rs[mt], __uint_as_float(vv[o + 1]) * rs[mt]);
+              w4.y = pack_bf16x2(__uint_as_float(vv[o + 2]) * rs[mt], __uint_as_float(vv[o + 3]) * rs[mt]);
+              w4.z = pack_bf16x2(__uint_as_float(vv[o + 4]) * rs[mt], __uint_as_float(vv[o + 5]) * rs[mt]);
+              w4.w = pack_bf16x2(__uint_as_float(vv[o + 6]) * rs[mt], __uint_as_float(vv[o + 7]) * rs[mt]);
+              const int chunk = (cw * CW + u * 16) / 8 + c2;
+              *reinterpret_cast<uint4*>(trow + ((chunk ^ (pix & 7)) << 4)) = w4;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");   // t tile complete (also: previous store was read out)
+      if (ew == 0 && lane == 0) mbar_arrive(t_ready);
+      // ---------- epilogue 2: depthwise result (TMEM) -> (gate) -> staged -> TMA store ----------
+      mbar_wait_relaxed(d2_full, it & 1);
+      tc_fence_after();
+      {
+        const uint32_t t_row = tmem_base + d2_col + ((uint32_t)(quarter * 32) << 16) + cw * CW;
+        uint32_t a[CW / 16][16], b[CW / 16][16];
+#pragma unroll
+        for (int u = 0; u < CW / 16; ++u) {
+          if (cw * CW + u * 16 < ch_valid) {      // warp-uniform
+            tmem_ld16_issue(t_row + u * 16, a[u]);
+            if (GATE) tmem_ld16_issue(t_row + PD_CB + u * 16, b[u]);
+          }
+        }
+        uint8_t* srow = o_gen + opix * 128;
+#pragma unroll
+        for (int u = 0; u < CW / 16; ++u) {
+          if (cw * CW + u * 16 < ch_valid) {
+            tmem_ld16_wait(a[u]);
+            if (GATE) tmem_ld16_wait(b[u]);
+            if (in_box) {
+#pragma unroll
+              for (int v8 = 0; v8 < 2; ++v8) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float x1 = __uint_as_float(a[u][v8 * 8 + i]);
+                  f[i] = GATE ? gelu_as2(x1) * __uint_as_float(b[u][v8 * 8 + i]) : x1;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                const int chunk = (cw * CW + u * 16) / 8 + v8;
+                *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(EPW * 32) : "memory");   // output tile staged
+      if (ew == 0 && lane == 0) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&map_out), "r"(o_base), "r"(cb * PD_CB), "r"(x0), "r"(y0), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free before this thread joins "bar.sync 1"
+      }
+    }
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(GATE ? 512 : 256));
+  }
+}
+
+int g_pd_sms = 0;
+
+}  // namespace
+
+bool pwdw_tc_eligible(int C, int Nt, int gate) {
+  return C % 16 == 0 && C >= 16 && C <= 128 && Nt % 8 == 0 && (!gate || Nt % 16 == 0);
+}
+
+// x [nimg,H,W,C] (row stride ldx) --1x1 (w1: [Nt][C] bf16, LayerNorm gamma folded), * rstd--> t --dw3x3 (wtc)--> [gate] --> out
+int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const void* wtc, bf16* out, long ldo, int nimg,
+            int H, int W, int C, int gate, cudaStream_t s) {
+  KD_CHECK(pwdw_tc_eligible(C, Nt, gate), "pwdw_tc: shape not eligible (C=%d Nt=%d)", C, Nt);
+  KD_CHECK(!(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && !(reinterpret_cast<uintptr_t>(w1) & 15) &&
+               !(reinterpret_cast<uintptr_t>(wtc) & 15) && ldx % 8 == 0 && ldo % 8 == 0,
+           "pwdw_tc: misaligned operands");
+  PdParams p;
+  p.H = H; p.W = W; p.C = C; p.Nt = Nt; p.Cout = gate ? Nt / 2 : Nt; p.nimg = nimg;
+  p.kc = (C + 63) / 64;
+  p.tiles_x = cdiv(W, PD_OW); p.tiles_y = cdiv(H, PD_OH); p.cblocks = cdiv(p.Cout, PD_CB);
+  p.tiles_per_cb = (long)nimg * p.tiles_x * p.tiles_y;
+  KD_CHECK(p.tiles_per_cb < (1L << 24), "pwdw_tc: too many tiles");
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  p.rstd = rstd;
+  const int NH = gate ? 2 : 1;
+  const uint32_t smem = 1024 + p.kc * NH * 8192 + NH * PD_DWB + p.kc * PD_XCHUNK + NH * PD_TSLOT + 16384 + 128;
+  static bool attr = false;
+  if (!attr) {
+    int dev = 0;
+    KD_CUDA(cudaGetDevice(&dev));
+    KD_CUDA(cudaDeviceGetAttribute(&g_pd_sms, cudaDevAttrMultiProcessorCount, dev));
+    KD_CUDA(cudaFuncSetAttribute(k_pwdw_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KD_CUDA(cudaFuncSetAttribute(k_pwdw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  KD_CHECK(smem <= 227 * 1024, "pwdw_tc: shared memory budget exceeded (%u)", smem);
+  CUtensorMap map_x, map_w1, map_out;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
+    const cuuint32_t box[4] = {64, PD_TW, PD_IH, 1};
+    KD_TRY(make_map(&map_x, x, 4, dims, str, box));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Nt, 1};
+    const cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * Nt};
+    const cuuint32_t box[3] = {64, 64, 1};
+    KD_TRY(make_map(&map_w1, w1, 3, dims, str, box));
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    const cuuint64_t str[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)ldo * 2 * W, (cuuint64_t)ldo * 2 * W * H};
+    const cuuint32_t box[4] = {PD_CB, PD_OW, PD_OH, 1};
+    KD_TRY(make_map(&map_out, out, 4, dims, str, box));
+  }
+  // one launch does the work of conv_gemm (1x1) + dwconv3x3: report it under its own class
+  const double pix = (double)nimg * H * W;
+  ProfScope prof(PC_PWDW, s, 2.0 * pix * Nt * C + 18.0 * pix * Nt, pix * (C + p.Cout) * 2.0 + 4.0 * pix + 2.0 * Nt * C);
+  const int blocks_per_sm = (smem <= 110 * 1024 && !gate) ? 2 : 1;   // non-gate C<=64: 2 CTAs/SM fit smem and TMEM (256 cols)
+  int grid = (int)std::min<long>((long)p.cblocks * p.tiles_per_cb, (long)g_pd_sms * blocks_per_sm);
+  if (grid < p.cblocks) grid = p.cblocks;
+  if (gate) k_pwdw_tc<1><<<grid, PdCfg<1>::THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
+  else k_pwdw_tc<0><<<grid, PdCfg<0>::THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace kd

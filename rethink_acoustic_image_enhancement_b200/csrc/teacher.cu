@@ -5,6 +5,7 @@
 //   ln_stats -> [1x1 qkv GEMM, LN folded: weight into W, rstd as epilogue row scale] -> dw3x3
 //   -> Gram/norm reduction -> softmax folded into project_out (per-image CxC) -> [1x1 GEMM on v + residual]
 //   ln_stats -> [1x1 project_in GEMM, LN folded] -> dw3x3 + GELU gate -> [1x1 project_out GEMM + residual]
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 #include "models.cuh"
@@ -165,6 +166,15 @@ struct Scratch {
 
 // One TransformerBlock (KDLAE_model.py:159-163) over `nimg` images of H x W pixels, C channels.
 // x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
+// KDLAE_FUSE_PWDW=1 routes qkv->dw and project_in->dw->gate through the fused kernel (pwdw_tc.cu).  Measured on B200
+// (profiles/r01_summary.md): parity-identical, 23 % less HBM traffic, but 66 vs 79 images/s - its two epilogues are
+// CUDA-core issue bound - so the unfused schedule stays the default until the epilogue instruction count is cut.
+inline bool fuse_pwdw_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KDLAE_FUSE_PWDW"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
 // rows (C <= 256, one accumulator chunk), so only the first norm1 of a stage needs the stand-alone ln_stats pass.
 template <typename T>
@@ -178,13 +188,21 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   const bool fused_stats = epilogue_emits_stats<T>(C);
   // ---- x = x + project_out(attn(norm1(x))) ----
   if (!(have_stats && fused_stats)) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
+  const bool fuse = fuse_pwdw_enabled() && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
+                    pwdw_tc_eligible(C, 3 * C, 0) && pwdw_tc_eligible(C, 2 * w.hp, 1);
   ConvOp g;
-  g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
-  g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
-  g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.qkv_s1; g.epi.col_bias = w.qkv_s2;
-  g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
-  KD_TRY(conv_gemm<T>(g, s));
-  KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s, w.wdw_qkv_tc));
+  if (fuse) {
+    KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv_tc,
+                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
+  } else {
+    g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
+    g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
+    g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.qkv_s1; g.epi.col_bias = w.qkv_s2;
+    g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
+    KD_TRY(conv_gemm<T>(g, s));
+    KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s, w.wdw_qkv_tc));
+  }
   const int splits = mdta_gram_splits(HW, nimg * w.heads);
   KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
   KD_TRY(mdta_fold<T>(sc.gram, nimg, C, w.heads, splits, w.temp, w.wproj, sc.mb, C, (long)C * C, s));
@@ -196,13 +214,18 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   KD_TRY(conv_gemm<T>(g, s));
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
-  g = ConvOp();
-  g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
-  g.w = w.win; g.w_ld = C; g.w_tap_ld = C;
-  g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.in_s1; g.epi.col_bias = w.in_s2;
-  g.epi.out = sc.bufA; g.epi.out_ld = 2 * w.hp; g.epi.N = 2 * w.hp; g.epi.H = H; g.epi.W = W;
-  KD_TRY(conv_gemm<T>(g, s));
-  KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s, w.wdw_ffn_tc));
+  if (fuse) {
+    KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn_tc,
+                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
+  } else {
+    g = ConvOp();
+    g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
+    g.w = w.win; g.w_ld = C; g.w_tap_ld = C;
+    g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.in_s1; g.epi.col_bias = w.in_s2;
+    g.epi.out = sc.bufA; g.epi.out_ld = 2 * w.hp; g.epi.N = 2 * w.hp; g.epi.H = H; g.epi.W = W;
+    KD_TRY(conv_gemm<T>(g, s));
+    KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s, w.wdw_ffn_tc));
+  }
   g = ConvOp();
   g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w.wout; g.w_ld = w.hp; g.w_tap_ld = w.hp;
