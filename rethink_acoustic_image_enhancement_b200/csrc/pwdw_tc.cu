@@ -20,15 +20,10 @@ namespace kd {
 namespace {
 
 constexpr int PD_TW = 32, PD_OW = 30, PD_OH = 4, PD_IH = 6, PD_CB = 64;
-constexpr uint32_t PD_XCHUNK = PD_TW * PD_IH * 128;          // 24576: one 64-channel K chunk of the x tile
-constexpr uint32_t PD_TSLOT = PD_XCHUNK + 1024;              // t tile of one half (+ slack for shifted reads)
+constexpr uint32_t PD_XCHUNK = PD_TW * PD_IH * 128;          // 24576: one 64-channel K chunk of the x tile / one t tile
 constexpr uint32_t PD_DWB = 4 * 3 * 2048;                    // diagonal dw blocks per half
-constexpr uint32_t PD_STAGE_OUT = PD_OW * PD_OH * 128;       // 15360: output staging [4][30][64 ch]
-// epilogue warps: the gate variant is bound by CUDA-core epilogue work (192x128 scalings + 120x64 GELUs per tile), so it
-// gets 16 warps on its single CTA per SM; the non-gate variant keeps 8 and runs 2 CTAs per SM
-template <int GATE> struct PdCfg {
-  static constexpr int EPW = GATE ? 16 : 8, THREADS = (3 + EPW) * 32, CW = 64 / (EPW / 4);   // CW: channels per warp per half
-};
+constexpr int PD_GROUP_WARPS = 8;                            // warps per epilogue group
+constexpr int PD_THREADS = (3 + 2 * PD_GROUP_WARPS) * 32;    // producer, 2 issuers, epilogue-1 group, epilogue-2 group
 
 struct PdParams {
   int H, W, C, Nt, Cout, nimg;     // Nt = rows of W1 (3C or 2hp); Cout = output channels (3C or hp)
@@ -54,27 +49,32 @@ __device__ __forceinline__ float gelu_as2(float x) {   // exact GELU via A&S 7.1
   return fmaf(hx, erf_x, hx);
 }
 
+// Two tiles are in flight per CTA: while epilogue group 2 gates / stores tile i, epilogue group 1 already converts the
+// 1x1 result of tile i+1 and the tensor pipe runs MMA1(i+2) / MMA2(i+1).  t tiles and the depthwise accumulators are
+// double buffered; the consumed t tile doubles as the output staging buffer of its own tile.
 template <int GATE>
-__global__ void __launch_bounds__(PdCfg<GATE>::THREADS, GATE ? 1 : 2)
+__global__ void __launch_bounds__(PD_THREADS, 1)
 k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
           const __grid_constant__ CUtensorMap map_out, const uint8_t* __restrict__ wtc, const PdParams p) {
   constexpr int NH = GATE ? 2 : 1;
   constexpr int N1 = 64 * NH;                       // MMA1 N: t channels of this block (both halves for the gate)
-  constexpr int EPW = PdCfg<GATE>::EPW, CW = PdCfg<GATE>::CW;
+  constexpr int GT = PD_GROUP_WARPS * 32;           // threads per epilogue group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // smem carve-up (all 1024-aligned): W1 [kc][NH][64 rows][128 B] | dw blocks | x chunks | t tiles | out staging | barriers
+  // smem (all 1024-aligned): W1 [kc][NH][64 rows][128 B] | dw blocks | x chunks | t[2][NH] tiles (+1 KB slack) | barriers
   const uint32_t w1_base = sbase;
   const uint32_t dwb_base = w1_base + p.kc * NH * 8192;
   const uint32_t x_base = dwb_base + NH * PD_DWB;
   const uint32_t t_base = x_base + p.kc * PD_XCHUNK;
-  const uint32_t o_base = t_base + NH * PD_TSLOT;
-  const uint32_t bar_base = o_base + 16384;
-  const uint32_t w_bar = bar_base, x_full = bar_base + 8, x_empty = bar_base + 16, d1_full = bar_base + 24,
-                 t_ready = bar_base + 32, d2_full = bar_base + 40, tmem_slot = bar_base + 48;
+  const uint32_t bar_base = t_base + 2 * NH * PD_XCHUNK + 1024;
+  const uint32_t w_bar = bar_base, x_full = bar_base + 8, x_empty = bar_base + 16, d1_full = bar_base + 24, d1_empty = bar_base + 32;
+  auto t_ready = [&](int b) { return bar_base + 40 + 8u * b; };
+  auto t_free = [&](int b) { return bar_base + 56 + 8u * b; };
+  auto d2_full = [&](int b) { return bar_base + 72 + 8u * b; };
+  auto d2_empty = [&](int b) { return bar_base + 88 + 8u * b; };
+  const uint32_t tmem_slot = bar_base + 104;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* t_gen = smem_raw + (t_base - smem_u32(smem_raw));
-  uint8_t* o_gen = smem_raw + (o_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cb = blockIdx.x % p.cblocks;
@@ -84,11 +84,12 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   const int ch_valid = min(PD_CB, p.Cout - cb * PD_CB);
   const int ngroups = (ch_valid + 15) / 16;
   const int ksteps = (p.C + 15) / 16;               // K = 16 MMA steps over the C input channels
+  const int ntiles = (cta_in_cb < p.tiles_per_cb) ? (int)((p.tiles_per_cb - cta_in_cb + ctas_in_cb - 1) / ctas_in_cb) : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out);
-    mbar_init(w_bar, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(d1_full, 1);
-    mbar_init(t_ready, 1); mbar_init(d2_full, NH);
+    mbar_init(w_bar, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, PD_GROUP_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(t_ready(b), 1); mbar_init(t_free(b), 1); mbar_init(d2_full(b), NH); mbar_init(d2_empty(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -99,11 +100,11 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t d1_col = 0;                        // D1: 2 M-tiles x N1 columns
-  const uint32_t d2_col = 2 * N1;                   // D2: NH x 64 columns
+  const uint32_t d1_col = 0;                                       // D1: 2 M-tiles x N1 columns
+  auto d2_col = [&](int b) { return (uint32_t)(2 * N1 + b * NH * PD_CB); };   // D2[b]: NH x 64 columns
 
-  auto tile_xy = [&](long t64, int& img, int& y0, int& x0) {
-    const int t = (int)t64;
+  auto tile_xy = [&](int i, int& img, int& y0, int& x0) {          // i-th tile of this CTA
+    const int t = cta_in_cb + i * ctas_in_cb;
     const int rowt = fast_div(t, p.tiles_x, p.inv_tiles_x);
     const int txi = t - rowt * p.tiles_x;
     img = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
@@ -114,7 +115,6 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // resident weights: W1 rows of this block (per K chunk, per half) and the diagonal depthwise blocks
       mbar_expect_tx(w_bar, p.kc * NH * 8192 + NH * PD_DWB);
       for (int k = 0; k < p.kc; ++k)
         for (int h = 0; h < NH; ++h)
@@ -123,26 +123,29 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dwb_base + h * PD_DWB), "l"(wtc + ((size_t)h * p.cblocks + cb) * PD_DWB), "r"(PD_DWB), "r"(w_bar) : "memory");
       }
-      uint32_t it = 0;
-      for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
-        mbar_wait_relaxed(x_empty, (it & 1) ^ 1);
+      for (int i = 0; i < ntiles; ++i) {
         int img, y0, x0;
-        tile_xy(t, img, y0, x0);
+        if (i + 1 < ntiles) {   // the x tile is single buffered: keep the next one warm in L2
+          tile_xy(i + 1, img, y0, x0);
+          for (int k = 0; k < p.kc; ++k) tma_prefetch_4d(&map_x, k * 64, x0 - 1, y0 - 1, img);
+        }
+        mbar_wait_relaxed(x_empty, (i & 1) ^ 1);
+        tile_xy(i, img, y0, x0);
         mbar_expect_tx(x_full, p.kc * PD_XCHUNK);
         for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * PD_XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
       }
     }
-  } else if (warp == 1 || (GATE && warp == 2)) {
+  } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers =====================
-    if (lane == 0) {
+    if (lane == 0 && (warp == 1 || GATE)) {
       const int h = warp - 1;
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lo_tag = 1u << 16;
       mbar_wait(w_bar, 0);
-      auto issue_mma1 = [&](uint32_t it) {          // T = X . W1^T for both M tiles (pixels 0..127, 128..255)
-        mbar_wait(x_full, it & 1);
+      auto issue_mma1 = [&](int i) {                // T = X . W1^T for both M tiles (pixels 0..127, 128..255)
+        mbar_wait(x_full, i & 1);
         tc_fence_after();
         for (int mt = 0; mt < 2; ++mt) {
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -155,13 +158,19 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         umma_commit(x_empty);      // x tile consumed
         umma_commit(d1_full);      // T accumulators ready for epilogue 1
       };
-      const uint32_t t_lo0 = (((t_base + h * PD_TSLOT) & 0x3FFFF) >> 4) | lo_tag;
       const uint32_t b_lo0 = (((dwb_base + h * PD_DWB) & 0x3FFFF) >> 4) | lo_tag;
-      uint32_t it = 0;
-      if (h == 0 && cta_in_cb < p.tiles_per_cb) issue_mma1(0);
-      for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
-        mbar_wait(t_ready, it & 1);                 // epilogue 1 of tile `it` stored the t tile (and drained D1, and D2 is free)
+      if (h == 0 && ntiles > 0) issue_mma1(0);
+      for (int i = 0; i < ntiles; ++i) {
+        const int b = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        if (h == 0 && i + 1 < ntiles) {             // next tile's 1x1 as soon as epilogue 1 has drained D1
+          mbar_wait(d1_empty, i & 1);
+          issue_mma1(i + 1);
+        }
+        mbar_wait(t_ready(b), ph);                  // t tile of tile i written
+        mbar_wait(d2_empty(b), ph ^ 1);             // D2[b] drained by epilogue 2 of tile i-2
         tc_fence_after();
+        const uint32_t t_lo0 = (((t_base + (b * NH + h) * PD_XCHUNK) & 0x3FFFF) >> 4) | lo_tag;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (g < ngroups) {
@@ -170,28 +179,23 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
               const int dy = tap / 3, dx = tap % 3;
               const uint32_t a_lo = t_lo0 + (uint32_t)((dy * PD_TW + dx) * 8 + g * 2);
               const uint32_t b_lo = b_lo0 + (uint32_t)((g * 6144 + (tap >> 2) * 2048 + (tap & 3) * 32) >> 4);
-              umma_bf16_lohi(tmem_base + d2_col + h * PD_CB + g * 16, a_lo, b_lo, desc_hi, idesc2, tap != 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base + d2_col(b) + h * PD_CB + g * 16, a_lo, b_lo, desc_hi, idesc2, tap != 0 ? 1u : 0u);
             }
           }
         }
-        umma_commit(d2_full);
-        if (h == 0 && t + ctas_in_cb < p.tiles_per_cb) issue_mma1(it + 1);   // next tile's 1x1 overlaps epilogue 2
+        umma_commit(d2_full(b));
       }
     }
-  } else if (warp >= 3) {
-    // ===================== epilogue warps =====================
+  } else if (warp < 3 + PD_GROUP_WARPS) {
+    // ===================== epilogue group 1: T (fp32, TMEM) * rstd -> bf16 t tile =====================
     const int ew = warp - 3;
     const int quarter = warp & 3;
-    const int cw = ew >> 2;                   // column group: channels [cw*CW, +CW) of each chunk(2) half
+    const int half = ew >> 2;                 // 32 of the 64 channels of each chunk(2) half
     const int r = quarter * 32 + lane;        // TMEM lane = row of the M tile
-    const int oy_l = r / PD_TW, ox_l = r % PD_TW;
-    const int opix = oy_l * PD_OW + ox_l;
-    const bool in_box = ox_l < PD_OW;
-    uint32_t it = 0;
-    for (long t = cta_in_cb; t < p.tiles_per_cb; t += ctas_in_cb, ++it) {
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
       int img, y0, x0;
-      tile_xy(t, img, y0, x0);
-      // ---------- epilogue 1: T (fp32, TMEM) * rstd -> bf16 t tile in smem ----------
+      tile_xy(i, img, y0, x0);
       float rs[2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
@@ -200,89 +204,105 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         const bool inimg = pix < PD_TW * PD_IH && y >= 0 && y < p.H && x >= 0 && x < p.W;
         rs[mt] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;   // 0 outside: conv zero padding of t
       }
-      mbar_wait_relaxed(d1_full, it & 1);
+      mbar_wait_relaxed(t_free(b), ((i >> 1) & 1) ^ 1);   // t[b] no longer read by MMA2(i-2) / its output store
+      mbar_wait_relaxed(d1_full, i & 1);
       tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        if (mt == 1 && quarter >= 2) continue;  // pixels 192..255 do not exist (warp-uniform)
+        const bool live = !(mt == 1 && quarter >= 2);      // pixels 192..255 do not exist (warp-uniform)
         const int pix = mt * 128 + r;
         const uint32_t t_row = tmem_base + d1_col + mt * N1 + ((uint32_t)(quarter * 32) << 16);
-        uint32_t v[NH * (CW / 16)][16];
+        uint32_t v[NH * 2][16];
+        if (live) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h)
+          for (int h = 0; h < NH; ++h) {
+            tmem_ld16_issue(t_row + h * 64 + half * 32, v[h * 2]);
+            tmem_ld16_issue(t_row + h * 64 + half * 32 + 16, v[h * 2 + 1]);
+          }
 #pragma unroll
-          for (int u = 0; u < CW / 16; ++u) tmem_ld16_issue(t_row + h * 64 + cw * CW + u * 16, v[h * (CW / 16) + u]);
+          for (int u = 0; u < NH * 2; ++u) tmem_ld16_wait(v[u]);
+        }
+        if (mt == 1) {                          // all TMEM reads of this tile done: MMA1 of the next tile may overwrite D1
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d1_empty);
+        }
+        if (live) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          uint8_t* trow = t_gen + h * PD_TSLOT + pix * 128;
+          for (int h = 0; h < NH; ++h) {
+            uint8_t* trow = t_gen + (b * NH + h) * PD_XCHUNK + pix * 128;
 #pragma unroll
-          for (int u = 0; u < CW / 16; ++u) {
-            uint32_t (&vv)[16] = v[h * (CW / 16) + u];
-            tmem_ld16_wait(vv);
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-              const int o = c2 * 8;
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t (&vv)[16] = v[h * 2 + (c4 >> 1)];
+              const int o = (c4 & 1) * 8;
               uint4 w4;
               w4.x = pack_bf16x2(__uint_as_float(vv[o + 0]) * rs[mt], __uint_as_float(vv[o + 1]) * rs[mt]);
               w4.y = pack_bf16x2(__uint_as_float(vv[o + 2]) * rs[mt], __uint_as_float(vv[o + 3]) * rs[mt]);
               w4.z = pack_bf16x2(__uint_as_float(vv[o + 4]) * rs[mt], __uint_as_float(vv[o + 5]) * rs[mt]);
               w4.w = pack_bf16x2(__uint_as_float(vv[o + 6]) * rs[mt], __uint_as_float(vv[o + 7]) * rs[mt]);
-              const int chunk = (cw * CW + u * 16) / 8 + c2;
+              const int chunk = half * 4 + c4;
               *reinterpret_cast<uint4*>(trow + ((chunk ^ (pix & 7)) << 4)) = w4;
             }
           }
         }
       }
-      tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");   // t tile complete (also: previous store was read out)
-      if (ew == 0 && lane == 0) mbar_arrive(t_ready);
-      // ---------- epilogue 2: depthwise result (TMEM) -> (gate) -> staged -> TMA store ----------
-      mbar_wait_relaxed(d2_full, it & 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");          // t tile complete
+      if (ew == 0 && lane == 0) mbar_arrive(t_ready(b));
+    }
+  } else {
+    // ===================== epilogue group 2: depthwise result -> (gate) -> staged in the consumed t tile -> TMA store =====
+    const int ew = warp - 3 - PD_GROUP_WARPS;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int r = quarter * 32 + lane;
+    const int oy_l = r / PD_TW, ox_l = r % PD_TW;
+    const int opix = oy_l * PD_OW + ox_l;
+    const bool in_box = ox_l < PD_OW;
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
+      mbar_wait_relaxed(d2_full(b), (i >> 1) & 1);    // all MMA2(i) retired: D2[b] valid, t[b] no longer read
       tc_fence_after();
-      {
-        const uint32_t t_row = tmem_base + d2_col + ((uint32_t)(quarter * 32) << 16) + cw * CW;
-        uint32_t a[CW / 16][16], b[CW / 16][16];
+      const uint32_t t_row = tmem_base + d2_col(b) + ((uint32_t)(quarter * 32) << 16) + half * 32;
+      uint8_t* srow = t_gen + (b * NH) * PD_XCHUNK + opix * 128;     // staging = half-0 t tile of this buffer
 #pragma unroll
-        for (int u = 0; u < CW / 16; ++u) {
-          if (cw * CW + u * 16 < ch_valid) {      // warp-uniform
-            tmem_ld16_issue(t_row + u * 16, a[u]);
-            if (GATE) tmem_ld16_issue(t_row + PD_CB + u * 16, b[u]);
-          }
-        }
-        uint8_t* srow = o_gen + opix * 128;
+      for (int q = 0; q < 2; ++q) {
+        if (half * 32 + q * 16 < ch_valid) {          // warp-uniform
+          uint32_t a[16], bb[16];
+          tmem_ld16_issue(t_row + q * 16, a);
+          if (GATE) tmem_ld16_issue(t_row + PD_CB + q * 16, bb);
+          tmem_ld16_wait(a);
+          if (GATE) tmem_ld16_wait(bb);
+          if (in_box) {
 #pragma unroll
-        for (int u = 0; u < CW / 16; ++u) {
-          if (cw * CW + u * 16 < ch_valid) {
-            tmem_ld16_wait(a[u]);
-            if (GATE) tmem_ld16_wait(b[u]);
-            if (in_box) {
+            for (int v8 = 0; v8 < 2; ++v8) {
+              float f[8];
 #pragma unroll
-              for (int v8 = 0; v8 < 2; ++v8) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float x1 = __uint_as_float(a[u][v8 * 8 + i]);
-                  f[i] = GATE ? gelu_as2(x1) * __uint_as_float(b[u][v8 * 8 + i]) : x1;
-                }
-                uint4 o;
-                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                const int chunk = (cw * CW + u * 16) / 8 + v8;
-                *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
+              for (int e = 0; e < 8; ++e) {
+                const float x1 = __uint_as_float(a[v8 * 8 + e]);
+                f[e] = GATE ? gelu_as2(x1) * __uint_as_float(bb[v8 * 8 + e]) : x1;
               }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              const int chunk = half * 4 + q * 2 + v8;
+              *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
             }
           }
         }
       }
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 2, %0;" ::"n"(EPW * 32) : "memory");   // output tile staged
+      asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");          // D2[b] drained by the whole group, output tile staged
       if (ew == 0 && lane == 0) {
+        mbar_arrive(d2_empty(b));
+        int img, y0, x0;
+        tile_xy(i, img, y0, x0);
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(&map_out), "r"(o_base), "r"(cb * PD_CB), "r"(x0), "r"(y0), "r"(img) : "memory");
+                     ::"l"(&map_out), "r"(t_base + (b * NH) * PD_XCHUNK), "r"(cb * PD_CB), "r"(x0), "r"(y0), "r"(img) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free before this thread joins "bar.sync 1"
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(t_free(b));                        // t[b] may be rewritten by epilogue 1 of tile i+2
       }
     }
     if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -320,7 +340,7 @@ int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.rstd = rstd;
   const int NH = gate ? 2 : 1;
-  const uint32_t smem = 1024 + p.kc * NH * 8192 + NH * PD_DWB + p.kc * PD_XCHUNK + NH * PD_TSLOT + 16384 + 128;
+  const uint32_t smem = 1024 + p.kc * NH * 8192 + NH * PD_DWB + p.kc * PD_XCHUNK + 2 * NH * PD_XCHUNK + 1024 + 128;
   static bool attr = false;
   if (!attr) {
     int dev = 0;
@@ -330,7 +350,7 @@ int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  KD_CHECK(smem <= 227 * 1024, "pwdw_tc: shared memory budget exceeded (%u)", smem);
+  KD_CHECK(smem <= 232448, "pwdw_tc: shared memory budget exceeded (%u)", smem);
   CUtensorMap map_x, map_w1, map_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
@@ -353,11 +373,11 @@ int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   // one launch does the work of conv_gemm (1x1) + dwconv3x3: report it under its own class
   const double pix = (double)nimg * H * W;
   ProfScope prof(PC_PWDW, s, 2.0 * pix * Nt * C + 18.0 * pix * Nt, pix * (C + p.Cout) * 2.0 + 4.0 * pix + 2.0 * Nt * C);
-  const int blocks_per_sm = (smem <= 110 * 1024 && !gate) ? 2 : 1;   // non-gate C<=64: 2 CTAs/SM fit smem and TMEM (256 cols)
+  const int blocks_per_sm = 1;
   int grid = (int)std::min<long>((long)p.cblocks * p.tiles_per_cb, (long)g_pd_sms * blocks_per_sm);
   if (grid < p.cblocks) grid = p.cblocks;
-  if (gate) k_pwdw_tc<1><<<grid, PdCfg<1>::THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
-  else k_pwdw_tc<0><<<grid, PdCfg<0>::THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
+  if (gate) k_pwdw_tc<1><<<grid, PD_THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
+  else k_pwdw_tc<0><<<grid, PD_THREADS, smem, s>>>(map_x, map_w1, map_out, reinterpret_cast<const uint8_t*>(wtc), p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

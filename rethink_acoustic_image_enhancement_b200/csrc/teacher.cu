@@ -169,10 +169,10 @@ struct Scratch {
 // KDLAE_FUSE_PWDW=1 routes qkv->dw and project_in->dw->gate through the fused kernel (pwdw_tc.cu).  Measured on B200
 // (profiles/r01_summary.md): parity-identical, 23 % less HBM traffic, but 66 vs 79 images/s - its two epilogues are
 // CUDA-core issue bound - so the unfused schedule stays the default until the epilogue instruction count is cut.
-inline bool fuse_pwdw_enabled() {
+inline int fuse_pwdw_mode() {   // 0: unfused (default), 1: fuse both branches, 2: fuse only the qkv branch
   static int v = -1;
-  if (v < 0) { const char* e = getenv("KDLAE_FUSE_PWDW"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v != 0;
+  if (v < 0) { const char* e = getenv("KDLAE_FUSE_PWDW"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
@@ -189,7 +189,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   // ---- x = x + project_out(attn(norm1(x))) ----
   if (!(have_stats && fused_stats)) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
-  const bool fuse = fuse_pwdw_enabled() && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
+  const bool fuse = fuse_pwdw_mode() != 0 && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
                     pwdw_tc_eligible(C, 3 * C, 0) && pwdw_tc_eligible(C, 2 * w.hp, 1);
   ConvOp g;
   if (fuse) {
@@ -214,7 +214,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   KD_TRY(conv_gemm<T>(g, s));
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
-  if (fuse) {
+  if (fuse && fuse_pwdw_mode() == 1) {
     KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn_tc,
                    reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else {
