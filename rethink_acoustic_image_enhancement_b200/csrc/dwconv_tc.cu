@@ -233,7 +233,7 @@ k_dwconv_tc(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float x1 = __uint_as_float(a[v8 * 8 + i]);
-              f[i] = GATE ? gelu_as(x1) * __uint_as_float(b[v8 * 8 + i]) : x1;
+              f[i] = GATE ? gelu_fast(x1) * __uint_as_float(b[v8 * 8 + i]) : x1;
             }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);

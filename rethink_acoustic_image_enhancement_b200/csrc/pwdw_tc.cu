@@ -22,8 +22,9 @@ namespace {
 constexpr int PD_TW = 32, PD_OW = 30, PD_OH = 4, PD_IH = 6, PD_CB = 64;
 constexpr uint32_t PD_XCHUNK = PD_TW * PD_IH * 128;          // 24576: one 64-channel K chunk of the x tile / one t tile
 constexpr uint32_t PD_DWB = 4 * 3 * 2048;                    // diagonal dw blocks per half
-constexpr int PD_GROUP_WARPS = 8;                            // warps per epilogue group
-constexpr int PD_THREADS = (3 + 2 * PD_GROUP_WARPS) * 32;    // producer, 2 issuers, epilogue-1 group, epilogue-2 group
+constexpr int PD_E1_WARPS = 4;                               // epilogue 1 (scale + convert): one warp per TMEM lane quarter
+constexpr int PD_E2_WARPS = 16;                              // epilogue 2 (GELU gate, latency bound): 4 lane quarters x 4 channel quarters
+constexpr int PD_THREADS = (3 + PD_E1_WARPS + PD_E2_WARPS) * 32;
 
 struct PdParams {
   int H, W, C, Nt, Cout, nimg;     // Nt = rows of W1 (3C or 2hp); Cout = output channels (3C or hp)
@@ -58,7 +59,6 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap map_out, const uint8_t* __restrict__ wtc, const PdParams p) {
   constexpr int NH = GATE ? 2 : 1;
   constexpr int N1 = 64 * NH;                       // MMA1 N: t channels of this block (both halves for the gate)
-  constexpr int GT = PD_GROUP_WARPS * 32;           // threads per epilogue group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // smem (all 1024-aligned): W1 [kc][NH][64 rows][128 B] | dw blocks | x chunks | t[2][NH] tiles (+1 KB slack) | barriers
@@ -88,7 +88,7 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out);
-    mbar_init(w_bar, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, PD_GROUP_WARPS);
+    mbar_init(w_bar, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, PD_E1_WARPS);
     for (int b = 0; b < 2; ++b) { mbar_init(t_ready(b), 1); mbar_init(t_free(b), 1); mbar_init(d2_full(b), NH); mbar_init(d2_empty(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -186,11 +186,10 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         umma_commit(d2_full(b));
       }
     }
-  } else if (warp < 3 + PD_GROUP_WARPS) {
+  } else if (warp < 3 + PD_E1_WARPS) {
     // ===================== epilogue group 1: T (fp32, TMEM) * rstd -> bf16 t tile =====================
     const int ew = warp - 3;
     const int quarter = warp & 3;
-    const int half = ew >> 2;                 // 32 of the 64 channels of each chunk(2) half
     const int r = quarter * 32 + lane;        // TMEM lane = row of the M tile
     for (int i = 0; i < ntiles; ++i) {
       const int b = i & 1;
@@ -212,49 +211,52 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         const bool live = !(mt == 1 && quarter >= 2);      // pixels 192..255 do not exist (warp-uniform)
         const int pix = mt * 128 + r;
         const uint32_t t_row = tmem_base + d1_col + mt * N1 + ((uint32_t)(quarter * 32) << 16);
-        uint32_t v[NH * 2][16];
-        if (live) {
 #pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            tmem_ld16_issue(t_row + h * 64 + half * 32, v[h * 2]);
-            tmem_ld16_issue(t_row + h * 64 + half * 32 + 16, v[h * 2 + 1]);
+        for (int half = 0; half < 2; ++half) {   // two runs of 32 channels per chunk(2) half
+          uint32_t v[NH * 2][16];
+          if (live) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              tmem_ld16_issue(t_row + h * 64 + half * 32, v[h * 2]);
+              tmem_ld16_issue(t_row + h * 64 + half * 32 + 16, v[h * 2 + 1]);
+            }
+#pragma unroll
+            for (int u = 0; u < NH * 2; ++u) tmem_ld16_wait(v[u]);
           }
+          if (mt == 1 && half == 1) {             // all TMEM reads of this tile done: MMA1 of the next tile may overwrite D1
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d1_empty);
+          }
+          if (live) {
 #pragma unroll
-          for (int u = 0; u < NH * 2; ++u) tmem_ld16_wait(v[u]);
-        }
-        if (mt == 1) {                          // all TMEM reads of this tile done: MMA1 of the next tile may overwrite D1
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d1_empty);
-        }
-        if (live) {
+            for (int h = 0; h < NH; ++h) {
+              uint8_t* trow = t_gen + (b * NH + h) * PD_XCHUNK + pix * 128;
 #pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            uint8_t* trow = t_gen + (b * NH + h) * PD_XCHUNK + pix * 128;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint32_t (&vv)[16] = v[h * 2 + (c4 >> 1)];
-              const int o = (c4 & 1) * 8;
-              uint4 w4;
-              w4.x = pack_bf16x2(__uint_as_float(vv[o + 0]) * rs[mt], __uint_as_float(vv[o + 1]) * rs[mt]);
-              w4.y = pack_bf16x2(__uint_as_float(vv[o + 2]) * rs[mt], __uint_as_float(vv[o + 3]) * rs[mt]);
-              w4.z = pack_bf16x2(__uint_as_float(vv[o + 4]) * rs[mt], __uint_as_float(vv[o + 5]) * rs[mt]);
-              w4.w = pack_bf16x2(__uint_as_float(vv[o + 6]) * rs[mt], __uint_as_float(vv[o + 7]) * rs[mt]);
-              const int chunk = half * 4 + c4;
-              *reinterpret_cast<uint4*>(trow + ((chunk ^ (pix & 7)) << 4)) = w4;
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t (&vv)[16] = v[h * 2 + (c4 >> 1)];
+                const int o = (c4 & 1) * 8;
+                uint4 w4;
+                w4.x = pack_bf16x2(__uint_as_float(vv[o + 0]) * rs[mt], __uint_as_float(vv[o + 1]) * rs[mt]);
+                w4.y = pack_bf16x2(__uint_as_float(vv[o + 2]) * rs[mt], __uint_as_float(vv[o + 3]) * rs[mt]);
+                w4.z = pack_bf16x2(__uint_as_float(vv[o + 4]) * rs[mt], __uint_as_float(vv[o + 5]) * rs[mt]);
+                w4.w = pack_bf16x2(__uint_as_float(vv[o + 6]) * rs[mt], __uint_as_float(vv[o + 7]) * rs[mt]);
+                const int chunk = half * 4 + c4;
+                *reinterpret_cast<uint4*>(trow + ((chunk ^ (pix & 7)) << 4)) = w4;
+              }
             }
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");          // t tile complete
+      asm volatile("bar.sync 1, %0;" ::"n"(PD_E1_WARPS * 32) : "memory");          // t tile complete
       if (ew == 0 && lane == 0) mbar_arrive(t_ready(b));
     }
   } else {
     // ===================== epilogue group 2: depthwise result -> (gate) -> staged in the consumed t tile -> TMA store =====
-    const int ew = warp - 3 - PD_GROUP_WARPS;
+    const int ew = warp - 3 - PD_E1_WARPS;
     const int quarter = warp & 3;
-    const int half = ew >> 2;
+    const int cq = ew >> 2;                   // 16 of the 64 channels
     const int r = quarter * 32 + lane;
     const int oy_l = r / PD_TW, ox_l = r % PD_TW;
     const int opix = oy_l * PD_OW + ox_l;
@@ -263,37 +265,34 @@ k_pwdw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
       const int b = i & 1;
       mbar_wait_relaxed(d2_full(b), (i >> 1) & 1);    // all MMA2(i) retired: D2[b] valid, t[b] no longer read
       tc_fence_after();
-      const uint32_t t_row = tmem_base + d2_col(b) + ((uint32_t)(quarter * 32) << 16) + half * 32;
+      const uint32_t t_row = tmem_base + d2_col(b) + ((uint32_t)(quarter * 32) << 16) + cq * 16;
       uint8_t* srow = t_gen + (b * NH) * PD_XCHUNK + opix * 128;     // staging = half-0 t tile of this buffer
+      if (cq * 16 < ch_valid) {                       // warp-uniform
+        uint32_t a[16], bb[16];
+        tmem_ld16_issue(t_row, a);
+        if (GATE) tmem_ld16_issue(t_row + PD_CB, bb);
+        tmem_ld16_wait(a);
+        if (GATE) tmem_ld16_wait(bb);
+        if (in_box) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (half * 32 + q * 16 < ch_valid) {          // warp-uniform
-          uint32_t a[16], bb[16];
-          tmem_ld16_issue(t_row + q * 16, a);
-          if (GATE) tmem_ld16_issue(t_row + PD_CB + q * 16, bb);
-          tmem_ld16_wait(a);
-          if (GATE) tmem_ld16_wait(bb);
-          if (in_box) {
+          for (int v8 = 0; v8 < 2; ++v8) {
+            float f[8];
 #pragma unroll
-            for (int v8 = 0; v8 < 2; ++v8) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x1 = __uint_as_float(a[v8 * 8 + e]);
-                f[e] = GATE ? gelu_as2(x1) * __uint_as_float(bb[v8 * 8 + e]) : x1;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              const int chunk = half * 4 + q * 2 + v8;
-              *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
+            for (int e = 0; e < 8; ++e) {
+              const float x1 = __uint_as_float(a[v8 * 8 + e]);
+              f[e] = GATE ? gelu_fast(x1) * __uint_as_float(bb[v8 * 8 + e]) : x1;
             }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            const int chunk = cq * 2 + v8;
+            *reinterpret_cast<uint4*>(srow + ((chunk ^ (opix & 7)) << 4)) = o;
           }
         }
       }
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");          // D2[b] drained by the whole group, output tile staged
+      asm volatile("bar.sync 2, %0;" ::"n"(PD_E2_WARPS * 32) : "memory");   // D2[b] drained by the whole group, output tile staged
       if (ew == 0 && lane == 0) {
         mbar_arrive(d2_empty(b));
         int img, y0, x0;

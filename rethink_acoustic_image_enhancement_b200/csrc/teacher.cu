@@ -166,13 +166,13 @@ struct Scratch {
 
 // One TransformerBlock (KDLAE_model.py:159-163) over `nimg` images of H x W pixels, C channels.
 // x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
-// KDLAE_FUSE_PWDW=1 routes qkv->dw and project_in->dw->gate through the fused kernel (pwdw_tc.cu).  Measured on B200
-// (profiles/r01_summary.md): parity-identical, 23 % less HBM traffic, but 66 vs 79 images/s - its two epilogues are
-// CUDA-core issue bound - so the unfused schedule stays the default until the epilogue instruction count is cut.
-inline int fuse_pwdw_mode() {   // 0: unfused (default), 1: fuse both branches, 2: fuse only the qkv branch
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("KDLAE_FUSE_PWDW"); v = e ? atoi(e) : 0; }
-  return v;
+// KDLAE_FUSE_PWDW (read per forward; 0 = default): 1 routes qkv->dw and project_in->dw->gate through the fused kernel
+// (pwdw_tc.cu), 2 only the qkv branch.  Measured on B200 (profiles/r01_summary.md): bit-identical outputs, 50 % less HBM
+// traffic in those stages, same speed (77 vs 78 images/s): both schedules end up bound by the tensor core's shared-memory
+// operand reads of the 9-tap depthwise MMAs, so the simpler unfused schedule stays the default.
+inline int fuse_pwdw_mode() {
+  const char* e = getenv("KDLAE_FUSE_PWDW");
+  return e ? atoi(e) : 0;
 }
 
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output

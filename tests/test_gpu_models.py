@@ -81,6 +81,25 @@ def test_teacher_128_against_oracle_and_batch_invariance(precision):
     assert torch.equal(out["hq"][2:3], one["hq"]) and torch.equal(out["sr"][2:3], one["sr"])
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_teacher_fused_conv1x1_dwconv_schedule_matches_reference(mode, manifest, monkeypatch):
+    """KDLAE_FUSE_PWDW: the fused 1x1 -> depthwise tcgen05 kernel must give the same parity as the default schedule."""
+    monkeypatch.setenv("KDLAE_FUSE_PWDW", mode)
+    name = "teacher_c1_biasfree_64"
+    case, g = manifest[name], load_golden(name)
+    m = _teacher(case["kwargs"], case["seed"], case["temp_scale"], "bf16")
+    b, h, w = case["shape"]
+    rate = g["rate"].view(b, 1, 1, 1).expand(b, 1, h, w).to(DEV)
+    with torch.no_grad():
+        out = m({"img": g["img"].to(DEV), "denoise_rate": rate})
+        monkeypatch.setenv("KDLAE_FUSE_PWDW", "0")
+        base = m({"img": g["img"].to(DEV), "denoise_rate": rate})
+    for key in ("hq", "sr"):
+        p = synth.psnr(out[key].cpu(), g[key])
+        print(f"fused mode {mode} {key}: psnr={p:.2f} dB, max|fused-unfused|={(out[key] - base[key]).abs().max().item():.2e}")
+        assert p >= BF16_PSNR
+
+
 def test_teacher_repack_after_weight_update():
     kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no")
     m = _teacher(kw, 3, 1.0, "bf16")
