@@ -98,6 +98,39 @@ def cpu_oracle_rate(size: int, threads: int, repeats: int = 1):
     return scale / best, best
 
 
+def time_other_models(pk, synth, dev, pk_):
+    """Device-resident throughput of the other two forwards of the path (BASELINE configs 3 and 4 shapes, bf16)."""
+    def timeit(f, n=3):
+        for _ in range(2):
+            f()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            f()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    out = {}
+    with torch.no_grad():
+        s = pk.KDLAE_student(residual=True)
+        s.load_state_dict(synth.student_state_dict())
+        s = s.to(dev).eval().set_precision("bf16")
+        x = torch.rand(32, 5, 512, 512, device=dev)
+        ms = timeit(lambda: s(x))
+        out["KDLAE-S 5x512x512 stacks/s"] = {"value": 32 / ms * 1e3, "batch": 32, "tflops": 32 * 1.4881e11 / ms / 1e9,
+                                             "tensor_frac": 32 * 1.4881e11 / ms / 1e9 / pk_["bf16_tflops"]}
+        del s, x
+        a = pk.DenoiseRatePredictor()
+        a.load_state_dict(synth.asdqe_state_dict(), strict=False)
+        a = a.to(dev).eval().set_precision("bf16")
+        lq, gt = torch.rand(64, 3, 512, 512, device=dev), torch.rand(64, 3, 512, 512, device=dev)
+        ms = timeit(lambda: a(lq, gt))
+        out["ASDQE 3x512x512 pairs/s"] = {"value": 64 / ms * 1e3, "batch": 64, "tflops": 64 * 2.1368e11 / ms / 1e9,
+                                          "tensor_frac": 64 * 2.1368e11 / ms / 1e9 / pk_["bf16_tflops"]}
+    return out
+
+
 def run_reference(args, rank):
     """Reference arm: the reference's CPU implementation of the path (oracle port) on all host cores."""
     if rank != 0:
@@ -142,6 +175,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time KDLAE-S (config 3) and ASDQE (config 4) on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -290,6 +324,8 @@ def main():
         "model_tflops_per_gpu": whole_tflops,
         "model_tensor_frac": whole_tflops / pk_["bf16_tflops"],
     }
+    if args.extras:
+        line["other_models"] = time_other_models(pk, synth, dev, pk_)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cpu_oracle_rate(64, cores)
