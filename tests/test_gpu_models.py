@@ -175,3 +175,50 @@ def test_asdqe_matches_reference_fixture(name, precision, manifest):
         assert es <= 1e-3 and ef <= 1e-3 * max(1.0, g["feat"].abs().max().item())
     else:
         assert es <= 1e-2 and rel <= 5e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_minimum_and_ragged_sizes_against_oracle(precision):
+    """Smallest legal inputs and sizes that are not multiples of any tile: teacher 8x8 and 24x40, student 4x4x1 frame,
+    ASDQE 1x1 and 17x50 (zero-padded to 16/32 x 64 inside)."""
+    tol_t = FP32_TOL if precision == "fp32" else None
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+    sd = synth.teacher_state_dict(seed=11, temp_scale=4.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision(precision)
+    for (h, w) in ((8, 8), (24, 40)):
+        img = synth.seeded_tensor(f"rag.{h}x{w}", (2, 1, h, w), 11)
+        rate = torch.full((2, 1, h, w), 0.3)
+        with torch.no_grad():
+            hq_ref, sr_ref = oracle.teacher_forward(sd, img, rate)
+            out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+        for got, ref, key in ((out["hq"].cpu(), hq_ref, "hq"), (out["sr"].cpu(), sr_ref, "sr")):
+            err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+            print(f"teacher {h}x{w} {precision} {key}: max|d|={err:.3e} psnr={p:.2f}")
+            assert (err <= tol_t) if tol_t else (p >= BF16_PSNR)
+    ss = synth.student_state_dict(seed=4)
+    s = pk.KDLAE_student(residual=True)
+    s.load_state_dict(ss)
+    s = s.to(DEV).eval().set_precision(precision)
+    for shape in ((1, 1, 4, 4), (2, 3, 12, 20)):
+        x = synth.seeded_tensor(f"rag.s.{shape}", shape, 4)
+        with torch.no_grad():
+            ref = oracle.student_forward(ss, x, residual=True)
+            got = s(x.to(DEV)).cpu()
+        err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+        print(f"student {shape} {precision}: max|d|={err:.3e} psnr={p:.2f}")
+        assert (err <= FP32_TOL) if precision == "fp32" else (p >= BF16_PSNR)
+    sa = synth.asdqe_state_dict(seed=5)
+    a = pk.DenoiseRatePredictor()
+    a.load_state_dict(sa, strict=False)
+    a = a.to(DEV).eval().set_precision(precision)
+    for (h, w) in ((1, 1), (17, 50)):
+        lq = synth.seeded_tensor(f"rag.a.{h}", (2, 3, h, w), 5)
+        gt = synth.seeded_tensor(f"rag.g.{h}", (2, 3, h, w), 6)
+        with torch.no_grad():
+            ref = oracle.asdqe_forward(sa, lq, gt)
+            got = a(lq.to(DEV), gt.to(DEV)).cpu()
+        err = (got - ref).abs().max().item()
+        print(f"asdqe {h}x{w} {precision}: score max|d|={err:.3e}")
+        assert err <= (1e-3 if precision == "fp32" else 1e-2)
