@@ -299,7 +299,15 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": tv["flops"] / tv["launches"] / per_launch_s / 1e12,
                 "peak": pk_["bf16_tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
     roof["traffic"] = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write per launch, from an ncu capture
+    if os.path.exists(tpath) and B >= 8 and S == 512:             # (same micro-batch of 8 images at 512x512)
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if top in tj:
+            roof["traffic"] = tj[top]["dram_bytes_per_launch"]
+            roof["traffic_source"] = tj["_provenance"]
     roof["peak_source"] = pk_["source"] + (" sustained (kernel timed inside a long step)" if pk_["source"] == "measured" else "")
     roof["avg_launch_ms"] = per_launch_s * 1e3
     roof["share_of_step"] = classes[top]["share"]
