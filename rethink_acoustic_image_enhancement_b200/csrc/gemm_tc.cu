@@ -416,6 +416,13 @@ int pick_nc(int N, int* n_chunks) {
 
 int g_num_sms = 0;
 
+// KDLAE_CONV3X3_LEGACY=1 keeps 3x3 convs on this file's tap-by-tap path (A/B comparison in scripts/time_models.py)
+bool conv3x3_legacy() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KDLAE_CONV3X3_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 cudaError_t set_smem_attr() {
   cudaError_t e = cudaSuccess;
 #define KD_TC_ATTR(F, M) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_gemm_tc<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -448,6 +455,12 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     KD_CUDA(set_smem_attr());
+  }
+  if (op.kh == 3 && op.dil == 1 && op.epi.row_scale == nullptr && op.epi.row_mu == nullptr && op.epi.stat_rstd == nullptr &&
+      !conv3x3_legacy()) {
+    int n_chunks = 1;
+    const int nc = pick_nc(op.epi.N, &n_chunks);
+    return conv3x3_tc(op, nc, n_chunks, s);     // one activation load per tile, taps = shifted descriptors (conv3x3_tc.cu)
   }
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -25,6 +25,8 @@ template <typename T> int conv_gemm_simt(const ConvOp& op, cudaStream_t s);
 // tcgen05/TMEM/TMA implicit GEMM (bf16 storage). Returns -1 if the shape is not eligible.
 int conv_gemm_tc(const ConvOp& op, cudaStream_t s);
 bool conv_gemm_tc_eligible(const ConvOp& op);
+// dense 3x3 / 3x3x3 (dilation 1) with a single halo-tile load per K chunk; N pre-split by conv_gemm_tc (conv3x3_tc.cu)
+int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s);
 // dispatch: bf16 -> tcgen05 when eligible, SIMT otherwise; fp32 -> SIMT
 template <typename T> int conv_gemm(const ConvOp& op, cudaStream_t s);
 
