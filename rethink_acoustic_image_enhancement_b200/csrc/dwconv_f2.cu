@@ -1,0 +1,250 @@
+// Depthwise 3x3 (+ optional GELU gate) for NHWC bf16 on the CUDA cores with packed fp32 FMAs (FFMA2, fma.rn.f32x2)
+//   (KDLAE_model.py:97,103-104 FeedForward.dwconv + gate, :119 Attention.qkv_dwconv).
+//
+// Why not the tensor cores (dwconv_tc.cu): a depthwise conv has no reuse across channels, so the diagonal-weight MMA reads
+// its 128 x 16 activation operand from shared memory once per tap - 9x the tile - and ncu shows that kernel pinned on
+// L1/shared-memory throughput (82 %) at ~55 % of the HBM rate.  Here every input value is read from shared memory ~1.9x:
+//   * lane = one bf16x2 channel pair of a 64-channel block (a warp-wide LDS.32 is exactly one pixel's 128-byte row, so
+//     there are no bank conflicts and global stores are full 128-byte lines), warp = PXT adjacent output columns;
+//   * the warp walks down the tile rows: each input row is loaded and unpacked once ((PXT+2) LDS.32 + as many shift/mask
+//     pairs) and feeds the three output rows it belongs to, which live in 3 x PXT rotating packed accumulators;
+//   * the 9 (18 with the gate) weight pairs stay in registers for the whole persistent CTA (a CTA keeps one channel block);
+//   * one FFMA2 does two channel FMAs: 4.5 issue slots per output instead of 9, which is what makes the CUDA-core
+//     version fit the issue budget at HBM speed (B200 measured: FFMA and FFMA2 both sustain 128 FMA/clk/SM).
+// Staging: one 4-D TMA box {64 ch, TW+2, TH+2, 1} per tile (two with the gate: the matching channels of both chunk(2)
+// halves); zero padding = TMA out-of-bounds fill; two stages per CTA, two CTAs per SM.
+// Weights are the fp32 originals (the tensor-core variant had to round them to bf16).
+#include <algorithm>
+#include "sm100.cuh"
+
+namespace kd {
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// bf16x2 word -> packed {fp32 even channel, fp32 odd channel}
+__device__ __forceinline__ u64 unpack2(uint32_t w) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ float2 as_float2(u64 v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ u64 pack2f(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 splat2(float c) { return pack2f(c, c); }
+
+// gelu(a) * b on a packed channel pair.  gelu(x) = relu(x) - |x| * (erfc(|x|/sqrt2) / 2) with the same erfc as gelu_fast
+// (Abramowitz-Stegun 7.1.26, rcp.approx / ex2.approx); this form needs no copysign and the polynomial, the exponent
+// argument and the products run as packed FFMA2/FMUL2 - about 10 issue slots per value instead of 17.
+// q = |x| * sqrt(log2(e) / 2), so that exp(-x^2/2) = 2^(-q*q) and 1 + p*|x|/sqrt2 = 1 + (p / sqrt(log2 e)) * q.
+__device__ __forceinline__ u64 gelu_gate2(u64 a, u64 b) {
+  const float2 x = as_float2(a);
+  const u64 q = pack2f(fabsf(x.x) * 0.84932180028801904272f, fabsf(x.y) * 0.84932180028801904272f);
+  const float2 d = as_float2(ffma2(q, splat2(0.27274160926128944f), splat2(1.0f)));
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d.y));
+  const u64 t = pack2f(t0, t1);
+  u64 y = ffma2(t, splat2(0.5f * 1.061405429f), splat2(0.5f * -1.453152027f));     // erfc / 2: coefficients halved
+  y = ffma2(y, t, splat2(0.5f * 1.421413741f));
+  y = ffma2(y, t, splat2(0.5f * -0.284496736f));
+  y = ffma2(y, t, splat2(0.5f * 0.254829592f));
+  y = fmul2(y, t);
+  const float2 qq = as_float2(fmul2(q, q));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-qq.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-qq.y));
+  const float2 ye = as_float2(fmul2(y, pack2f(e0, e1)));
+  const float g0 = fmaf(-fabsf(x.x), ye.x, fmaxf(x.x, 0.f));
+  const float g1 = fmaf(-fabsf(x.y), ye.y, fmaxf(x.y, 0.f));
+  return fmul2(pack2f(g0, g1), b);
+}
+
+constexpr int F2_TH = 8, F2_IN_H = F2_TH + 2, F2_WARPS = 8, F2_THREADS = F2_WARPS * 32;
+template <int GATE> struct F2Cfg {
+  static constexpr int PXT = GATE ? 2 : 4;              // output columns per warp
+  static constexpr int TW = F2_WARPS * PXT, IN_W = TW + 2;
+  static constexpr uint32_t TILE_BYTES = IN_W * F2_IN_H * 128;
+  static constexpr uint32_t STAGE = (GATE ? 2 : 1) * TILE_BYTES;
+  static constexpr uint32_t SMEM = 2 * STAGE + 128 + 64;
+};
+
+struct F2Params {
+  bf16* out; long ldo;
+  const float* w9c;
+  int H, W, C, Cout, hp;
+  int tiles_x, tiles_y, cblocks, G;
+  int nsp;                  // spatial tiles (images x tiles_y x tiles_x), < 2^24
+  float inv_tiles_x, inv_tiles_img;
+};
+
+template <int GATE>
+__global__ void __launch_bounds__(F2_THREADS, 2)
+k_dwconv_f2(const __grid_constant__ CUtensorMap map, const F2Params p) {
+  constexpr int PXT = F2Cfg<GATE>::PXT, TW = F2Cfg<GATE>::TW, IN_W = F2Cfg<GATE>::IN_W;
+  constexpr uint32_t TILE_BYTES = F2Cfg<GATE>::TILE_BYTES, STAGE = F2Cfg<GATE>::STAGE;
+  constexpr int NH = GATE ? 2 : 1;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t bar0 = sbase + 2 * STAGE;
+
+  const int cb = blockIdx.x % p.cblocks, g = blockIdx.x / p.cblocks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_img = p.tiles_x * p.tiles_y;
+
+  auto issue = [&](int sp, int stage) {   // one elected thread: arm the barrier and launch the TMA box(es)
+    const int img = fast_div(sp, tiles_img, p.inv_tiles_img);
+    const int r = sp - img * tiles_img;
+    const int tyi = fast_div(r, p.tiles_x, p.inv_tiles_x), txi = r - tyi * p.tiles_x;
+    const uint32_t bar = bar0 + 8u * stage, dst = sbase + stage * STAGE;
+    mbar_expect_tx(bar, STAGE);
+    tma_load_4d(dst, &map, bar, cb * 64, txi * TW - 1, tyi * F2_TH - 1, img);
+    if (GATE) tma_load_4d(dst + TILE_BYTES, &map, bar, p.hp + cb * 64, txi * TW - 1, tyi * F2_TH - 1, img);
+  };
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (g < p.nsp) issue(g, 0);
+  }
+
+  // this lane's channel pair and its 9 (x2) packed weights
+  const int ch = cb * 64 + lane * 2;
+  const bool ch_ok = ch < p.Cout;
+  u64 w[NH][9];
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float2 f = make_float2(0.f, 0.f);
+      if (ch_ok) f = __ldg(reinterpret_cast<const float2*>(p.w9c + (long)t * p.C + h * p.hp + ch));
+      asm("mov.b64 %0, {%1, %2};" : "=l"(w[h][t]) : "f"(f.x), "f"(f.y));
+    }
+  __syncthreads();
+
+  const int xs = warp * PXT;
+  const long row_pitch2 = (long)p.W * p.ldo * 2;
+  int it = 0;
+  const int ldo2 = (int)p.ldo * 2;
+  for (int sp = g; sp < p.nsp; sp += p.G, ++it) {
+    const int stage = it & 1;
+    if (threadIdx.x == 0 && sp + p.G < p.nsp) issue(sp + p.G, stage ^ 1);
+    const int img = fast_div(sp, tiles_img, p.inv_tiles_img);
+    const int r = sp - img * tiles_img;
+    const int tyi = fast_div(r, p.tiles_x, p.inv_tiles_x), txi = r - tyi * p.tiles_x;
+    const int x0 = txi * TW + xs, y0 = tyi * F2_TH;
+    const int nq = ch_ok ? p.W - x0 : 0, nr = p.H - y0;     // valid output columns / rows of this thread's strip
+    uint8_t* orp = reinterpret_cast<uint8_t*>(p.out + (((long)img * p.H + y0) * p.W + x0) * p.ldo + ch);
+    const uint32_t sa = sbase + stage * STAGE + xs * 128 + lane * 4;
+
+    mbar_wait(bar0 + 8u * stage, (it >> 1) & 1);
+
+    u64 acc[NH][3][PXT];
+#pragma unroll
+    for (int ir = 0; ir < F2_IN_H; ++ir) {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        u64 v[PXT + 2];
+#pragma unroll
+        for (int j = 0; j < PXT + 2; ++j) v[j] = unpack2(lds32(sa + h * TILE_BYTES + (ir * IN_W + j) * 128));
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int orow = ir - dy;
+          if (orow >= 0 && orow < F2_TH) {
+            const int a = orow % 3;
+#pragma unroll
+            for (int q = 0; q < PXT; ++q) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                if (dy == 0 && dx == 0) acc[h][a][q] = fmul2(v[q], w[h][0]);
+                else acc[h][a][q] = ffma2(v[q + dx], w[h][dy * 3 + dx], acc[h][a][q]);
+              }
+            }
+          }
+        }
+      }
+      if (ir >= 2) {
+        const int orow = ir - 2, a = orow % 3;
+#pragma unroll
+        for (int q = 0; q < PXT; ++q) {
+          const float2 f = as_float2(GATE ? gelu_gate2(acc[0][a][q], acc[NH - 1][a][q]) : acc[0][a][q]);
+          if (orow < nr && q < nq) *reinterpret_cast<uint32_t*>(orp + q * ldo2) = pack_bf16x2(f.x, f.y);
+        }
+        orp += row_pitch2;
+      }
+    }
+    __syncthreads();   // everyone is done reading this stage before it is refilled two iterations later
+  }
+}
+
+int g_f2_sms = 0;
+
+template <int GATE>
+int launch_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, cudaStream_t s) {
+  typedef F2Cfg<GATE> Cfg;
+  static bool attr = false;
+  if (!attr) {
+    KD_CUDA(cudaFuncSetAttribute(k_dwconv_f2<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+  const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
+  const cuuint32_t box[4] = {64, (cuuint32_t)Cfg::IN_W, F2_IN_H, 1};
+  KD_TRY(make_map(&map, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+  F2Params p;
+  p.out = out; p.ldo = ldo; p.w9c = w9c;
+  p.H = H; p.W = W; p.C = C; p.Cout = GATE ? C / 2 : C; p.hp = GATE ? C / 2 : 0;
+  p.tiles_x = cdiv(W, Cfg::TW); p.tiles_y = cdiv(H, F2_TH); p.cblocks = cdiv(p.Cout, 64);
+  const long nsp = (long)nimg * p.tiles_x * p.tiles_y;
+  KD_CHECK(nsp < (1L << 24) && ldo < (1L << 28), "dwconv3x3: too many tiles (%ld)", nsp);
+  p.nsp = (int)nsp;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_img = 1.0f / (float)(p.tiles_x * p.tiles_y);
+  p.G = (int)std::min<long>(nsp, std::max(1, 2 * g_f2_sms / p.cblocks));
+  ProfScope prof(PC_DWCONV, s, 18.0 * nimg * H * W * C, (double)nimg * H * W * (C + p.Cout) * 2.0 + 36.0 * C);
+  k_dwconv_f2<GATE><<<p.G * p.cblocks, F2_THREADS, Cfg::SMEM, s>>>(map, p);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// bf16 entry used by dwconv3x3<bf16>; returns -1 when the shape is not eligible
+int dwconv3x3_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
+                 cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) || ldx % 8 || ldo % 2 || C % (gate ? 16 : 8)) return -1;
+  if (g_f2_sms == 0) {
+    int dev = 0;
+    KD_CUDA(cudaGetDevice(&dev));
+    KD_CUDA(cudaDeviceGetAttribute(&g_f2_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return gate ? launch_f2<1>(x, ldx, out, ldo, w9c, nimg, H, W, C, s) : launch_f2<0>(x, ldx, out, ldo, w9c, nimg, H, W, C, s);
+}
+
+}  // namespace kd

@@ -129,10 +129,28 @@ int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c
 int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, int nimg, int H, int W, int C, int gate,
                  cudaStream_t s);
 
+int dwconv3x3_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
+                 cudaStream_t s);
+
+// KDLAE_DW selects the bf16 depthwise kernel: "f2" (default: packed-FFMA2 CUDA-core kernel, dwconv_f2.cu), "tc"
+// (tensor-core diagonal-weight kernel, dwconv_tc.cu), "tma" (first TMA-tiled CUDA-core kernel, dwconv_tma.cu)
+static int dw_mode() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("KDLAE_DW");
+    m = (e && !strcmp(e, "tc")) ? 0 : (e && !strcmp(e, "tma")) ? 2 : 1;
+  }
+  return m;
+}
+
 template <typename T>
 int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias, int nimg, int H, int W, int C,
               int gate, cudaStream_t s, const void* wtc) {
-  if (std::is_same<T, bf16>::value && bias == nullptr && wtc != nullptr) {   // tensor-core kernel (diagonal-weight implicit GEMM)
+  if (std::is_same<T, bf16>::value && bias == nullptr && dw_mode() == 1) {
+    const int r = dwconv3x3_f2(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, w9c, nimg, H, W, C, gate, s);
+    if (r >= 0) return r;
+  }
+  if (std::is_same<T, bf16>::value && bias == nullptr && wtc != nullptr && dw_mode() != 2) {   // tensor-core kernel (diagonal-weight implicit GEMM)
     const int r = dwconv3x3_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, wtc, nimg, H, W, C, gate, s);
     if (r >= 0) return r;
   }
