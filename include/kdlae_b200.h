@@ -134,6 +134,11 @@ int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scr
 int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* wtc_scratch, void* out, int nimg,
                   int H, int W, int C, int gate, void* stream);
 
+/* Same fused stage with the depthwise part on the CUDA cores (packed FFMA2; pwdw_f2.cu) - the default schedule of the bf16
+ * TransformerBlock when C <= 128 and the LayerNorm is BiasFree.  Bit-identical to kdlae_conv_gemm + kdlae_dwconv3x3. */
+int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
+                  int gate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

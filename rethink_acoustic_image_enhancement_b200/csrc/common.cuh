@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 
 namespace kd {
 
@@ -44,6 +45,15 @@ const char* get_error();
 // ---- launch counter (bench.py reports gpu_launches) -------------------------------------
 extern unsigned long long g_launch_count;
 inline void count_launch() { ++g_launch_count; }
+
+// ---- SM budget of the persistent kernels ---------------------------------------------------
+// KDLAE_SM_LIMIT=n caps the grid of every persistent kernel at n SMs, so two forwards on two streams can run side by side
+// on disjoint SM sets (scripts/two_stream_probe.py: overlapping write-bound with read-bound stages).  Default: all SMs.
+inline int sm_limit(int sms) {
+  static int lim = -1;
+  if (lim < 0) { const char* e = getenv("KDLAE_SM_LIMIT"); lim = e ? atoi(e) : 0; }
+  return (lim > 0 && lim < sms) ? lim : sms;
+}
 
 // ---- optional per-kernel-class CUDA-event profiler (bench.py roofline; off by default) ----------
 enum ProfClass {

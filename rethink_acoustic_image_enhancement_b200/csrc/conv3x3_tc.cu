@@ -327,6 +327,7 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_c3_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_c3_sms = sm_limit(g_c3_sms);
     KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
     KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
   }

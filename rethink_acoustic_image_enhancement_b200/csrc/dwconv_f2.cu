@@ -243,6 +243,7 @@ int dwconv3x3_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c,
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_f2_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_f2_sms = sm_limit(g_f2_sms);
   }
   return gate ? launch_f2<1>(x, ldx, out, ldo, w9c, nimg, H, W, C, s) : launch_f2<0>(x, ldx, out, ldo, w9c, nimg, H, W, C, s);
 }

@@ -323,6 +323,7 @@ int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, 
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_dt_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_dt_sms = sm_limit(g_dt_sms);
     KD_CUDA(cudaFuncSetAttribute(k_dwconv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0));
     KD_CUDA(cudaFuncSetAttribute(k_dwconv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     const char* e = getenv("KDLAE_DWTC_BASE_OFFSET");

@@ -191,6 +191,7 @@ int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_dw_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_dw_sms = sm_limit(g_dw_sms);
     const char* e = getenv("KDLAE_DW_PX");
     if (e && atoi(e) == 4) g_dw_px = 4;
     if (e && atoi(e) == 8) g_dw_px = 8;

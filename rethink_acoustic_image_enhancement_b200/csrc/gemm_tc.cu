@@ -454,6 +454,7 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = sm_limit(g_num_sms);
     KD_CUDA(set_smem_attr());
   }
   if (op.kh == 3 && op.dil == 1 && op.epi.row_scale == nullptr && op.epi.row_mu == nullptr && op.epi.stat_rstd == nullptr &&

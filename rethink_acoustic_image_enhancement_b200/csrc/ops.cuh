@@ -42,6 +42,10 @@ size_t dwconv_tc_weight_bytes(int C, int gate);
 int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
 // fused LN-folded 1x1 conv -> depthwise 3x3 (-> GELU gate), bf16 tcgen05 (pwdw_tc.cu)
 bool pwdw_tc_eligible(int C, int Nt, int gate);
+// same fusion with the depthwise conv on the CUDA cores (packed FFMA2, pwdw_f2.cu); w9c: fp32 [9][Nt]
+bool pwdw_f2_eligible(int C, int Nt, int gate);
+int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
+            int H, int W, int C, int gate, cudaStream_t s);
 int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const void* wtc, bf16* out, long ldo, int nimg,
             int H, int W, int C, int gate, cudaStream_t s);
 

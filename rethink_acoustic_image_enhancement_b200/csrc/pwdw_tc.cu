@@ -345,6 +345,7 @@ int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
     int dev = 0;
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_pd_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_pd_sms = sm_limit(g_pd_sms);
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;

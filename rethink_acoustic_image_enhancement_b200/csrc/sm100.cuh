@@ -61,6 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 }
+// Long-period variant for roles that run a whole tile ahead of the consumer (producer / MMA / conversion warps of the fused
+// kernels): with 40 ns polls those waits were a quarter of all issued instructions of pwdw_f2 (ncu source counters).
+__device__ __forceinline__ void mbar_wait_lazy(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(250);
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

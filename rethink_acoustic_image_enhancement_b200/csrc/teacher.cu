@@ -166,14 +166,18 @@ struct Scratch {
 
 // One TransformerBlock (KDLAE_model.py:159-163) over `nimg` images of H x W pixels, C channels.
 // x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
-// KDLAE_FUSE_PWDW (read per forward; 0 = default): 1 routes qkv->dw and project_in->dw->gate through the fused kernel
-// (pwdw_tc.cu), 2 only the qkv branch.  Measured on B200 (profiles/r01_summary.md): bit-identical outputs, 50 % less HBM
-// traffic in those stages, same speed (77 vs 78 images/s): both schedules end up bound by the tensor core's shared-memory
-// operand reads of the 9-tap depthwise MMAs, so the simpler unfused schedule stays the default.
+// KDLAE_FUSE_PWDW (read per forward) picks the schedule of the two "1x1 conv -> depthwise 3x3" pairs of a block:
+//   0  unfused (conv_gemm + dwconv3x3);
+//   1  both pairs through the all-tensor-core fused kernel pwdw_tc.cu, 2 only the qkv pair (bit-identical to each other;
+//      no faster than unfused: bound by the tensor core's shared-memory operand reads of the 9-tap depthwise MMAs);
+//   3  (default) both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
+//      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn.
 inline int fuse_pwdw_mode() {
   const char* e = getenv("KDLAE_FUSE_PWDW");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 3;
 }
+inline bool fuse_f2_qkv(int m) { return m == 3 || m == 4; }
+inline bool fuse_f2_ffn(int m) { return m == 3 || m == 5; }
 
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
 // rows (C <= 256, one accumulator chunk), so only the first norm1 of a stage needs the stand-alone ln_stats pass.
@@ -189,10 +193,15 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   // ---- x = x + project_out(attn(norm1(x))) ----
   if (!(have_stats && fused_stats)) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
-  const bool fuse = fuse_pwdw_mode() != 0 && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
+  const int fmode = fuse_pwdw_mode();
+  const bool f2ok = std::is_same<T, bf16>::value && !lnb && pwdw_f2_eligible(C, 3 * C, 0) && pwdw_f2_eligible(C, 2 * w.hp, 1);
+  const bool fuse = (fmode == 1 || fmode == 2) && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
                     pwdw_tc_eligible(C, 3 * C, 0) && pwdw_tc_eligible(C, 2 * w.hp, 1);
   ConvOp g;
-  if (fuse) {
+  if (f2ok && fuse_f2_qkv(fmode)) {
+    KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
+                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
+  } else if (fuse) {
     KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv_tc,
                    reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
   } else {
@@ -214,7 +223,10 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   KD_TRY(conv_gemm<T>(g, s));
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
-  if (fuse && fuse_pwdw_mode() == 1) {
+  if (f2ok && fuse_f2_ffn(fmode)) {
+    KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
+                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
+  } else if (fuse && fmode == 1) {
     KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn_tc,
                    reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else {

@@ -234,7 +234,7 @@ class KDLAE_teacher(_FusedModule):
 
             packed = eng.packed(tensors, dev, prec, nbytes, pack)
             one = lib.kdlae_teacher_workspace_bytes(cfg, 1, H, W, prec)
-            mb = self.micro_batch or eng.pick_micro_batch(B, one, dev, cap=8)
+            mb = self.micro_batch or eng.pick_micro_batch(B, one, dev, cap=16)
             mb = min(mb, B)
             ws_bytes = lib.kdlae_teacher_workspace_bytes(cfg, mb, H, W, prec)
             ws = eng.workspace(dev, ws_bytes)
