@@ -302,13 +302,18 @@ def main():
     roof["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
     roof["traffic"] = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write per launch, from an ncu capture
-    if os.path.exists(tpath) and B >= 8 and S == 512:             # (same micro-batch of 8 images at 512x512)
+    if os.path.exists(tpath) and S == 512:
         with open(tpath) as fh:
             tj = json.load(fh)
-        if top in tj:
+        same_mb = min(B, 16) == tj.get("_micro_batch") and (args.micro_batch or tj.get("_micro_batch")) == tj.get("_micro_batch")
+        if top in tj and same_mb:                                  # captured at the same micro-batch (launch = same tensors)
             roof["traffic"] = tj[top]["dram_bytes_per_launch"]
             roof["traffic_source"] = tj["_provenance"]
     roof["peak_source"] = pk_["source"] + (" sustained (kernel timed inside a long step)" if pk_["source"] == "measured" else "")
+    if top.startswith("fused_conv1x1_dwconv3x3"):
+        roof["note"] = ("fused tcgen05 1x1 -> FFMA2 depthwise (+gate) kernel: t never reaches HBM, so the HBM fraction is low by design; "
+                        "ncu: smsp__issue_active 56-59 %, bound by CUDA-core issue slots of the depthwise/GELU warps "
+                        "(profiles/r01_summary.md)")
     roof["avg_launch_ms"] = per_launch_s * 1e3
     roof["share_of_step"] = classes[top]["share"]
 

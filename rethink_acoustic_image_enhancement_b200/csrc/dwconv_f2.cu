@@ -173,14 +173,14 @@ k_dwconv_f2(const __grid_constant__ CUtensorMap map, const F2Params p) {
 #pragma unroll
         for (int j = 0; j < PXT + 2; ++j) v[j] = unpack2(lds32(sa + h * TILE_BYTES + (ir * IN_W + j) * 128));
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int orow = ir - dy;
-          if (orow >= 0 && orow < F2_TH) {
-            const int a = orow % 3;
+        for (int dx = 0; dx < 3; ++dx) {        // dx outermost: consecutive FFMA2s go to different accumulators
 #pragma unroll
-            for (int q = 0; q < PXT; ++q) {
+          for (int dy = 0; dy < 3; ++dy) {
+            const int orow = ir - dy;
+            if (orow >= 0 && orow < F2_TH) {
+              const int a = orow % 3;
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
+              for (int q = 0; q < PXT; ++q) {
                 if (dy == 0 && dx == 0) acc[h][a][q] = fmul2(v[q], w[h][0]);
                 else acc[h][a][q] = ffma2(v[q + dx], w[h][dy * 3 + dx], acc[h][a][q]);
               }

@@ -11,9 +11,9 @@
 //   3. conversion warps: tcgen05.ld, * rstd[pixel] (BiasFree LayerNorm folded: gamma in W1, rstd here), bf16, st.shared
 //      into a 128B-swizzled t tile with a row pitch of 32 pixels (same rounding point as the unfused schedule, so the
 //      two schedules are bit-identical)
-//   4. depthwise warps: the sliding-window FFMA2 loop of dwconv_f2.cu over the t tile (lane = channel pair, warp = 4
+//   4. depthwise warps: the sliding-window FFMA2 loop of dwconv_f2.cu over the t tile (lane = channel pair, warp = 3
 //      output columns, 9 weight pairs per half in registers), GELU gate, direct 128-byte-per-pixel global stores.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2..5 conversion (one per TMEM lane quarter), 6..13 depthwise.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2..5 conversion (one per TMEM lane quarter), 6..15 depthwise (3 columns each).
 // t tiles are double buffered, so the conversion of item n+1 and the GEMM of item n+2 run under the depthwise of item n
 // (item = (tile, channel block)).
 #include <algorithm>
@@ -27,7 +27,7 @@ typedef unsigned long long u64;
 
 constexpr int PF_TW = 32, PF_OW = 30, PF_OH = 6, PF_IH = 8, PF_CB = 64;
 constexpr uint32_t PF_XCHUNK = PF_TW * PF_IH * 128;          // 32768: one 64-channel K chunk of the x tile / one t tile
-constexpr int PF_E1_WARPS = 4, PF_DW_WARPS = 8;
+constexpr int PF_E1_WARPS = 4, PF_DW_WARPS = 10;     // 10 depthwise warps x 3 columns = the 30 output columns of a tile
 constexpr int PF_THREADS = (2 + PF_E1_WARPS + PF_DW_WARPS) * 32;
 
 struct PfParams {
@@ -100,8 +100,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
 k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1, const PfParams p) {
   constexpr int NH = GATE ? 2 : 1;
   constexpr int N1 = 64 * NH;                       // GEMM N: t channels of this block (both halves for the gate)
-  constexpr int PXT = GATE ? 2 : 4;                 // output columns per depthwise pass (register budget)
-  constexpr int NPASS = 4 / PXT;                    // a warp owns 4 output columns
+  constexpr int PXT = 3;                            // output columns per depthwise warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // smem (all 1024-aligned): W1 [kc][NH][64 rows][128 B] | x chunks | t[2][NH] tiles | barriers
@@ -245,11 +244,14 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
             for (int c4 = 0; c4 < 4; ++c4) {
               uint32_t (&vv)[16] = v[h * 2 + (c4 >> 1)];
               const int o = (c4 & 1) * 8;
-              uint4 w4;
-              w4.x = pack_bf16x2(__uint_as_float(vv[o + 0]) * rs[mt], __uint_as_float(vv[o + 1]) * rs[mt]);
-              w4.y = pack_bf16x2(__uint_as_float(vv[o + 2]) * rs[mt], __uint_as_float(vv[o + 3]) * rs[mt]);
-              w4.z = pack_bf16x2(__uint_as_float(vv[o + 4]) * rs[mt], __uint_as_float(vv[o + 5]) * rs[mt]);
-              w4.w = pack_bf16x2(__uint_as_float(vv[o + 6]) * rs[mt], __uint_as_float(vv[o + 7]) * rs[mt]);
+              uint4 w4;       // packed multiply by rstd (FMUL2), then one cvt.rn.bf16x2 per pair
+              const u64 rs2 = splat2(rs[mt]);
+              const float2 f0 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1])), rs2));
+              const float2 f1 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), rs2));
+              const float2 f2 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])), rs2));
+              const float2 f3 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), rs2));
+              w4.x = pack_bf16x2(f0.x, f0.y); w4.y = pack_bf16x2(f1.x, f1.y);
+              w4.z = pack_bf16x2(f2.x, f2.y); w4.w = pack_bf16x2(f3.x, f3.y);
               const int chunk = half * 4 + c4;
               *reinterpret_cast<uint4*>(trow + ((chunk ^ (pix & 7)) << 4)) = w4;
             }
@@ -262,7 +264,7 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     }
   } else {
     // ===================== depthwise warps: sliding-window FFMA2 over the t tile -> (gate) -> global =====================
-    const int fw = warp - 2 - PF_E1_WARPS;      // owns output columns 4*fw .. 4*fw+3 of the tile
+    const int fw = warp - 2 - PF_E1_WARPS;      // owns output columns 3*fw .. 3*fw+2 of the tile
     const long row_pitch2 = (long)p.W * p.ldo * 2;
     const int ldo2 = (int)p.ldo * 2;
     const uint32_t lsw = (uint32_t)(lane >> 2), lw = (uint32_t)((lane & 3) << 2);
@@ -285,16 +287,15 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
           w[h][t] = pack2f(f.x, f.y);
         }
       mbar_wait_relaxed(t_ready(b), (n >> 1) & 1);
-#pragma unroll 1
-      for (int pass = 0; pass < NPASS; ++pass) {
-        const int xs = fw * 4 + pass * PXT;
+      {
+        const int xs = fw * PXT;
         // byte offsets of this lane's word in tile columns xs .. xs+PXT+1 (128B swizzle: 16-byte chunk ^ (pixel & 7); the
         // row pitch is 32 pixels, so pixel & 7 depends on the column only)
         uint32_t off[PXT + 2];
 #pragma unroll
         for (int j = 0; j < PXT + 2; ++j) off[j] = (uint32_t)(xs + j) * 128 + ((lsw ^ (uint32_t)((xs + j) & 7)) << 4) + lw;
         const uint32_t tb = t_base + (b * NH) * PF_XCHUNK;
-        const int nq = ch_ok ? min(p.W - x0 - xs, PF_OW - xs) : 0, nr = p.H - y0;
+        const int nq = ch_ok ? p.W - x0 - xs : 0, nr = p.H - y0;
         uint8_t* orp = reinterpret_cast<uint8_t*>(p.out + (((long)img * p.H + y0) * p.W + x0 + xs) * p.ldo + ch);
         u64 acc[NH][3][PXT];
 #pragma unroll
@@ -305,14 +306,14 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < PXT + 2; ++j) v[j] = unpack2(lds32(tb + h * PF_XCHUNK + ir * (PF_TW * 128) + off[j]));
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const int orow = ir - dy;
-              if (orow >= 0 && orow < PF_OH) {
-                const int a = orow % 3;
+            for (int dx = 0; dx < 3; ++dx) {        // dx outermost: consecutive FFMA2s go to different accumulators
 #pragma unroll
-                for (int q = 0; q < PXT; ++q) {
+              for (int dy = 0; dy < 3; ++dy) {
+                const int orow = ir - dy;
+                if (orow >= 0 && orow < PF_OH) {
+                  const int a = orow % 3;
 #pragma unroll
-                  for (int dx = 0; dx < 3; ++dx) {
+                  for (int q = 0; q < PXT; ++q) {
                     if (dy == 0 && dx == 0) acc[h][a][q] = fmul2(v[q], w[h][0]);
                     else acc[h][a][q] = ffma2(v[q + dx], w[h][dy * 3 + dx], acc[h][a][q]);
                   }
@@ -370,7 +371,6 @@ int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.rstd = rstd; p.w9c = w9c; p.out = out; p.ldo = ldo;
   const int NH = gate ? 2 : 1;
-  // +1 KB: the last warp's two discarded columns read up to 2 pixels past the tile
   const uint32_t smem = 1024 + p.kc * NH * 8192 + p.kc * PF_XCHUNK + 2 * NH * PF_XCHUNK + 1024;
   static bool attr = false;
   if (!attr) {
