@@ -139,6 +139,11 @@ int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, cons
 int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
                   int gate, void* stream);
 
+/* Same fused stage, transposed schedule (pwdw_t.cu): the 1x1 runs as W1 . X^T so the fp32 accumulator has lane = channel and
+ * column = pixel, and the depthwise warps read their inputs straight from TMEM (t stays fp32, never leaves the SM). */
+int kdlae_pwdw_t(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
+                 int gate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -300,4 +300,12 @@ int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, cons
                      reinterpret_cast<bf16*>(out), gate ? Nt / 2 : Nt, nimg, H, W, C, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int kdlae_pwdw_t(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
+                 int gate, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && rstd && w1 && w9c && out, "kdlae_pwdw_t: NULL argument");
+  return kd::pwdw_t(reinterpret_cast<const bf16*>(x), C, rstd, reinterpret_cast<const bf16*>(w1), Nt, w9c,
+                    reinterpret_cast<bf16*>(out), gate ? Nt / 2 : Nt, nimg, H, W, C, gate, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

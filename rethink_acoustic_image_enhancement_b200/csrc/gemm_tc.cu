@@ -218,7 +218,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int r = quarter * 32 + lane;    // accumulator row (pixel within the tile)
     uint32_t it = 0, slab_ctr = 0;
     for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const TileCoord t = tile_coord(p, item);
+      TileCoord t = tile_coord(p, item);
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
       long prow; int y = 0, x = 0; bool valid;
       if (p.spatial) {
@@ -229,6 +229,11 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const long rr = (long)t.r0 + r;
         valid = rr < p.rows_per_group;
         prow = (long)t.g * p.rows_per_group + rr;
+        if (p.epi.mode == OUT_PLANAR_F32) {     // 1x1 to fp32 planes: (image, pixel) from the linear row; epilogue uses y*W + x
+          const long hw = (long)p.H * p.W;
+          t.img = (int)(prow / hw);
+          x = (int)(prow - (long)t.img * hw); y = 0;
+        }
       }
       const uint32_t t_row = tmem_base + acc * TC_NC_MAX + ((uint32_t)(quarter * 32) << 16);
       const int nbase = t.nchunk * p.nc;
@@ -443,7 +448,7 @@ bool conv_gemm_tc_eligible(const ConvOp& op) {
   if (op.c1 > 0 && (op.c1 % 8 || op.ld1 % 8 || (reinterpret_cast<uintptr_t>(op.a1) & 15))) return false;
   if (op.w_ld % 8 || op.w_tap_ld % 8 || (reinterpret_cast<uintptr_t>(op.w) & 15) || op.w_group_stride % 8) return false;
   if ((k33 || k333) && op.groups != 1) return false;
-  if (k11 && op.epi.mode != OUT_IDENTITY) return false;
+  if (k11 && op.epi.mode != OUT_IDENTITY && op.epi.mode != OUT_PLANAR_F32) return false;
   if (op.epi.mode == OUT_PIXEL_SHUFFLE && (op.epi.cq % 8 != 0)) return false;
   return true;
 }

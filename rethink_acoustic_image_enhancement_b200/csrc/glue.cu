@@ -545,6 +545,36 @@ int conv_few_out(const SmallConvOut& op, cudaStream_t s) {
   KD_LAUNCH_CHECK();
   return 0;
 }
+// ---- 3x3 tap gather-sum over per-tap partial planes (fp32 planar) ----
+__global__ void __launch_bounds__(256) k_tap_sum(const float* __restrict__ part, int cout, int H, int W, const float* __restrict__ res,
+                                                 long res_img, long res_ch, float* __restrict__ out, long out_img, long out_ch) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int img = blockIdx.z / cout, co = blockIdx.z - img * cout;
+  if (x >= W || y >= H) return;
+  const long HW = (long)H * W;
+  const float* pp = part + ((long)img * cout + co) * 9 * HW;
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(pp + t * HW + (long)yy * W + xx);
+  }
+  const long sp = (long)y * W + x;
+  if (res) acc += __ldg(res + img * res_img + co * res_ch + sp);
+  out[img * out_img + co * out_ch + sp] = acc;
+}
+
+int tap_sum(const float* part, int cout, int nimg, int H, int W, const float* res, long res_img, long res_ch, float* out, long out_img,
+            long out_ch, cudaStream_t s) {
+  KD_CHECK((long)nimg * cout <= 65535, "tap_sum: too many planes");
+  const double px = (double)nimg * cout * H * W;
+  ProfScope prof(PC_SMALL_CONV, s, 9.0 * px, px * (9 + 1 + (res ? 1 : 0)) * 4.0);
+  k_tap_sum<<<dim3(cdiv(W, 64), cdiv(H, 4), nimg * cout), 256, 0, s>>>(part, cout, H, W, res, res_img, res_ch, out, out_img, out_ch);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
 template int conv_few_out<float>(const SmallConvOut&, cudaStream_t);
 template int conv_few_out<bf16>(const SmallConvOut&, cudaStream_t);
 

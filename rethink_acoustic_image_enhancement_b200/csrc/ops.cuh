@@ -43,6 +43,9 @@ int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
 // fused LN-folded 1x1 conv -> depthwise 3x3 (-> GELU gate), bf16 tcgen05 (pwdw_tc.cu)
 bool pwdw_tc_eligible(int C, int Nt, int gate);
 // same fusion with the depthwise conv on the CUDA cores (packed FFMA2, pwdw_f2.cu); w9c: fp32 [9][Nt]
+bool pwdw_t_eligible(int C, int Nt, int gate);   // transposed schedule (pwdw_t.cu): depthwise inputs straight from TMEM
+int pwdw_t(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
+           int H, int W, int C, int gate, cudaStream_t s);
 bool pwdw_f2_eligible(int C, int Nt, int gate);
 int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
             int H, int W, int C, int gate, cudaStream_t s);
@@ -81,6 +84,10 @@ struct SmallConvOut {
   float* out = nullptr; long out_img = 0, out_ch = 0;          // planar output
 };
 template <typename T> int conv_few_out(const SmallConvOut& op, cudaStream_t s);
+// out[img, co, y, x] = sum_{tap} part[img, co*9 + tap, y+dy-1, x+dx-1] (zero outside) (+ res): finishes a 3x3 conv whose nine
+// per-tap channel contractions were computed as ONE 1x1 GEMM with 9*cout output columns (teacher.cu conv_to_planar)
+int tap_sum(const float* part, int cout, int nimg, int H, int W, const float* res, long res_img, long res_ch, float* out, long out_img,
+            long out_ch, cudaStream_t s);
 
 // pooling / resampling / misc glue
 template <typename T> int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s);

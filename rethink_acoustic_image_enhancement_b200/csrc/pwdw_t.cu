@@ -1,0 +1,449 @@
+// Fused  LayerNorm-folded 1x1 conv  ->  depthwise 3x3  (-> GELU gate), bf16 path, "transposed" schedule:
+//   qkv branch  (KDLAE_model.py:118-119):  qkv' = dw3x3(W_qkv . LN(x))
+//   GDFN branch (KDLAE_model.py:95-104):   g    = gelu(dw(t)[:h]) * dw(t)[h:],  t = W_in . LN(x)
+// The 1x1 conv runs on tcgen05 as  T^T = W1 . X^T  (M = 128 output channels, N = the pixels of a halo tile, K = C), so the
+// fp32 accumulator sits in TMEM with lane = channel and column = pixel.  That is exactly the orientation the depthwise
+// stage wants: a thread owns one channel (two with the gate: lane j holds x1-channel j in one column range and the matching
+// x2-channel j in another), pulls a row of pixels with tcgen05.ld (a second load shifted by one column gives the odd-aligned
+// register pairs), and runs the 3x3 taps as packed FFMA2 over pixel pairs with the tap weight broadcast.
+// Compared with pwdw_f2.cu (GEMM in the usual orientation, bf16 t tile in shared memory, channel-pair lanes) this removes the
+// TMEM->bf16->smem conversion pass, the t tile, the LDS + bf16 unpack of every input (which was ~40 % of the issue slots)
+// and keeps t in fp32.  LayerNorm's rstd[pixel] is a per-column scale here: a helper warp stages the tile's rstd values
+// (0 outside the image = the conv's zero padding of t) in shared memory, pair-aligned twice (even / odd columns).
+// Results leave through per-warp [pixel][32 ch] bf16 staging blocks and one small TMA store per warp and item (TMA clips at
+// the image edge), so the depthwise warps never synchronise with each other: with CTA-wide barriers per item they ran in
+// lockstep, all in their FFMA2 bursts at once (ncu: math-pipe throttle on top) and all idle together in the store phase.
+//   GATE = 0: tile = 8 x 32 pixels (6 x 30 outputs), item = (tile, 128 channels), D = 256 TMEM columns, double buffered.
+//   GATE = 1: tile = 8 x 16 pixels (6 x 14 outputs), item = (tile, 128 gated channels): x1 rows -> columns [0,128),
+//             x2 rows -> columns [128,256), double buffered.
+// Warps: 0 TMA producer, 1 MMA issuer, 2 rstd staging, 3 idle, 4.. depthwise (TMEM lane quarter = warp % 4).
+#include <algorithm>
+#include "sm100.cuh"
+
+namespace kd {
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float2 as_float2(u64 v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+__device__ __forceinline__ u64 pack2f(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 pack2u(uint32_t lo, uint32_t hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 splat2(float c) { return pack2f(c, c); }
+__device__ __forceinline__ u64 lds64(uint32_t addr) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+// gelu(a) * b on a packed pair (same arithmetic as dwconv_f2.cu / pwdw_f2.cu)
+__device__ __forceinline__ u64 gelu_gate2(u64 a, u64 b) {
+  const float2 x = as_float2(a);
+  const u64 q = pack2f(fabsf(x.x) * 0.84932180028801904272f, fabsf(x.y) * 0.84932180028801904272f);
+  const float2 d = as_float2(ffma2(q, splat2(0.27274160926128944f), splat2(1.0f)));
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d.y));
+  const u64 t = pack2f(t0, t1);
+  u64 y = ffma2(t, splat2(0.5f * 1.061405429f), splat2(0.5f * -1.453152027f));
+  y = ffma2(y, t, splat2(0.5f * 1.421413741f));
+  y = ffma2(y, t, splat2(0.5f * -0.284496736f));
+  y = ffma2(y, t, splat2(0.5f * 0.254829592f));
+  y = fmul2(y, t);
+  const float2 qq = as_float2(fmul2(q, q));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-qq.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-qq.y));
+  const float2 ye = as_float2(fmul2(y, pack2f(e0, e1)));
+  const float g0 = fmaf(-fabsf(x.x), ye.x, fmaxf(x.x, 0.f));
+  const float g1 = fmaf(-fabsf(x.y), ye.y, fmaxf(x.y, 0.f));
+  return fmul2(pack2f(g0, g1), b);
+}
+
+// tcgen05.ld 32x32b of 2 / 4 / 8 consecutive columns (this thread's TMEM lane)
+__device__ __forceinline__ void tld2(uint32_t a, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+__device__ __forceinline__ void tld4(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void tld8(uint32_t a, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
+}
+
+constexpr int PT_IH = 8, PT_OH = 6, PT_MB = 128;     // halo rows, output rows, channels per item
+template <int GATE> struct PtCfg {
+  static constexpr int PITCH = GATE ? 16 : 32;       // pixels per tile row (= TMEM columns per row)
+  static constexpr int OW = PITCH - 2;               // output columns per tile
+  static constexpr int NPX = PITCH * PT_IH;          // pixels per tile = GEMM N
+  static constexpr int NG = GATE ? 2 : 3;            // column groups of depthwise warps
+  static constexpr int GP = GATE ? 4 : 5;            // output pixel pairs per group per row (gate: 8 + 6 columns; 16 warps of
+                                                     // 4 + 4 + 4 + 2 columns were measured 5 % slower)
+  static constexpr int NDW = NG * 4;                 // depthwise warps
+  static constexpr int THREADS = (4 + NDW) * 32;
+  static constexpr uint32_t XCHUNK = NPX * 128;      // one 64-channel K chunk of the x tile
+  static constexpr uint32_t WSTAGE = 2 * GP * PT_OH * 64;   // per-warp staging block [row][column][32 ch] bf16
+  static constexpr uint32_t STAGE = NDW * WSTAGE;
+};
+
+struct PtParams {
+  int H, W, C, Nt, Cout, nimg;     // Nt = rows of W1 (3C or 2hp); Cout = output channels (3C or hp)
+  int kc;                          // 64-wide K chunks of C (1 or 2)
+  int tiles_x, tiles_y, ncb;
+  long ntiles_all;
+  float inv_tiles_x, inv_tiles_y;
+  const float* rstd;               // [nimg*H*W]
+  const float* w9c;                // depthwise weights fp32 [9][Nt]
+};
+
+template <int GATE>
+__global__ void __launch_bounds__(PtCfg<GATE>::THREADS, 1)
+k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+         const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out_last, const PtParams p) {
+  typedef PtCfg<GATE> Cfg;
+  constexpr int NH = GATE ? 2 : 1;
+  constexpr int PITCH = Cfg::PITCH, OW = Cfg::OW, NPX = Cfg::NPX, NG = Cfg::NG, GP = Cfg::GP, GW = 2 * GP;
+  constexpr uint32_t XCHUNK = Cfg::XCHUNK, STAGE = Cfg::STAGE, WSTAGE = Cfg::WSTAGE;
+  constexpr uint32_t W1CHUNK = PT_MB * 128;          // 128 rows x 64 channels of one chunk(2) half
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // smem (1024-aligned): W1 [kc][NH] chunks | x chunks | staging[2] | rs[2][NPX] (even pairs) + rsb[2][NPX] (odd pairs) | barriers
+  const uint32_t w1_base = sbase;
+  const uint32_t x_base = w1_base + p.kc * NH * W1CHUNK;
+  const uint32_t stage_base = x_base + p.kc * XCHUNK;
+  const uint32_t rs_base = stage_base + 2 * STAGE;
+  const uint32_t bar_base = rs_base + 4 * NPX * 4;
+  const uint32_t w_full = bar_base, w_empty = bar_base + 8, x_full = bar_base + 16, x_empty = bar_base + 24;
+  auto d_full = [&](int b) { return bar_base + 32 + 8u * b; };
+  auto d_empty = [&](int b) { return bar_base + 48 + 8u * b; };
+  auto rs_full = [&](int b) { return bar_base + 64 + 8u * b; };
+  auto rs_empty = [&](int b) { return bar_base + 80 + 8u * b; };
+  const uint32_t tmem_slot = bar_base + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* rs_gen = reinterpret_cast<float*>(smem_raw + (rs_base - smem_u32(smem_raw)));
+  uint8_t* stage_gen = smem_raw + (stage_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp = p.Nt / 2;
+  const int ksteps = (p.C + 15) / 16;
+  const int ntiles = ((long)blockIdx.x < p.ntiles_all) ? (int)((p.ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int ncb = p.ncb;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out); prefetch_tmap(&map_out_last);
+    mbar_init(w_full, 1); mbar_init(w_empty, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d_full(b), 1); mbar_init(d_empty(b), Cfg::NDW);
+      mbar_init(rs_full(b), 1); mbar_init(rs_empty(b), Cfg::NDW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_xy = [&](int i, int& img, int& y0, int& x0) {          // i-th tile of this CTA
+    const int t = blockIdx.x + i * gridDim.x;
+    const int rowt = fast_div(t, p.tiles_x, p.inv_tiles_x);
+    const int txi = t - rowt * p.tiles_x;
+    img = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
+    const int tyi = rowt - img * p.tiles_y;
+    x0 = txi * OW; y0 = tyi * PT_OH;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int i = 0; i < ntiles; ++i) {
+        int img, y0, x0;
+        if (i + 1 < ntiles) {   // the x tile is single buffered: keep the next one warm in L2
+          tile_xy(i + 1, img, y0, x0);
+          for (int k = 0; k < p.kc; ++k) tma_prefetch_4d(&map_x, k * 64, x0 - 1, y0 - 1, img);
+        }
+        mbar_wait_lazy(x_empty, (i & 1) ^ 1);        // last GEMM of tile i-1 retired
+        tile_xy(i, img, y0, x0);
+        mbar_expect_tx(x_full, p.kc * XCHUNK);
+        for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
+        for (int cb = 0; cb < ncb; ++cb, ++n) {
+          mbar_wait_lazy(w_empty, (n & 1) ^ 1);      // GEMM n-1 retired: the W1 buffer is free
+          mbar_expect_tx(w_full, p.kc * NH * W1CHUNK);
+          for (int k = 0; k < p.kc; ++k)
+            for (int h = 0; h < NH; ++h)
+              tma_load_3d(w1_base + (k * NH + h) * W1CHUNK, &map_w1, w_full, k * 64, (GATE ? h * hp : 0) + cb * PT_MB, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: T^T = W1 . X^T (A = W1 rows, B = pixels) =====================
+    if (lane == 0) {
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lo_tag = 1u << 16;
+      uint32_t n = 0;
+      for (int i = 0; i < ntiles; ++i) {
+        for (int cb = 0; cb < ncb; ++cb, ++n) {
+          const int b = n & 1;
+          mbar_wait_lazy(d_empty(b), ((n >> 1) & 1) ^ 1);   // depthwise warps have drained D[b] (item n-2)
+          mbar_wait_relaxed(w_full, n & 1);
+          if (cb == 0) mbar_wait_relaxed(x_full, i & 1);
+          tc_fence_after();
+          for (int h = 0; h < NH; ++h) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const int k = ks >> 2, kk = ks & 3;
+              const uint32_t a_lo = (((w1_base + (k * NH + h) * W1CHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+              const uint32_t b_lo = (((x_base + k * XCHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+              umma_bf16_lohi(tmem_base + b * 256 + h * NPX, a_lo, b_lo, desc_hi, idesc, ks != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(w_empty);                       // W1 block consumed
+          if (cb == ncb - 1) umma_commit(x_empty);    // x tile consumed
+          umma_commit(d_full(b));                     // accumulators ready
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== rstd staging: rs[p] = rstd of halo-tile pixel p (0 outside the image), rsb[p] = rs[p+1] ==========
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
+      int img, y0, x0;
+      tile_xy(i, img, y0, x0);
+      float v[NPX / 32];
+#pragma unroll
+      for (int j = 0; j < NPX / 32; ++j) {
+        const int pix = j * 32 + lane;
+        const int y = y0 - 1 + pix / PITCH, x = x0 - 1 + pix % PITCH;
+        const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W;
+        v[j] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;
+      }
+      mbar_wait_lazy(rs_empty(b), ((i >> 1) & 1) ^ 1);
+      float* rs = rs_gen + b * NPX;
+      float* rsb = rs_gen + (2 + b) * NPX;
+#pragma unroll
+      for (int j = 0; j < NPX / 32; ++j) {
+        const int pix = j * 32 + lane;
+        rs[pix] = v[j];
+        if (pix > 0) rsb[pix - 1] = v[j];
+      }
+      if (lane == 31) rsb[NPX - 1] = 0.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rs_full(b));
+    }
+  } else if (warp >= 4) {
+    // ===================== depthwise warps =====================
+    const int dwp = warp - 4;
+    const int quarter = warp & 3;                 // TMEM lane quarter (== dwp & 3)
+    const int g = dwp >> 2;                       // column group
+    const int s0 = g * GW;                        // first input column (tile coordinates) of this group
+    const int chl = quarter * 32 + lane;          // channel within the item
+    const bool last_g = (g == NG - 1);
+    const int gw = (GATE && last_g) ? OW - s0 : GW;     // output columns of this group (gate: 8, 6; otherwise 10 each)
+    uint32_t n = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      int img, y0, x0;
+      tile_xy(i, img, y0, x0);
+      mbar_wait_relaxed(rs_full(i & 1), (i >> 1) & 1);
+      const uint32_t rs_a = rs_base + ((i & 1) * NPX + s0) * 4;
+      const uint32_t rs_b = rs_base + ((2 + (i & 1)) * NPX + s0) * 4;
+      for (int cb = 0; cb < ncb; ++cb, ++n) {
+        const int b = n & 1;
+        const int ch = cb * PT_MB + chl;
+        const bool ch_ok = ch < p.Cout;
+        u64 w[NH][9];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) w[h][t] = splat2(ch_ok ? __ldg(p.w9c + (long)t * p.Nt + h * hp + ch) : 0.f);
+        mbar_wait_relaxed(d_full(b), (n >> 1) & 1);
+        tc_fence_after();
+        // this warp's staging block b was handed to TMA two items ago: wait until that store has read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t trow = tmem_base + b * 256 + ((uint32_t)(quarter * 32) << 16) + s0;
+        uint8_t* st = stage_gen + b * STAGE + dwp * WSTAGE + lane * 2;
+        u64 acc[NH][3][GP];
+#pragma unroll
+        for (int ir = 0; ir < PT_IH; ++ir) {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            // A: columns s0 .. s0+GW+1 (even-aligned pairs), B: columns s0+1 .. s0+GW (odd-aligned pairs)
+            uint32_t ra[GW + 2], rb[GW];
+            const uint32_t ta = trow + h * NPX + ir * PITCH;
+            if (GATE) {
+              tld8(ta, ra);
+              if (!last_g) tld2(ta + 8, ra[8], ra[9]); else { ra[8] = 0; ra[9] = 0; }
+              tld4(ta + 1, rb[0], rb[1], rb[2], rb[3]);
+              if (!last_g) tld4(ta + 5, rb[4], rb[5], rb[6], rb[7]);
+              else { tld2(ta + 5, rb[4], rb[5]); rb[6] = 0; rb[7] = 0; }
+            } else {
+              tld8(ta, ra);
+              tld4(ta + 8, ra[8], ra[9], ra[10], ra[11]);
+              tld8(ta + 1, rb);
+              tld2(ta + 9, rb[8], rb[9]);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            u64 va[GP + 1], vb[GP];
+#pragma unroll
+            for (int j = 0; j < GP + 1; ++j) va[j] = fmul2(pack2u(ra[2 * j], ra[2 * j + 1]), lds64(rs_a + (ir * PITCH + 2 * j) * 4));
+#pragma unroll
+            for (int j = 0; j < GP; ++j) vb[j] = fmul2(pack2u(rb[2 * j], rb[2 * j + 1]), lds64(rs_b + (ir * PITCH + 2 * j) * 4));
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int orow = ir - dy;
+              if (orow >= 0 && orow < PT_OH) {
+                const int a = orow % 3;
+#pragma unroll
+                for (int j = 0; j < GP; ++j) {
+                  if (dy == 0) acc[h][a][j] = fmul2(va[j], w[h][0]);
+                  else acc[h][a][j] = ffma2(va[j], w[h][dy * 3], acc[h][a][j]);
+                  acc[h][a][j] = ffma2(vb[j], w[h][dy * 3 + 1], acc[h][a][j]);
+                  acc[h][a][j] = ffma2(va[j + 1], w[h][dy * 3 + 2], acc[h][a][j]);
+                }
+              }
+            }
+          }
+          if (ir == PT_IH - 1) {                  // all TMEM reads of this item done: the GEMM of item n+2 may overwrite D[b]
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty(b));
+          }
+          if (ir >= 2) {
+            const int orow = ir - 2, a = orow % 3;
+#pragma unroll
+            for (int j = 0; j < GP; ++j) {
+              const float2 f = as_float2(GATE ? gelu_gate2(acc[0][a][j], acc[NH - 1][a][j]) : acc[0][a][j]);
+              // output columns 2j, 2j+1 of this group; the last group of the gate tile is 6 columns wide
+              if (2 * j < gw) {
+                *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j) * 64) = __float2bfloat16_rn(f.x);
+                *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j + 1) * 64) = __float2bfloat16_rn(f.y);
+              }
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          const CUtensorMap* mo = (GATE && last_g) ? &map_out_last : &map_out;
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(mo), "r"(stage_base + b * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + quarter * 32), "r"(x0 + s0), "r"(y0), "r"(img)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rs_empty(i & 1));
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+int g_pt_sms = 0;
+
+template <int GATE>
+int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg, int H,
+              int W, int C, cudaStream_t s) {
+  typedef PtCfg<GATE> Cfg;
+  PtParams p;
+  p.H = H; p.W = W; p.C = C; p.Nt = Nt; p.Cout = GATE ? Nt / 2 : Nt; p.nimg = nimg;
+  p.kc = (C + 63) / 64;
+  p.tiles_x = cdiv(W, Cfg::OW); p.tiles_y = cdiv(H, PT_OH); p.ncb = cdiv(p.Cout, PT_MB);
+  p.ntiles_all = (long)nimg * p.tiles_x * p.tiles_y;
+  KD_CHECK(p.ntiles_all < (1L << 24), "pwdw_t: too many tiles");
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  p.rstd = rstd; p.w9c = w9c;
+  const int NH = GATE ? 2 : 1;
+  const uint32_t smem = 1024 + p.kc * NH * PT_MB * 128 + p.kc * Cfg::XCHUNK + 2 * Cfg::STAGE + 4 * Cfg::NPX * 4 + 128;
+  KD_CHECK(smem <= 232448, "pwdw_t: shared memory budget exceeded (%u)", smem);
+  static bool attr = false;
+  if (!attr) {
+    KD_CUDA(cudaFuncSetAttribute(k_pwdw_t<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  CUtensorMap map_x, map_w1, map_out, map_out_last;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
+    const cuuint32_t box[4] = {64, (cuuint32_t)Cfg::PITCH, PT_IH, 1};
+    KD_TRY(make_map(&map_x, x, 4, dims, str, box));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Nt, 1};
+    const cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * Nt};
+    const cuuint32_t box[3] = {64, PT_MB, 1};
+    KD_TRY(make_map(&map_w1, w1, 3, dims, str, box));
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    const cuuint64_t str[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)ldo * 2 * W, (cuuint64_t)ldo * 2 * W * H};
+    const cuuint32_t box[4] = {32, (cuuint32_t)(2 * Cfg::GP), PT_OH, 1};
+    KD_TRY(make_map(&map_out, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+    const cuuint32_t box_last[4] = {32, (cuuint32_t)(Cfg::OW - (Cfg::NG - 1) * 2 * Cfg::GP), PT_OH, 1};
+    KD_TRY(make_map(&map_out_last, out, 4, dims, str, box_last, CU_TENSOR_MAP_SWIZZLE_NONE));
+  }
+  const double pix = (double)nimg * H * W;
+  ProfScope prof(PC_PWDW, s, 2.0 * pix * Nt * C + 18.0 * pix * Nt, pix * (C + p.Cout) * 2.0 + 4.0 * pix + 2.0 * Nt * C);
+  const int grid = (int)std::min<long>(p.ntiles_all, (long)g_pt_sms);
+  k_pwdw_t<GATE><<<grid, Cfg::THREADS, smem, s>>>(map_x, map_w1, map_out, map_out_last, p);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+bool pwdw_t_eligible(int C, int Nt, int gate) {
+  return C % 16 == 0 && C >= 16 && C <= 128 && Nt % 8 == 0 && (!gate || Nt % 16 == 0);
+}
+
+// x [nimg,H,W,C] (row stride ldx) --1x1 (w1: [Nt][C] bf16, LayerNorm gamma folded), * rstd--> t --dw3x3 (w9c fp32 [9][Nt])
+// --> [gate] --> out (row stride ldo)
+int pwdw_t(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg, int H,
+           int W, int C, int gate, cudaStream_t s) {
+  KD_CHECK(pwdw_t_eligible(C, Nt, gate), "pwdw_t: shape not eligible (C=%d Nt=%d)", C, Nt);
+  KD_CHECK(!(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && !(reinterpret_cast<uintptr_t>(w1) & 15) &&
+               ldx % 8 == 0 && ldo % 8 == 0,
+           "pwdw_t: misaligned operands");
+  if (g_pt_sms == 0) {
+    int dev = 0;
+    KD_CUDA(cudaGetDevice(&dev));
+    KD_CUDA(cudaDeviceGetAttribute(&g_pt_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_pt_sms = sm_limit(g_pt_sms);
+  }
+  return gate ? launch_pt<1>(x, ldx, rstd, w1, Nt, w9c, out, ldo, nimg, H, W, C, s)
+              : launch_pt<0>(x, ldx, rstd, w1, Nt, w9c, out, ldo, nimg, H, W, C, s);
+}
+
+}  // namespace kd

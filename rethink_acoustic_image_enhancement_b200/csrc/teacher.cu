@@ -170,14 +170,18 @@ struct Scratch {
 //   0  unfused (conv_gemm + dwconv3x3);
 //   1  both pairs through the all-tensor-core fused kernel pwdw_tc.cu, 2 only the qkv pair (bit-identical to each other;
 //      no faster than unfused: bound by the tensor core's shared-memory operand reads of the 9-tap depthwise MMAs);
-//   3  (default) both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
-//      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn.
+//   3  both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
+//      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn;
+//   6  both pairs through pwdw_t.cu (transposed GEMM, depthwise inputs read from TMEM in fp32), 7 (default) qkv via pwdw_t +
+//      ffn via pwdw_f2 (the fastest pairing measured: 94.6 vs 92.3 images/s for mode 3), 8 the other way round.
 inline int fuse_pwdw_mode() {
   const char* e = getenv("KDLAE_FUSE_PWDW");
-  return e ? atoi(e) : 3;
+  return e ? atoi(e) : 7;
 }
-inline bool fuse_f2_qkv(int m) { return m == 3 || m == 4; }
-inline bool fuse_f2_ffn(int m) { return m == 3 || m == 5; }
+inline bool fuse_f2_qkv(int m) { return m == 3 || m == 4 || m == 8; }
+inline bool fuse_f2_ffn(int m) { return m == 3 || m == 5 || m == 7; }
+inline bool fuse_t_qkv(int m) { return m == 6 || m == 7; }
+inline bool fuse_t_ffn(int m) { return m == 6 || m == 8; }
 
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
 // rows (C <= 256, one accumulator chunk), so only the first norm1 of a stage needs the stand-alone ln_stats pass.
@@ -198,7 +202,10 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   const bool fuse = (fmode == 1 || fmode == 2) && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
                     pwdw_tc_eligible(C, 3 * C, 0) && pwdw_tc_eligible(C, 2 * w.hp, 1);
   ConvOp g;
-  if (f2ok && fuse_f2_qkv(fmode)) {
+  if (f2ok && fuse_t_qkv(fmode)) {
+    KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
+                  reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
+  } else if (f2ok && fuse_f2_qkv(fmode)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
                    reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
   } else if (fuse) {
@@ -223,7 +230,10 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   KD_TRY(conv_gemm<T>(g, s));
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
-  if (f2ok && fuse_f2_ffn(fmode)) {
+  if (f2ok && fuse_t_ffn(fmode)) {
+    KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
+                  reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
+  } else if (f2ok && fuse_f2_ffn(fmode)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                    reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else if (fuse && fmode == 1) {
@@ -275,7 +285,21 @@ int conv3x3(const T* a, int cin, long lda, const T* w, int cout, int nimg, int H
 // in the bf16 path, CUDA-core direct conv otherwise
 template <typename T>
 int conv_to_planar(const T* in, int cin, long ld, const float* w_few, const T* w_tc, int cout, int nimg, int H, int W,
-                   const float* res, long res_img, long res_ch, float* out, long out_img, long out_ch, cudaStream_t s) {
+                   const float* res, long res_img, long res_ch, float* out, long out_img, long out_ch, float* part, cudaStream_t s) {
+  // bf16: the nine taps' channel contractions as ONE 1x1 tcgen05 GEMM with 9*cout output columns (w_tc [cout][9][cin] read as
+  // [9*cout][cin]) into fp32 planes, then a 9-point gather-sum.  The implicit-GEMM form needs 9 N=16 MMAs per K step for a
+  // single output channel and is bound by the tensor core's shared-memory operand reads (2.7 ms vs 0.5 ms at 16 x 1024^2).
+  if (w_tc != nullptr && part != nullptr) {
+    ConvOp g;
+    g.a0 = in; g.c0 = cin; g.ld0 = ld; g.nimg = nimg; g.H = H; g.W = W;
+    g.w = w_tc; g.w_ld = cin; g.w_tap_ld = cin;
+    g.epi.mode = OUT_PLANAR_F32; g.epi.N = 9 * cout; g.epi.H = H; g.epi.W = W;
+    g.epi.planar_out = part; g.epi.planar_img = 9L * cout * H * W; g.epi.planar_ch = (long)H * W;
+    if (conv_gemm_tc_eligible(g)) {
+      KD_TRY(conv_gemm_tc(g, s));
+      return tap_sum(part, cout, nimg, H, W, res, res_img, res_ch, out, out_img, out_ch, s);
+    }
+  }
   if (w_tc != nullptr) {
     ConvOp g;
     g.a0 = in; g.c0 = cin; g.ld0 = ld; g.nimg = nimg; g.H = H; g.W = W; g.kh = 3; g.kw = 3;
@@ -498,7 +522,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
     KD_CHECK(ic == oc, "KDLAE_teacher: out + inp_img needs inp_channels == out_channels");
     const float* last_w = w.output; const T* last_w_tc = w.output_tc;
     if (c.params_cat) {
-      KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, w.output, w.output_tc, oc, n, H, W, nullptr, 0, 0, o1, oc * HW, HW, s));
+      KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, w.output, w.output_tc, oc, n, H, W, nullptr, 0, 0, o1, oc * HW, HW, reinterpret_cast<float*>(sc.bufA), s));
       fi = SmallConv();
       fi.in0 = o1; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc;
       fi.in1 = rate_b; fi.in1_img = HW; fi.in1_ch = HW; fi.cin1 = 1;
@@ -508,7 +532,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       last_w = w.output2; last_w_tc = w.output2_tc;
     }
     // out_hq = out + inp_img (:321)
-    KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, last_w, last_w_tc, oc, n, H, W, img_b, ic * HW, HW, hq_b, oc * HW, HW, s));
+    KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, last_w, last_w_tc, oc, n, H, W, img_b, ic * HW, HW, hq_b, oc * HW, HW, reinterpret_cast<float*>(sc.bufA), s));
     // 7. SR head (:324-329): cen -> upen (PixelShuffle) -> enhance -> outputen
     if (c.sr_head) {
       fi = SmallConv();
@@ -517,7 +541,8 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       KD_TRY(conv_few_in<T>(fi, s));
       KD_TRY(conv3x3<T>(d1, 2 * d, 2 * d, w.upen, 4 * d, n, H, W, OUT_PIXEL_SHUFFLE, s0, d, 0, s));
       KD_TRY(run_blocks<T>(w.enhance, lnb, s0, d, s0, d, n, 2 * H, 2 * W, sc, s));
-      KD_TRY(conv_to_planar<T>(s0, d, d, w.outputen, w.outputen_tc, oc, n, 2 * H, 2 * W, nullptr, 0, 0, sr_b, oc * HW * 4, HW * 4, s));
+      KD_TRY(conv_to_planar<T>(s0, d, d, w.outputen, w.outputen_tc, oc, n, 2 * H, 2 * W, nullptr, 0, 0, sr_b, oc * HW * 4, HW * 4,
+                               reinterpret_cast<float*>(sc.bufA), s));
     }
   }
   return 0;

@@ -258,3 +258,30 @@ def test_fused_conv1x1_dwconv3x3_cuda_core(lib, shape):
     torch.cuda.synchronize()
     if os.environ.get("KDLAE_DW", "f2") == "f2":
         assert torch.equal(out, out2), f"fused vs unfused differ by {(out.float() - out2.float()).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 72, 48, 144, 0), (2, 16, 33, 96, 288, 0), (1, 24, 64, 48, 256, 1), (1, 36, 36, 96, 512, 1),
+                                   (3, 9, 5, 48, 144, 0), (1, 6, 30, 128, 384, 0), (2, 13, 61, 16, 48, 1), (1, 64, 64, 96, 512, 1)])
+def test_fused_conv1x1_dwconv3x3_transposed(lib, shape):
+    """k_pwdw_t (W1 . X^T on tcgen05, depthwise inputs read from TMEM in fp32): against float64 with t kept unrounded."""
+    n, H, W, C, Nt, gate = shape
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(n, H, W, C, generator=g).to(DEV).bfloat16()
+    rstd = (0.5 + torch.rand(n, H, W, generator=g)).to(DEV)
+    w1 = (torch.randn(Nt, C, generator=g) / C ** 0.5).to(DEV).bfloat16()
+    wd = torch.randn(Nt, 1, 3, 3, generator=g) / 3
+    w9c = wd.view(Nt, 9).t().contiguous().to(DEV)
+    Co = Nt // 2 if gate else Nt
+    out = torch.full((n, H, W, Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.kdlae_pwdw_t(x.data_ptr(), rstd.data_ptr(), w1.data_ptr(), Nt, w9c.data_ptr(), out.data_ptr(), n, H, W, C, gate,
+                                _stream()), "pwdw_t")
+    torch.cuda.synchronize()
+    t = (x.double().cpu() @ w1.double().cpu().t()) * rstd.double().cpu().unsqueeze(-1)
+    y = F.conv2d(t.permute(0, 3, 1, 2), wd.double(), padding=1, groups=Nt)
+    if gate:
+        y = F.gelu(y[:, :Co]) * y[:, Co:]
+    ref = y.permute(0, 2, 3, 1)
+    assert torch.isfinite(out).all()
+    err = (out.double().cpu() - ref).abs().max().item()
+    print(f"pwdw_t {shape}: max err {err:.3e} (ref max {ref.abs().max().item():.2f})")
+    assert err < 6e-3 * max(1.0, ref.abs().max().item())      # one bf16 rounding of the result

@@ -81,10 +81,11 @@ def test_teacher_128_against_oracle_and_batch_invariance(precision):
     assert torch.equal(out["hq"][2:3], one["hq"]) and torch.equal(out["sr"][2:3], one["sr"])
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5", "6", "7", "8"])
 def test_teacher_fused_conv1x1_dwconv_schedule_matches_reference(mode, manifest, monkeypatch):
     """KDLAE_FUSE_PWDW: every schedule of the 1x1 -> depthwise pairs (unfused 0, all-tensor-core fused 1/2, tcgen05 + FFMA2
-    fused 3/4/5 with 3 the default) must hold the parity gate; 3/4/5 are bit-identical to the unfused schedule."""
+    fused 3/4/5, transposed-GEMM fused 6/7/8 with 7 the default) must hold the parity gate; 3/4/5 are bit-identical to the
+    unfused schedule (6/7/8 keep the intermediate in fp32 instead of rounding it to bf16)."""
     monkeypatch.setenv("KDLAE_FUSE_PWDW", mode)
     name = "teacher_c1_biasfree_64"
     case, g = manifest[name], load_golden(name)
