@@ -391,67 +391,81 @@ template <typename T, int CIN, int KD>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
   extern __shared__ __align__(16) float wsm_in[];   // [KD*9*CIN][cout]
   constexpr int TAPS = KD * 9;
+  constexpr int PXF = (KD == 1) ? 4 : 1;            // consecutive output pixels per thread: one weight fetch feeds PXF pixels
   for (int e = threadIdx.x; e < TAPS * CIN * op.cout; e += blockDim.x) wsm_in[e] = op.w[e];
   __syncthreads();
   const unsigned cgroups = op.cout / 8;
-  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index math: one image per blockIdx.y
-  if (idx >= (unsigned)op.H * op.W * cgroups) return;
-  const int cg = (int)(idx % cgroups); idx /= cgroups;
-  const int x = (int)(idx % (unsigned)op.W);
-  const int y = (int)(idx / (unsigned)op.W);
+  const unsigned xgroups = (unsigned)(op.W + PXF - 1) / PXF;
+  const unsigned total = (unsigned)op.H * xgroups * cgroups;     // 32-bit index math: one image per blockIdx.y
   const int img = blockIdx.y;
   const int d = img % op.D, b = img / op.D;
-  float in[TAPS * CIN];
+  // grid-stride over (row, pixel group, channel group): the weight staging above is paid once per block
+  for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += gridDim.x * blockDim.x) {
+    unsigned idx = idx0;
+    const int cg = (int)(idx % cgroups); idx /= cgroups;
+    const int x0 = (int)(idx % xgroups) * PXF;
+    const int y = (int)(idx / xgroups);
+    float acc[PXF][8];
 #pragma unroll
-  for (int td = 0; td < KD; ++td) {
-    const int dd = d + td - KD / 2;
-    const bool d_ok = dd >= 0 && dd < op.D;
-    const long im = (long)b * op.D + dd;
+    for (int q = 0; q < PXF; ++q)
 #pragma unroll
-    for (int ty = 0; ty < 3; ++ty) {
-      const int yy = y + (ty - 1) * op.dil;
+      for (int i = 0; i < 8; ++i) acc[q][i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
 #pragma unroll
-      for (int tx = 0; tx < 3; ++tx) {
-        const int xx = x + (tx - 1) * op.dil;
-        const bool ok = d_ok && yy >= 0 && yy < Hin && xx >= 0 && xx < Win;
-        const long sp = (long)yy * Win + xx;
+    for (int td = 0; td < KD; ++td) {
+      const int dd = d + td - KD / 2;
+      const bool d_ok = dd >= 0 && dd < op.D;
+      const long im = (long)b * op.D + dd;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) {
-          float v = 0.f;
-          if (ok) {
-            if (c < op.cin0) {
-              const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
-              v = __ldg(op.in0 + o);
-              if (op.sub0) v -= __ldg(op.sub0 + o);
-            } else {
-              v = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp);
+      for (int ty = 0; ty < 3; ++ty) {
+        const int yy = y + (ty - 1) * op.dil;
+        const bool y_ok = d_ok && yy >= 0 && yy < Hin;
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            float v[PXF];
+#pragma unroll
+            for (int q = 0; q < PXF; ++q) {
+              const int xx = x0 + q + (tx - 1) * op.dil;
+              float t = 0.f;
+              if (y_ok && xx >= 0 && xx < Win) {
+                const long sp = (long)yy * Win + xx;
+                if (c < op.cin0) {
+                  const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
+                  t = __ldg(op.in0 + o);
+                  if (op.sub0) t -= __ldg(op.sub0 + o);
+                } else {
+                  t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp);
+                }
+              }
+              v[q] = t;
+            }
+            const float* wp = wsm_in + (((td * 3 + ty) * 3 + tx) * CIN + c) * op.cout + cg * 8;
+            const float4 wa = *reinterpret_cast<const float4*>(wp);
+            const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+            for (int q = 0; q < PXF; ++q) {
+              acc[q][0] = fmaf(v[q], wa.x, acc[q][0]); acc[q][1] = fmaf(v[q], wa.y, acc[q][1]);
+              acc[q][2] = fmaf(v[q], wa.z, acc[q][2]); acc[q][3] = fmaf(v[q], wa.w, acc[q][3]);
+              acc[q][4] = fmaf(v[q], wb.x, acc[q][4]); acc[q][5] = fmaf(v[q], wb.y, acc[q][5]);
+              acc[q][6] = fmaf(v[q], wb.z, acc[q][6]); acc[q][7] = fmaf(v[q], wb.w, acc[q][7]);
             }
           }
-          in[((td * 3 + ty) * 3 + tx) * CIN + c] = v;
         }
       }
     }
-  }
-  float acc[8];
+    T* out = reinterpret_cast<T*>(op.out);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
+    for (int q = 0; q < PXF; ++q) {
+      if (x0 + q < op.W) {
+        if (op.relu) {
 #pragma unroll
-  for (int k = 0; k < TAPS * CIN; ++k) {
-    const float* wp = wsm_in + k * op.cout + cg * 8;
-    const float4 wa = *reinterpret_cast<const float4*>(wp);
-    const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
-    const float v = in[k];
-    acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]);
-    acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
-    acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]);
-    acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+          for (int i = 0; i < 8; ++i) acc[q][i] = fmaxf(acc[q][i], 0.f);
+        }
+        store8<T>(out + (((long)img * op.H + y) * op.W + x0 + q) * op.out_ld + cg * 8, acc[q]);
+      }
+    }
   }
-  if (op.relu) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-  }
-  T* out = reinterpret_cast<T*>(op.out);
-  store8<T>(out + (((long)img * op.H + y) * op.W + x) * op.out_ld + cg * 8, acc);
 }
 
 template <typename T>
@@ -459,12 +473,13 @@ int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
   const int cin = op.cin0 + op.cin1;
   KD_CHECK(cin >= 1 && cin <= 4 && (op.kd == 1 || (op.kd == 3 && cin == 1)), "conv_few_in: unsupported cin=%d kd=%d", cin, op.kd);
-  const long total = (long)op.H * op.W * (op.cout / 8);
-  KD_CHECK(total < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
+  const int pxf = op.kd == 1 ? 4 : 1;               // must match PXF in the kernel
+  const long total = (long)op.H * ((op.W + pxf - 1) / pxf) * (op.cout / 8);
+  KD_CHECK((long)op.H * op.W * (op.cout / 8) < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
   const double fi_pix = (double)op.nimg * op.H * op.W;
   ProfScope prof(PC_SMALL_CONV, s, 2.0 * fi_pix * op.cout * cin * 9 * op.kd,
                  fi_pix * (4.0 * cin * (op.sub0 ? 2 : 1) + (double)op.cout * sizeof(T)));
-  const dim3 grid(cdiv(total, 128), op.nimg);
+  const dim3 grid((unsigned)std::min<long>(cdiv(total, 128), std::max<long>(1, 148L * 16 / op.nimg)), op.nimg);
   const size_t smem = sizeof(float) * (size_t)op.kd * 9 * cin * op.cout;
   KD_CHECK(smem <= 48 * 1024, "conv_few_in: weights do not fit shared memory");
   if (op.kd == 3) k_conv_few_in<T, 1, 3><<<grid, 128, smem, s>>>(op, Hin, Win);

@@ -15,10 +15,17 @@ namespace kd {
 namespace {
 
 constexpr int GR_PIX = 64;                       // pixels per stage (4 MMA k-steps)
-constexpr int GR_STAGES = 4;
 constexpr uint32_t GR_ATOM = GR_PIX * 128;       // 64 pixels x 64 channels bf16 = 8 KB
-constexpr uint32_t GR_STAGE_BYTES = 4 * GR_ATOM; // q atom0/1, k atom0/1
-constexpr uint32_t GR_SMEM = GR_STAGES * GR_STAGE_BYTES + 1024 + 128;
+// NATOMS = 64-channel atoms per operand (1: head width <= 64, the KDLAE case; 2: up to 128).
+// NATOMS = 1: 6 stages of 16 KB and 256 TMEM columns, so two CTAs share an SM (one CTA's ramp-up / epilogue hides under the
+// other's stream); NATOMS = 2: 4 stages of 32 KB, 512 columns, one CTA per SM.
+template <int NATOMS> struct GrCfg {
+  static constexpr int STAGES = NATOMS == 1 ? 6 : 4;
+  static constexpr uint32_t STAGE_BYTES = 2 * NATOMS * GR_ATOM;    // q atoms, then k atoms
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 128;
+  static constexpr int ACC = NATOMS * 64;                          // TMEM columns per accumulator (G, Nq, Nk)
+  static constexpr int TMEM_COLS = NATOMS == 1 ? 256 : 512;
+};
 
 // MN-major SWIZZLE_128B descriptor: 64-element (128 B) MN chunks, 8 K-rows per 1024 B atom,
 // SBO = stride between 8-row K groups, LBO = stride between 64-wide MN chunks.
@@ -44,8 +51,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128, 1)
+template <int NATOMS>
+__global__ void __launch_bounds__(128, NATOMS == 1 ? 2 : 1)
 k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads, int splits, int per, float* __restrict__ part) {
+  constexpr int GR_STAGES = GrCfg<NATOMS>::STAGES, ACC = GrCfg<NATOMS>::ACC;
+  constexpr uint32_t GR_STAGE_BYTES = GrCfg<NATOMS>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = sbase + GR_STAGES * GR_STAGE_BYTES;
@@ -58,7 +68,7 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
   const int ch = C / heads;
   const int split = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int natoms = (ch > 64) ? 2 : 1;
+  constexpr int natoms = NATOMS;
   const int p_begin = split * per;
   const int p_end = min(HW, p_begin + per);
   const int nchunks = (p_end > p_begin) ? (p_end - p_begin + GR_PIX - 1) / GR_PIX : 0;
@@ -70,7 +80,7 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(GrCfg<NATOMS>::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -88,7 +98,7 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
       mbar_expect_tx(full_bar(s), 2 * natoms * GR_ATOM);
       const int p = p_begin + i * GR_PIX;
       tma_load_3d(dst, &map, full_bar(s), cq, p, img);
-      tma_load_3d(dst + 2 * GR_ATOM, &map, full_bar(s), ck, p, img);
+      tma_load_3d(dst + natoms * GR_ATOM, &map, full_bar(s), ck, p, img);
       if (natoms == 2) {
         tma_load_3d(dst + GR_ATOM, &map, full_bar(s), cq + 64, p, img);
         tma_load_3d(dst + 3 * GR_ATOM, &map, full_bar(s), ck + 64, p, img);
@@ -102,14 +112,14 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
       const int s = i % GR_STAGES;
       mbar_wait(full_bar(s), (i / GR_STAGES) & 1);
       tc_fence_after();
-      const uint32_t qa = sbase + s * GR_STAGE_BYTES, ka = qa + 2 * GR_ATOM;
+      const uint32_t qa = sbase + s * GR_STAGE_BYTES, ka = qa + natoms * GR_ATOM;
 #pragma unroll
       for (int k = 0; k < GR_PIX / 16; ++k) {
         const uint64_t dq = make_desc_mn(qa + k * 2048, lbo), dk = make_desc_mn(ka + k * 2048, lbo);
         const uint32_t accum = (i | k) != 0 ? 1u : 0u;
         umma_bf16(tmem_base + 0, dq, dk, idesc, accum);     // G  = q^T k
-        umma_bf16(tmem_base + 128, dq, dq, idesc, accum);   // Nq = q^T q
-        umma_bf16(tmem_base + 256, dk, dk, idesc, accum);   // Nk = k^T k
+        umma_bf16(tmem_base + ACC, dq, dq, idesc, accum);       // Nq = q^T q
+        umma_bf16(tmem_base + 2 * ACC, dk, dk, idesc, accum);   // Nk = k^T k
       }
       umma_commit(empty_bar(s));
     }
@@ -128,8 +138,8 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
     for (int c0 = 0; c0 < ch; c0 += 16) {
       uint32_t g[16], a[16], b[16];
       tmem_ld16(t_row + c0, g);
-      tmem_ld16(t_row + 128 + c0, a);
-      tmem_ld16(t_row + 256 + c0, b);
+      tmem_ld16(t_row + ACC + c0, a);
+      tmem_ld16(t_row + 2 * ACC + c0, b);
       if (i < ch) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -146,7 +156,7 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(GrCfg<NATOMS>::TMEM_COLS));
   }
 }
 
@@ -158,7 +168,8 @@ int mdta_gram_tc(const bf16* qk, long ld, int nimg, int HW, int C, int heads, in
   if (ch % 16 || ch > 128 || ch < 16 || ld % 8 || (reinterpret_cast<uintptr_t>(qk) & 15) || C % 8) return -1;
   static bool attr = false;
   if (!attr) {
-    KD_CUDA(cudaFuncSetAttribute(k_mdta_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM));
+    KD_CUDA(cudaFuncSetAttribute(k_mdta_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GrCfg<1>::SMEM));
+    KD_CUDA(cudaFuncSetAttribute(k_mdta_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GrCfg<2>::SMEM));
     attr = true;
   }
   CUtensorMap map;
@@ -170,7 +181,8 @@ int mdta_gram_tc(const bf16* qk, long ld, int nimg, int HW, int C, int heads, in
   per = (per + GR_PIX - 1) / GR_PIX * GR_PIX;   // split boundaries on 64-pixel chunks; the tail is TMA zero fill
   ProfScope prof(PC_MDTA_GRAM, s, 2.0 * nimg * HW * C * ch + 4.0 * nimg * HW * C,
                  (double)nimg * HW * 2 * C * 2.0 + 4.0 * nimg * heads * splits * (ch * ch + 2 * ch));
-  k_mdta_gram_tc<<<dim3(splits, heads, nimg), 128, GR_SMEM, s>>>(map, HW, C, heads, splits, per, part);
+  if (ch <= 64) k_mdta_gram_tc<1><<<dim3(splits, heads, nimg), 128, GrCfg<1>::SMEM, s>>>(map, HW, C, heads, splits, per, part);
+  else k_mdta_gram_tc<2><<<dim3(splits, heads, nimg), 128, GrCfg<2>::SMEM, s>>>(map, HW, C, heads, splits, per, part);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
