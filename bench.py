@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="for ncu launch lists: warm-up + timed device steps only (no e2e leg, no CPU baseline, no event profile); "
+                         "the printed line is not a bench value")
     ap.add_argument("--extras", action="store_true", help="also time KDLAE-S (config 3) and ASDQE (config 4) on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -271,6 +274,13 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public module with host buffers ("e2e") ----
     step_e2e()
