@@ -193,10 +193,16 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
         for (int cb = 0; cb < ncb; ++cb, ++n) {
           mbar_wait_lazy(w_empty, (n & 1) ^ 1);      // GEMM n-1 retired: the W1 buffer is free
-          mbar_expect_tx(w_full, p.kc * NH * W1CHUNK);
+          // W1 rows arrive per TMEM lane quarter (32 rows): a partial last block only loads its valid quarters, rotated by the
+          // tile index so that the extra work lands on a different scheduler every tile (see the depthwise warps)
+          const int nvalid = min(PT_MB, p.Cout - cb * PT_MB);
+          const int nq = (nvalid + 31) >> 5, rot = (nq < 4) ? (i & 3) : 0;
+          mbar_expect_tx(w_full, p.kc * NH * nq * 4096);
           for (int k = 0; k < p.kc; ++k)
             for (int h = 0; h < NH; ++h)
-              tma_load_3d(w1_base + (k * NH + h) * W1CHUNK, &map_w1, w_full, k * 64, (GATE ? h * hp : 0) + cb * PT_MB, 0);
+              for (int lq = 0; lq < nq; ++lq)
+                tma_load_3d(w1_base + (k * NH + h) * W1CHUNK + ((lq + rot) & 3) * 4096, &map_w1, w_full, k * 64,
+                            (GATE ? h * hp : 0) + cb * PT_MB + lq * 32, 0);
         }
       }
     }
@@ -261,7 +267,6 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
     const int quarter = warp & 3;                 // TMEM lane quarter (== dwp & 3)
     const int g = dwp >> 2;                       // column group
     const int s0 = g * GW;                        // first input column (tile coordinates) of this group
-    const int chl = quarter * 32 + lane;          // channel within the item
     const bool last_g = (g == NG - 1);
     const int gw = (GATE && last_g) ? OW - s0 : GW;     // output columns of this group (gate: 8, 6; otherwise 10 each)
     uint32_t n = 0;
@@ -273,7 +278,18 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
       const uint32_t rs_b = rs_base + ((2 + (i & 1)) * NPX + s0) * 4;
       for (int cb = 0; cb < ncb; ++cb, ++n) {
         const int b = n & 1;
-        const int ch = cb * PT_MB + chl;
+        // logical quarter of this warp in the item's channel block (partial blocks are rotated by the tile index); warps whose
+        // quarter holds no channel skip the item, so the depthwise work is proportional to the valid channels
+        const int nvalid = min(PT_MB, p.Cout - cb * PT_MB);
+        const int nq = (nvalid + 31) >> 5, rot = (nq < 4) ? (i & 3) : 0;
+        const int lq = (quarter - rot) & 3;
+        if (lq >= nq) {
+          mbar_wait_relaxed(d_full(b), (n >> 1) & 1);     // keeps the d_empty phase accounting in step
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty(b));
+          continue;
+        }
+        const int ch = cb * PT_MB + lq * 32 + lane;
         const bool ch_ok = ch < p.Cout;
         u64 w[NH][9];
 #pragma unroll
@@ -351,7 +367,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         if (lane == 0) {
           const CUtensorMap* mo = (GATE && last_g) ? &map_out_last : &map_out;
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                       ::"l"(mo), "r"(stage_base + b * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + quarter * 32), "r"(x0 + s0), "r"(y0), "r"(img)
+                       ::"l"(mo), "r"(stage_base + b * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + lq * 32), "r"(x0 + s0), "r"(y0), "r"(img)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -402,7 +418,7 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   {
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Nt, 1};
     const cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * Nt};
-    const cuuint32_t box[3] = {64, PT_MB, 1};
+    const cuuint32_t box[3] = {64, 32, 1};      // one TMEM lane quarter of W1 rows per load
     KD_TRY(make_map(&map_w1, w1, 3, dims, str, box));
   }
   {
