@@ -234,26 +234,28 @@ def main():
     # in and chunk k-1 out while chunk k computes (the usual way to feed an inference module from host memory)
     chunk = min(B, 16)
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    nchunks = (B + chunk - 1) // chunk
+    im_d = [torch.empty_like(img_d[c * chunk:(c + 1) * chunk]) for c in range(nchunks)]     # device staging, reused every step
+    rt_d = [torch.empty_like(rate_d[c * chunk:(c + 1) * chunk]) for c in range(nchunks)]
 
     def step_e2e():
         cur = torch.cuda.current_stream()
         with torch.no_grad():
-            staged = []
-            for c0 in range(0, B, chunk):
-                with torch.cuda.stream(s_in):
-                    im = img_h[c0:c0 + chunk].to(dev, non_blocking=True)
-                    rt = rate_h[c0:c0 + chunk].to(dev, non_blocking=True)
-                    ev = torch.cuda.Event(); ev.record(s_in)
-                staged.append((c0, im, rt, ev))
-            for c0, im, rt, ev in staged:
-                cur.wait_event(ev)
-                out = model({"img": im, "denoise_rate": rt})
-                im.record_stream(cur); rt.record_stream(cur)
+            s_in.wait_stream(cur)                      # last step's kernels have consumed the staging buffers
+            evs = []
+            with torch.cuda.stream(s_in):
+                for c in range(nchunks):
+                    im_d[c].copy_(img_h[c * chunk:(c + 1) * chunk], non_blocking=True)
+                    rt_d[c].copy_(rate_h[c * chunk:(c + 1) * chunk], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(s_in); evs.append(ev)
+            for c in range(nchunks):
+                cur.wait_event(evs[c])
+                out = model({"img": im_d[c], "denoise_rate": rt_d[c]})
                 done = torch.cuda.Event(); done.record(cur)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(done)
-                    hq_h[c0:c0 + chunk].copy_(out["hq"], non_blocking=True)
-                    sr_h[c0:c0 + chunk].copy_(out["sr"], non_blocking=True)
+                    hq_h[c * chunk:(c + 1) * chunk].copy_(out["hq"], non_blocking=True)
+                    sr_h[c * chunk:(c + 1) * chunk].copy_(out["sr"], non_blocking=True)
                     out["hq"].record_stream(s_out); out["sr"].record_stream(s_out)
             cur.wait_stream(s_out)
 
@@ -283,7 +285,8 @@ def main():
         return
 
     # ---- end to end through the public module with host buffers ("e2e") ----
-    step_e2e()
+    for _ in range(2):          # un-timed: lets the caching allocator reach its steady state for the per-chunk outputs
+        step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -35,6 +35,7 @@ struct C3Params {
   long items;
   int H, W, tiles_x, tiles_y;
   int has_res, relu;
+  int w_resident;            // 1: all 9 tap tiles of the (single) K chunk fit the weight ring -> loaded once per CTA
   float inv_n_chunks, inv_tiles_x, inv_tiles_y, inv_D;
   Epilogue epi;
 };
@@ -112,6 +113,11 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     // ===================== TMA producer: A tiles (one per 9 taps) and W tiles (one per tap) =====================
     if (lane == 0) {
       uint32_t aidx = 0, bidx = 0;
+      if (p.w_resident) {          // weight-stationary: 9 x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
+        mbar_expect_tx(b_full(0), 9u * (uint32_t)p.nc * 128);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), (int)(tap * p.w_tap_ld), 0, 0);
+      }
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const C3Tile t = c3_tile(p, item);
         int fb = 0, fd = 0;
@@ -126,7 +132,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             mbar_expect_tx(a_full(s), C3_A_BYTES);
             if (p.kd == 3) tma_load_5d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, fd + td - 1, fb);
             else tma_load_4d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, t.img);
-            for (int tap = 0; tap < 9; ++tap, ++bidx) {
+            for (int tap = 0; tap < 9 && !p.w_resident; ++tap, ++bidx) {
               const int bs = bidx % C3_BSLOTS;
               mbar_wait_relaxed(b_empty(bs), ((bidx / C3_BSLOTS) & 1) ^ 1);
               mbar_expect_tx(b_full(bs), (uint32_t)p.nc * 128);
@@ -144,6 +150,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t lo_tag = 1u << 16;
       uint32_t aidx = 0, bidx = 0, it = 0;
+      if (p.w_resident) mbar_wait(b_full(0), 0);
       for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1, aph = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -156,15 +163,16 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bidx) {
             const int bs = bidx % C3_BSLOTS;
-            mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1);
+            if (!p.w_resident) mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1);
             tc_fence_after();
             const int dy = tap / 3, dx = tap - dy * 3;
             const uint32_t a_lo = a_lo0 + (uint32_t)((dy * C3_TW + dx) * 8);
-            const uint32_t b_lo = (((b_base + bs * C3_B_SLOT) & 0x3FFFF) >> 4) | lo_tag;
+            const uint32_t b_addr = p.w_resident ? b_base + tap * p.nc * 128 : b_base + bs * C3_B_SLOT;
+            const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | lo_tag;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
-            umma_commit(b_empty(bs));
+            if (!p.w_resident) umma_commit(b_empty(bs));
           }
           umma_commit(a_empty(s));
         }
@@ -343,6 +351,7 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   p.items = (long)op.nimg * p.tiles_x * p.tiles_y * n_chunks;
   KD_CHECK(p.items < (1L << 24), "conv3x3_tc: too many tiles (%ld)", p.items);
   p.has_res = e.res != nullptr; p.relu = e.relu;
+  p.w_resident = (op.kd == 1 && p.kc0 + p.kc1 == 1 && n_chunks == 1 && 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT) ? 1 : 0;
   p.inv_n_chunks = 1.0f / (float)n_chunks; p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.inv_D = 1.0f / (float)(op.D > 0 ? op.D : 1);
   p.epi = e;

@@ -387,11 +387,12 @@ template int mdta_fold<bf16>(float*, int, int, int, int, const float*, const flo
 // =====================================================================================
 // CIN = total input planes (1..4), KD = temporal taps (1 or 3).  All tap inputs are gathered first (independent,
 // predicated loads), the [taps*CIN][cout] weights sit in shared memory.
-template <typename T, int CIN, int KD>
+// PXF = consecutive output pixels per thread: one weight fetch feeds PXF pixels (wide outputs: the weight LDS traffic is the
+// limiter); narrow outputs (ASDQE stems, 16 channels) keep PXF = 1 so a warp's input loads stay contiguous.
+template <typename T, int CIN, int KD, int PXF>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
   extern __shared__ __align__(16) float wsm_in[];   // [KD*9*CIN][cout]
   constexpr int TAPS = KD * 9;
-  constexpr int PXF = (KD == 1) ? 4 : 1;            // consecutive output pixels per thread: one weight fetch feeds PXF pixels
   for (int e = threadIdx.x; e < TAPS * CIN * op.cout; e += blockDim.x) wsm_in[e] = op.w[e];
   __syncthreads();
   const unsigned cgroups = op.cout / 8;
@@ -473,7 +474,7 @@ int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
   const int cin = op.cin0 + op.cin1;
   KD_CHECK(cin >= 1 && cin <= 4 && (op.kd == 1 || (op.kd == 3 && cin == 1)), "conv_few_in: unsupported cin=%d kd=%d", cin, op.kd);
-  const int pxf = op.kd == 1 ? 4 : 1;               // must match PXF in the kernel
+  const int pxf = (op.kd == 1 && op.cout >= 48) ? 4 : 1;
   const long total = (long)op.H * ((op.W + pxf - 1) / pxf) * (op.cout / 8);
   KD_CHECK((long)op.H * op.W * (op.cout / 8) < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
   const double fi_pix = (double)op.nimg * op.H * op.W;
@@ -482,11 +483,14 @@ int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   const dim3 grid((unsigned)std::min<long>(cdiv(total, 128), std::max<long>(1, 148L * 16 / op.nimg)), op.nimg);
   const size_t smem = sizeof(float) * (size_t)op.kd * 9 * cin * op.cout;
   KD_CHECK(smem <= 48 * 1024, "conv_few_in: weights do not fit shared memory");
-  if (op.kd == 3) k_conv_few_in<T, 1, 3><<<grid, 128, smem, s>>>(op, Hin, Win);
-  else if (cin == 1) k_conv_few_in<T, 1, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
-  else if (cin == 2) k_conv_few_in<T, 2, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
-  else if (cin == 3) k_conv_few_in<T, 3, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
-  else k_conv_few_in<T, 4, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
+#define KD_FEW_IN(CI, KDD) do { if (pxf == 4) k_conv_few_in<T, CI, KDD, 4><<<grid, 128, smem, s>>>(op, Hin, Win); \
+                                else k_conv_few_in<T, CI, KDD, 1><<<grid, 128, smem, s>>>(op, Hin, Win); } while (0)
+  if (op.kd == 3) k_conv_few_in<T, 1, 3, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
+  else if (cin == 1) KD_FEW_IN(1, 1);
+  else if (cin == 2) KD_FEW_IN(2, 1);
+  else if (cin == 3) KD_FEW_IN(3, 1);
+  else KD_FEW_IN(4, 1);
+#undef KD_FEW_IN
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
