@@ -33,6 +33,9 @@ TEACHER_CASES = {
     "teacher_c1_biasfree_64": (dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train"), 1, 64, 64, "uniform01", 1.0, 0),
     "teacher_c3_withbias_32x48": (dict(inp_channels=3, out_channels=3, LayerNorm_type="WithBias", static="train"), 2, 32, 48, "sonar", 8.0, 1),
     "teacher_c1_nosr_40x24": (dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no"), 1, 40, 24, "sonar", 6.0, 2),
+    # the pretrained-checkpoint layout (KDLAET.yml / KDLAE_T.ipynb: 3 channels, BiasFree): the fused 1x1 -> depthwise kernels
+    # with 3-plane input / output convs, at a size with ragged 30x6 / 14x6 tiles
+    "teacher_c3_biasfree_72x88": (dict(inp_channels=3, out_channels=3, LayerNorm_type="BiasFree", static="train"), 1, 72, 88, "sonar", 2.0, 3),
 }
 STUDENT_CASES = {
     "student_f5_32x40": (2, 5, 32, 40, True, 0),

@@ -24,7 +24,7 @@ def _teacher(kw, seed, temp_scale, precision):
     return m.to(DEV).eval().set_precision(precision)
 
 
-TEACHER = ["teacher_c1_biasfree_64", "teacher_c3_withbias_32x48", "teacher_c1_nosr_40x24"]
+TEACHER = ["teacher_c1_biasfree_64", "teacher_c3_withbias_32x48", "teacher_c1_nosr_40x24", "teacher_c3_biasfree_72x88"]
 
 
 @pytest.mark.parametrize("name", TEACHER)

@@ -9,7 +9,8 @@ from conftest import load_golden
 TOL = 2e-5  # fp32 noise between two orderings of the same arithmetic (reference fp32-vs-fp64 is 2.4e-7)
 
 
-@pytest.mark.parametrize("name", ["teacher_c1_biasfree_64", "teacher_c3_withbias_32x48", "teacher_c1_nosr_40x24"])
+@pytest.mark.parametrize("name", ["teacher_c1_biasfree_64", "teacher_c3_withbias_32x48", "teacher_c1_nosr_40x24",
+                                  "teacher_c3_biasfree_72x88"])
 def test_teacher_oracle_matches_reference_fixture(name, manifest):
     case, g = manifest[name], load_golden(name)
     kw = case["kwargs"]
