@@ -98,6 +98,52 @@ def cpu_oracle_rate(size: int, threads: int, repeats: int = 1):
     return scale / best, best
 
 
+def time_uint8_pipeline(pk, model, dev, B, S):
+    """uint8 HWC host images -> CUDA pre-pass -> KDLAE-T -> CUDA post-pass -> uint8 hq / sr on the host,
+    in chunks of one micro-batch on a copy-in / compute / copy-out stream triple (1 byte per element over PCIe each way)."""
+    chunk = min(B, 16)
+    n = (B + chunk - 1) // chunk
+    img_h = torch.randint(0, 256, (B, S, S, 1), dtype=torch.uint8).pin_memory()
+    hq_h = torch.empty(B, S, S, 1, dtype=torch.uint8).pin_memory()
+    sr_h = torch.empty(B, 2 * S, 2 * S, 1, dtype=torch.uint8).pin_memory()
+    rates = torch.rand(B, device=dev)
+    img_d = [torch.empty(chunk, S, S, 1, dtype=torch.uint8, device=dev) for _ in range(n)]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step():
+        cur = torch.cuda.current_stream()
+        s_in.wait_stream(cur)
+        evs = []
+        with torch.cuda.stream(s_in):
+            for c in range(n):
+                img_d[c].copy_(img_h[c * chunk:(c + 1) * chunk], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(s_in); evs.append(ev)
+        for c in range(n):
+            cur.wait_event(evs[c])
+            hq, sr = pk.teacher_infer_uint8(model, img_d[c], rates[c * chunk:(c + 1) * chunk])
+            done = torch.cuda.Event(); done.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                hq_h[c * chunk:(c + 1) * chunk].copy_(hq, non_blocking=True)
+                sr_h[c * chunk:(c + 1) * chunk].copy_(sr, non_blocking=True)
+                hq.record_stream(s_out); sr.record_stream(s_out)
+        cur.wait_stream(s_out)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        step()
+        torch.cuda.current_stream().synchronize()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    return {"value": B / ms * 1e3, "batch": B, "ms_per_step": ms, "h2d_bytes_per_step": int(img_h.numel() + 4 * B),
+            "d2h_bytes_per_step": int(hq_h.numel() + sr_h.numel())}
+
+
 def time_other_models(pk, synth, dev, pk_):
     """Device-resident throughput of the other two forwards of the path (BASELINE configs 3 and 4 shapes, bf16)."""
     def timeit(f, n=3):
@@ -374,6 +420,7 @@ def main():
     }
     if args.extras:
         line["other_models"] = time_other_models(pk, synth, dev, pk_)
+        line["other_models"]["KDLAE-T uint8 pipeline e2e images/s"] = time_uint8_pipeline(pk, model, dev, B, S)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cpu_oracle_rate(64, cores)

@@ -144,6 +144,16 @@ int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, cons
 int kdlae_pwdw_t(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
                  int gate, void* stream);
 
+/* ---- uint8 pre / post-processing around the KDLAE-T forward (KDLAE/KDLAE_T.ipynb cell 5) ------------
+ * pre:  src [B,h,w,c] uint8 (HWC) -> img [B,c,H,W] fp32 = src/255 with F.pad(...,'reflect') on the bottom/right edges
+ *       (H >= h, W >= w, pad < size); rate_map (nullable) [B,1,H,W] = rates[b] (device floats).
+ * post: pred [B,c,Hp,Wp] fp32 (Hp >= h*scale, Wp >= w*scale) -> clamp(0,1), crop to (h*scale, w*scale), rint(x*255)
+ *       (skimage.img_as_ubyte), 0 wherever all c channels of src[b, y/scale, x/scale] are 0 -> out [B,h*scale,w*scale,c]. */
+int kdlae_preprocess_u8(const unsigned char* src_hwc, int B, int h, int w, int c, const float* rates, float* img_nchw, float* rate_map,
+                        int H, int W, void* stream);
+int kdlae_postprocess_u8(const float* pred_nchw, const unsigned char* src_hwc, int B, int h, int w, int c, int Hp, int Wp, int scale,
+                         unsigned char* out_hwc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,5 +9,7 @@ C ABI in include/kdlae_b200.h.  The CUDA library is mandatory: nothing here fall
 from .kdlae_model import KDLAE_teacher, KDLAE_student, RestormerSuperResolutionParam2  # noqa: F401
 from .asdqe_model import DenoiseRatePredictor  # noqa: F401
 from . import _lib  # noqa: F401
+from .pipeline import teacher_infer_uint8, preprocess_u8, postprocess_u8  # noqa: F401
 
-__all__ = ["KDLAE_teacher", "KDLAE_student", "RestormerSuperResolutionParam2", "DenoiseRatePredictor"]
+__all__ = ["KDLAE_teacher", "KDLAE_student", "RestormerSuperResolutionParam2", "DenoiseRatePredictor",
+           "teacher_infer_uint8", "preprocess_u8", "postprocess_u8"]

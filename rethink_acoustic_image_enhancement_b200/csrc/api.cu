@@ -308,4 +308,18 @@ int kdlae_pwdw_t(const void* x, const float* rstd, const void* w1, int Nt, const
                     reinterpret_cast<bf16*>(out), gate ? Nt / 2 : Nt, nimg, H, W, C, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int kdlae_preprocess_u8(const unsigned char* src_hwc, int B, int h, int w, int c, const float* rates, float* img_nchw, float* rate_map,
+                        int H, int W, void* stream) {
+  API_BEGIN();
+  KD_CHECK(src_hwc && img_nchw, "kdlae_preprocess_u8: NULL argument");
+  return kd::preprocess_u8(src_hwc, B, h, w, c, rates, img_nchw, rate_map, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kdlae_postprocess_u8(const float* pred_nchw, const unsigned char* src_hwc, int B, int h, int w, int c, int Hp, int Wp, int scale,
+                         unsigned char* out_hwc, void* stream) {
+  API_BEGIN();
+  KD_CHECK(pred_nchw && src_hwc && out_hwc, "kdlae_postprocess_u8: NULL argument");
+  return kd::postprocess_u8(pred_nchw, src_hwc, B, h, w, c, Hp, Wp, scale, out_hwc, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

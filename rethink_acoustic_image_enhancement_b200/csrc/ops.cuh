@@ -89,6 +89,12 @@ template <typename T> int conv_few_out(const SmallConvOut& op, cudaStream_t s);
 int tap_sum(const float* part, int cout, int nimg, int H, int W, const float* res, long res_img, long res_ch, float* out, long out_img,
             long out_ch, cudaStream_t s);
 
+// uint8 pre / post-processing around the teacher forward (prepost.cu; KDLAE_T.ipynb cell 5)
+int preprocess_u8(const uint8_t* src, int B, int h, int w, int c, const float* rates, float* img, float* rate_map, int H, int W,
+                  cudaStream_t s);
+int postprocess_u8(const float* pred, const uint8_t* src, int B, int h, int w, int c, int Hp, int Wp, int scale, uint8_t* out,
+                   cudaStream_t s);
+
 // pooling / resampling / misc glue
 template <typename T> int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s);
 template <typename T> int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s);
