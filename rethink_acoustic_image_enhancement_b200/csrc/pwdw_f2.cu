@@ -314,13 +314,16 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
             u64 v[PXT + 2];
 #pragma unroll
             for (int j = 0; j < PXT + 2; ++j) v[j] = unpack2(lds32(tb + h * PF_XCHUNK + ir * (PF_TW * 128) + off[j]));
+            // taps of this input row, completing output row (dy = 2) first: in the last half its GELU / gate / store chain is
+            // issued right after and overlaps the independent dy = 1, 0 FMAs that follow (same per-accumulator order as before)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {        // dx outermost: consecutive FFMA2s go to different accumulators
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int dy = 2 - dyi;
+              const int orow = ir - dy;
+              if (orow >= 0 && orow < PF_OH) {
+                const int a = orow % 3;
 #pragma unroll
-              for (int dy = 0; dy < 3; ++dy) {
-                const int orow = ir - dy;
-                if (orow >= 0 && orow < PF_OH) {
-                  const int a = orow % 3;
+                for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                   for (int q = 0; q < PXT; ++q) {
                     if (dy == 0 && dx == 0) acc[h][a][q] = fmul2(v[q], w[h][0]);
@@ -328,16 +331,16 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
                   }
                 }
               }
-            }
-          }
-          if (ir >= 2) {
-            const int orow = ir - 2, a = orow % 3;
+              if (dyi == 0 && h == NH - 1 && ir >= 2) {
+                const int a = (ir - 2) % 3;
 #pragma unroll
-            for (int q = 0; q < PXT; ++q) {
-              const float2 f = as_float2(GATE ? gelu_gate2(acc[0][a][q], acc[NH - 1][a][q]) : acc[0][a][q]);
-              if (orow < nr && q < nq) *reinterpret_cast<uint32_t*>(orp + q * ldo2) = pack_bf16x2(f.x, f.y);
+                for (int q = 0; q < PXT; ++q) {
+                  const float2 f = as_float2(GATE ? gelu_gate2(acc[0][a][q], acc[NH - 1][a][q]) : acc[0][a][q]);
+                  if (ir - 2 < nr && q < nq) *reinterpret_cast<uint32_t*>(orp + q * ldo2) = pack_bf16x2(f.x, f.y);
+                }
+                orp += row_pitch2;
+              }
             }
-            orp += row_pitch2;
           }
         }
       }
