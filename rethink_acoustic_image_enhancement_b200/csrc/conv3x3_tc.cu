@@ -29,7 +29,7 @@ constexpr int C3_STORE_BAR_THREADS = C3_EPI_WARPS * 32 + 32;
 
 struct C3Params {
   int kd, D;                 // temporal taps (1 or 3) and frames per batch element
-  int kc0, kc1, c0;          // 64-wide K chunks of source 0 / 1; weight column offset of source 1
+  int kc0, kc1, c0, c1;      // 64-wide K chunks of source 0 / 1; channels of source 0 (= weight column offset of source 1) / 1
   long w_tap_ld;
   int n_chunks, nc;
   long items;
@@ -160,6 +160,11 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const int s = aidx % C3_ASLOTS;
           mbar_wait(a_full(s), (aidx / C3_ASLOTS) & 1);
           const uint32_t a_lo0 = (((a_base + s * C3_A_SLOT) & 0x3FFFF) >> 4) | lo_tag;
+          // K = 16 steps that hold real channels in this chunk (a 16-channel layer needs 1 of the 4: the rest of the box is TMA
+          // zero fill and would only burn tensor-pipe time - the KDLAE-S / ASDQE layers are 16..64 channels wide)
+          const int kci = ag / p.kd;
+          const int rem = kci < p.kc0 ? p.c0 - kci * 64 : p.c1 - (kci - p.kc0) * 64;
+          const int ksn = rem >= 64 ? 4 : (rem + 15) >> 4;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bidx) {
             const int bs = bidx % C3_BSLOTS;
@@ -171,7 +176,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | lo_tag;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
+              if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
             if (!p.w_resident) umma_commit(b_empty(bs));
           }
           umma_commit(a_empty(s));
@@ -343,7 +348,7 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   C3Params p;
   memset(&p, 0, sizeof(p));
   p.kd = op.kd; p.D = op.D;
-  p.kc0 = (op.c0 + 63) / 64; p.kc1 = (op.c1 + 63) / 64; p.c0 = op.c0;
+  p.kc0 = (op.c0 + 63) / 64; p.kc1 = (op.c1 + 63) / 64; p.c0 = op.c0; p.c1 = op.c1;
   p.w_tap_ld = op.w_tap_ld;
   p.nc = nc; p.n_chunks = n_chunks;
   p.H = op.H; p.W = op.W;
