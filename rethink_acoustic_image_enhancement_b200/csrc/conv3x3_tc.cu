@@ -111,12 +111,16 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
 
   if (warp == 0) {
     // ===================== TMA producer: A tiles (one per 9 taps) and W tiles (one per tap) =====================
-    if (lane == 0) {
+    // (warp-uniform loop, one elected lane issues - see elect_one())
+    {
       uint32_t aidx = 0, bidx = 0;
       if (p.w_resident) {          // weight-stationary: 9 x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
-        mbar_expect_tx(b_full(0), 9u * (uint32_t)p.nc * 128);
-        for (int tap = 0; tap < 9; ++tap)
-          tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), (int)(tap * p.w_tap_ld), 0, 0);
+        if (elect_one()) {
+          mbar_expect_tx(b_full(0), 9u * (uint32_t)p.nc * 128);
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), (int)(tap * p.w_tap_ld), 0, 0);
+        }
+        __syncwarp();
       }
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const C3Tile t = c3_tile(p, item);
@@ -129,23 +133,29 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           for (int td = 0; td < p.kd; ++td, ++aidx) {
             const int s = aidx % C3_ASLOTS;
             mbar_wait_relaxed(a_empty(s), ((aidx / C3_ASLOTS) & 1) ^ 1);
-            mbar_expect_tx(a_full(s), C3_A_BYTES);
-            if (p.kd == 3) tma_load_5d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, fd + td - 1, fb);
-            else tma_load_4d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, t.img);
+            if (elect_one()) {
+              mbar_expect_tx(a_full(s), C3_A_BYTES);
+              if (p.kd == 3) tma_load_5d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, fd + td - 1, fb);
+              else tma_load_4d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, t.img);
+            }
+            __syncwarp();
             for (int tap = 0; tap < 9 && !p.w_resident; ++tap, ++bidx) {
               const int bs = bidx % C3_BSLOTS;
               mbar_wait_relaxed(b_empty(bs), ((bidx / C3_BSLOTS) & 1) ^ 1);
-              mbar_expect_tx(b_full(bs), (uint32_t)p.nc * 128);
-              const int wk = (int)((td * 9 + tap) * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
-              tma_load_3d(b_base + bs * C3_B_SLOT, &map_w, b_full(bs), wk, t.nchunk * p.nc, 0);
+              if (elect_one()) {
+                mbar_expect_tx(b_full(bs), (uint32_t)p.nc * 128);
+                const int wk = (int)((td * 9 + tap) * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
+                tma_load_3d(b_base + bs * C3_B_SLOT, &map_w, b_full(bs), wk, t.nchunk * p.nc, 0);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t lo_tag = 1u << 16;
@@ -159,6 +169,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         for (int ag = 0; ag < agroups; ++ag, ++aidx) {
           const int s = aidx % C3_ASLOTS;
           mbar_wait(a_full(s), (aidx / C3_ASLOTS) & 1);
+          tc_fence_after();
           const uint32_t a_lo0 = (((a_base + s * C3_A_SLOT) & 0x3FFFF) >> 4) | lo_tag;
           // K = 16 steps that hold real channels in this chunk (a 16-channel layer needs 1 of the 4: the rest of the box is TMA
           // zero fill and would only burn tensor-pipe time - the KDLAE-S / ASDQE layers are 16..64 channels wide)
@@ -168,20 +179,24 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bidx) {
             const int bs = bidx % C3_BSLOTS;
-            if (!p.w_resident) mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1);
-            tc_fence_after();
+            if (!p.w_resident) { mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1); tc_fence_after(); }
             const int dy = tap / 3, dx = tap - dy * 3;
             const uint32_t a_lo = a_lo0 + (uint32_t)((dy * C3_TW + dx) * 8);
             const uint32_t b_addr = p.w_resident ? b_base + tap * p.nc * 128 : b_base + bs * C3_B_SLOT;
             const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | lo_tag;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
-            if (!p.w_resident) umma_commit(b_empty(bs));
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
+              if (!p.w_resident) umma_commit(b_empty(bs));
+            }
+            __syncwarp();
           }
-          umma_commit(a_empty(s));
+          if (elect_one()) umma_commit(a_empty(s));
+          __syncwarp();
         }
-        umma_commit(tfull_bar(acc));
+        if (elect_one()) umma_commit(tfull_bar(acc));
+        __syncwarp();
       }
     }
   } else if (warp < 2 + C3_EPI_WARPS) {

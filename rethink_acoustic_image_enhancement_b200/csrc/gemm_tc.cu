@@ -153,8 +153,8 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int nslabs = (p.nc + 63) / 64;
 
   if (warp == 0) {
-    // ===================== TMA producer (A and W tiles) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (A and W tiles): warp-uniform loop, elected issuer (see elect_one()) =====================
+    {
       uint32_t kidx = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const TileCoord t = tile_coord(p, item);
@@ -169,22 +169,25 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             mbar_wait_relaxed(empty_bar(s), ph ^ 1);
             const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
             const uint32_t b_dst = a_dst + TC_A_BYTES;
-            mbar_expect_tx(full_bar(s), stage_tx);
             const bool src1 = kc >= p.kc0;
             const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
             const int cc = (src1 ? kc - p.kc0 : kc) * TC_BK;
-            if (p.kd == 3) tma_load_5d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, fd + dd, fb);
-            else if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, t.img);
-            else tma_load_3d(a_dst, ma, full_bar(s), cc, t.r0, t.g);
             const int wk = (int)(tap * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
-            tma_load_3d(b_dst, &map_w, full_bar(s), wk, t.nchunk * p.nc, t.g);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), stage_tx);
+              if (p.kd == 3) tma_load_5d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, fd + dd, fb);
+              else if (p.spatial) tma_load_4d(a_dst, ma, full_bar(s), cc, t.tx0 + dx, t.ty0 + dy, t.img);
+              else tma_load_3d(a_dst, ma, full_bar(s), cc, t.r0, t.g);
+              tma_load_3d(b_dst, &map_w, full_bar(s), wk, t.nchunk * p.nc, t.g);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    {
       const uint32_t idesc = make_idesc(p.nc);
       uint32_t kidx = 0, it = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -199,15 +202,19 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * TC_STAGE_BYTES;
           const uint32_t b_addr = a_addr + TC_A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + k * 32);
+              const uint64_t bd = make_smem_desc(b_addr + k * 32);
+              umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));      // frees the smem stage when these MMAs retire
           }
-          umma_commit(empty_bar(s));      // frees the smem stage when these MMAs retire
+          __syncwarp();
         }
-        umma_commit(tfull_bar(acc));      // accumulator complete
+        if (elect_one()) umma_commit(tfull_bar(acc));      // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp < 2 + TC_EPI_WARPS) {

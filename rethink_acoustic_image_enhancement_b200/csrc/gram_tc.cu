@@ -88,24 +88,27 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0 && lane == 0) {
-    // ---- TMA producer: q and k channel atoms of 64 pixels per stage ----
+  if (warp == 0) {
+    // ---- TMA producer: q and k channel atoms of 64 pixels per stage (warp-uniform loop, elected issuer: see elect_one()) ----
     const int cq = head * ch, ck = C + head * ch;
     for (int i = 0; i < nchunks; ++i) {
       const int s = i % GR_STAGES;
       mbar_wait(empty_bar(s), ((i / GR_STAGES) & 1) ^ 1);
       const uint32_t dst = sbase + s * GR_STAGE_BYTES;
-      mbar_expect_tx(full_bar(s), 2 * natoms * GR_ATOM);
       const int p = p_begin + i * GR_PIX;
-      tma_load_3d(dst, &map, full_bar(s), cq, p, img);
-      tma_load_3d(dst + natoms * GR_ATOM, &map, full_bar(s), ck, p, img);
-      if (natoms == 2) {
-        tma_load_3d(dst + GR_ATOM, &map, full_bar(s), cq + 64, p, img);
-        tma_load_3d(dst + 3 * GR_ATOM, &map, full_bar(s), ck + 64, p, img);
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), 2 * natoms * GR_ATOM);
+        tma_load_3d(dst, &map, full_bar(s), cq, p, img);
+        tma_load_3d(dst + natoms * GR_ATOM, &map, full_bar(s), ck, p, img);
+        if (natoms == 2) {
+          tma_load_3d(dst + GR_ATOM, &map, full_bar(s), cq + 64, p, img);
+          tma_load_3d(dst + 3 * GR_ATOM, &map, full_bar(s), ck + 64, p, img);
+        }
       }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---- MMA issuer ----
+  } else if (warp == 1) {
+    // ---- MMA issuer (warp-uniform loop, elected issuer) ----
     const uint32_t idesc = make_idesc_mn(ch);
     const uint32_t lbo = (natoms == 2) ? GR_ATOM : 0u;
     for (int i = 0; i < nchunks; ++i) {
@@ -113,17 +116,21 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
       mbar_wait(full_bar(s), (i / GR_STAGES) & 1);
       tc_fence_after();
       const uint32_t qa = sbase + s * GR_STAGE_BYTES, ka = qa + natoms * GR_ATOM;
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < GR_PIX / 16; ++k) {
-        const uint64_t dq = make_desc_mn(qa + k * 2048, lbo), dk = make_desc_mn(ka + k * 2048, lbo);
-        const uint32_t accum = (i | k) != 0 ? 1u : 0u;
-        umma_bf16(tmem_base + 0, dq, dk, idesc, accum);     // G  = q^T k
-        umma_bf16(tmem_base + ACC, dq, dq, idesc, accum);       // Nq = q^T q
-        umma_bf16(tmem_base + 2 * ACC, dk, dk, idesc, accum);   // Nk = k^T k
+        for (int k = 0; k < GR_PIX / 16; ++k) {
+          const uint64_t dq = make_desc_mn(qa + k * 2048, lbo), dk = make_desc_mn(ka + k * 2048, lbo);
+          const uint32_t accum = (i | k) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base + 0, dq, dk, idesc, accum);     // G  = q^T k
+          umma_bf16(tmem_base + ACC, dq, dq, idesc, accum);       // Nq = q^T q
+          umma_bf16(tmem_base + 2 * ACC, dk, dk, idesc, accum);   // Nk = k^T k
+        }
+        umma_commit(empty_bar(s));
       }
-      umma_commit(empty_bar(s));
+      __syncwarp();
     }
-    umma_commit(done_bar);
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
   }
   __syncwarp();
 

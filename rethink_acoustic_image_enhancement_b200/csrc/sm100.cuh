@@ -130,6 +130,15 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One elected lane of a converged warp.  tcgen05 issue loops are written as warp-uniform code with the instruction itself under
+// `if (elect_one())`: inside an `if (lane == 0)` region ptxas treats every descriptor / address as a per-thread value and wraps
+// each UTCHMMA / UTCBAR in VOTEU + R2UR + ELECT + BRA.U.ANY sequences (~30 dependent instructions per MMA - the single issuing
+// thread then takes ~5000 clk per 36-MMA tile and starves the tensor pipe; measured on conv3x3_tc, scripts/c3_probe.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
