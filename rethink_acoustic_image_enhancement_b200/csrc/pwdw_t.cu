@@ -176,37 +176,45 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, elected issuer: see elect_one()) =====================
+    {
       uint32_t n = 0;
       for (int i = 0; i < ntiles; ++i) {
         int img, y0, x0;
         if (i + 1 < ntiles) {   // the x tile is single buffered: keep the next one warm in L2
           tile_xy(i + 1, img, y0, x0);
-          for (int k = 0; k < p.kc; ++k) tma_prefetch_4d(&map_x, k * 64, x0 - 1, y0 - 1, img);
+          if (elect_one())
+            for (int k = 0; k < p.kc; ++k) tma_prefetch_4d(&map_x, k * 64, x0 - 1, y0 - 1, img);
+          __syncwarp();
         }
         mbar_wait_lazy(x_empty, (i & 1) ^ 1);        // last GEMM of tile i-1 retired
         tile_xy(i, img, y0, x0);
-        mbar_expect_tx(x_full, p.kc * XCHUNK);
-        for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
+        if (elect_one()) {
+          mbar_expect_tx(x_full, p.kc * XCHUNK);
+          for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
+        }
+        __syncwarp();
         for (int cb = 0; cb < ncb; ++cb, ++n) {
           mbar_wait_lazy(w_empty, (n & 1) ^ 1);      // GEMM n-1 retired: the W1 buffer is free
           // W1 rows arrive per TMEM lane quarter (32 rows): a partial last block only loads its valid quarters, rotated by the
           // tile index so that the extra work lands on a different scheduler every tile (see the depthwise warps)
           const int nvalid = min(PT_MB, p.Cout - cb * PT_MB);
           const int nq = (nvalid + 31) >> 5, rot = (nq < 4) ? (i & 3) : 0;
-          mbar_expect_tx(w_full, p.kc * NH * nq * 4096);
-          for (int k = 0; k < p.kc; ++k)
-            for (int h = 0; h < NH; ++h)
-              for (int lq = 0; lq < nq; ++lq)
-                tma_load_3d(w1_base + (k * NH + h) * W1CHUNK + ((lq + rot) & 3) * 4096, &map_w1, w_full, k * 64,
-                            (GATE ? h * hp : 0) + cb * PT_MB + lq * 32, 0);
+          if (elect_one()) {
+            mbar_expect_tx(w_full, p.kc * NH * nq * 4096);
+            for (int k = 0; k < p.kc; ++k)
+              for (int h = 0; h < NH; ++h)
+                for (int lq = 0; lq < nq; ++lq)
+                  tma_load_3d(w1_base + (k * NH + h) * W1CHUNK + ((lq + rot) & 3) * 4096, &map_w1, w_full, k * 64,
+                              (GATE ? h * hp : 0) + cb * PT_MB + lq * 32, 0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: T^T = W1 . X^T (A = W1 rows, B = pixels) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: T^T = W1 . X^T (A = W1 rows, B = pixels); warp-uniform loop, elected issuer ============
+    {
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lo_tag = 1u << 16;
@@ -218,17 +226,20 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
           mbar_wait_relaxed(w_full, n & 1);
           if (cb == 0) mbar_wait_relaxed(x_full, i & 1);
           tc_fence_after();
-          for (int h = 0; h < NH; ++h) {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const int k = ks >> 2, kk = ks & 3;
-              const uint32_t a_lo = (((w1_base + (k * NH + h) * W1CHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
-              const uint32_t b_lo = (((x_base + k * XCHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
-              umma_bf16_lohi(tmem_base + b * 256 + h * NPX, a_lo, b_lo, desc_hi, idesc, ks != 0 ? 1u : 0u);
+          if (elect_one()) {
+            for (int h = 0; h < NH; ++h) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const int k = ks >> 2, kk = ks & 3;
+                const uint32_t a_lo = (((w1_base + (k * NH + h) * W1CHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+                const uint32_t b_lo = (((x_base + k * XCHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+                umma_bf16_lohi(tmem_base + b * 256 + h * NPX, a_lo, b_lo, desc_hi, idesc, ks != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(w_empty);                       // W1 block consumed
+            if (cb == ncb - 1) umma_commit(x_empty);    // x tile consumed
+            umma_commit(d_full(b));                     // accumulators ready
           }
-          umma_commit(w_empty);                       // W1 block consumed
-          if (cb == ncb - 1) umma_commit(x_empty);    // x tile consumed
-          umma_commit(d_full(b));                     // accumulators ready
+          __syncwarp();
         }
       }
     }

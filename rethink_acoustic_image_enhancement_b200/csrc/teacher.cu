@@ -173,14 +173,15 @@ struct Scratch {
 //   3  both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
 //      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn;
 //   6  both pairs through pwdw_t.cu (transposed GEMM, depthwise inputs read from TMEM in fp32), 7 (default) qkv via pwdw_t +
-//      ffn via pwdw_f2 (the fastest pairing measured: 94.6 vs 92.3 images/s for mode 3), 8 the other way round.
+//      ffn via pwdw_f2 (the fastest pairing measured: 94.6 vs 92.3 images/s for mode 3), 8 the other way round, 9 qkv via
+//      pwdw_t with the ffn pair unfused.
 inline int fuse_pwdw_mode() {
   const char* e = getenv("KDLAE_FUSE_PWDW");
   return e ? atoi(e) : 7;
 }
 inline bool fuse_f2_qkv(int m) { return m == 3 || m == 4 || m == 8; }
 inline bool fuse_f2_ffn(int m) { return m == 3 || m == 5 || m == 7; }
-inline bool fuse_t_qkv(int m) { return m == 6 || m == 7; }
+inline bool fuse_t_qkv(int m) { return m == 6 || m == 7 || m == 9; }
 inline bool fuse_t_ffn(int m) { return m == 6 || m == 8; }
 
 // In the bf16 path the GEMM that produces the residual stream also emits the LayerNorm statistics of its output
