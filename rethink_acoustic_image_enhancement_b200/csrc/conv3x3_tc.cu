@@ -9,6 +9,7 @@
 // Two smem rings: A (2 slots, each consumed by 9 taps) and W (3 slots, one per tap).  TMEM double buffered, epilogues as
 // in gemm_tc.cu: FAST = swizzled slabs + TMA stores/loads (bias, ReLU, residual), generic = epilogue_store8
 // (PixelShuffle / PixelUnshuffle / planar fp32).  Warps: 0 producer, 1 MMA, 2..17 epilogue, 18 residual loads, 19 stores.
+#include <algorithm>
 #include "sm100.cuh"
 
 namespace kd {
@@ -17,14 +18,15 @@ namespace {
 
 constexpr int C3_TW = 32, C3_OW = 30, C3_OH = 4, C3_IH = 6;
 constexpr int C3_NC_MAX = 256;
-constexpr int C3_ASLOTS = 2, C3_BSLOTS = 3, C3_NSLAB = 4;
+constexpr int C3_ASLOTS = 2, C3_ASLOTS_MAX = 4, C3_BSLOTS = 3, C3_NSLAB = 4;   // A ring: 2 slots, up to 4 in weight-stationary mode
 constexpr uint32_t C3_A_BYTES = C3_TW * C3_IH * 128;          // 24576
 constexpr uint32_t C3_A_SLOT = C3_A_BYTES + 1024;             // shifted reads run 2 pixels past the tile
 constexpr uint32_t C3_B_SLOT = C3_NC_MAX * 128;               // 32768
 constexpr uint32_t C3_SLAB = 16384;                           // 120 px x 128 B used
 constexpr int C3_EPI_WARPS = 16;
 constexpr int C3_THREADS = (2 + C3_EPI_WARPS + 2) * 32;
-constexpr uint32_t C3_SMEM = C3_ASLOTS * C3_A_SLOT + C3_BSLOTS * C3_B_SLOT + C3_NSLAB * C3_SLAB + 1024 + 256;
+constexpr uint32_t C3_SMEM = C3_ASLOTS * C3_A_SLOT + C3_BSLOTS * C3_B_SLOT + C3_NSLAB * C3_SLAB + 1024 + 512;   // streaming layout
+constexpr uint32_t C3_SMEM_MAX = 227 * 1024;
 constexpr int C3_STORE_BAR_THREADS = C3_EPI_WARPS * 32 + 32;
 
 struct C3Params {
@@ -35,6 +37,8 @@ struct C3Params {
   long items;
   int H, W, tiles_x, tiles_y;
   int has_res, relu;
+  int a_slots;               // depth of the activation-tile ring (weight-stationary mode: the freed weight-ring space deepens it)
+  uint32_t b_bytes;          // bytes of the weight region
   int w_resident;            // 1: all 9 tap tiles of the (single) K chunk fit the weight ring -> loaded once per CTA
   float inv_n_chunks, inv_tiles_x, inv_tiles_y, inv_D;
   Epilogue epi;
@@ -69,14 +73,14 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase;
-  const uint32_t b_base = a_base + C3_ASLOTS * C3_A_SLOT;
-  const uint32_t slab_base = b_base + C3_BSLOTS * C3_B_SLOT;
+  const uint32_t b_base = a_base + p.a_slots * C3_A_SLOT;
+  const uint32_t slab_base = b_base + p.b_bytes;
   const uint32_t bar_base = slab_base + C3_NSLAB * C3_SLAB;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (C3_ASLOTS + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS + C3_BSLOTS + s); };
-  const uint32_t bar2 = bar_base + 8u * (2 * C3_ASLOTS + 2 * C3_BSLOTS);
+  auto a_empty = [&](int s) { return bar_base + 8u * (C3_ASLOTS_MAX + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + C3_BSLOTS + s); };
+  const uint32_t bar2 = bar_base + 8u * (2 * C3_ASLOTS_MAX + 2 * C3_BSLOTS);
   auto tfull_bar = [&](int a) { return bar2 + 8u * a; };
   auto tempty_bar = [&](int a) { return bar2 + 8u * (2 + a); };
   auto sfull_bar = [&](int b) { return bar2 + 8u * (4 + b); };
@@ -90,7 +94,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     prefetch_tmap(&map_a0); prefetch_tmap(&map_w);
     if (p.kc1 > 0) prefetch_tmap(&map_a1);
     if (FAST) { prefetch_tmap(&map_out); if (p.has_res) prefetch_tmap(&map_res); }
-    for (int s = 0; s < C3_ASLOTS; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < C3_ASLOTS_MAX; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < C3_BSLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), C3_EPI_WARPS); }
     for (int b = 0; b < C3_NSLAB; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 1); }
@@ -131,8 +135,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
           const int cc = (src1 ? kc - p.kc0 : kc) * 64;
           for (int td = 0; td < p.kd; ++td, ++aidx) {
-            const int s = aidx % C3_ASLOTS;
-            mbar_wait_relaxed(a_empty(s), ((aidx / C3_ASLOTS) & 1) ^ 1);
+            const int s = aidx % p.a_slots;
+            mbar_wait_relaxed(a_empty(s), ((aidx / p.a_slots) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(a_full(s), C3_A_BYTES);
               if (p.kd == 3) tma_load_5d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, fd + td - 1, fb);
@@ -167,8 +171,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C3_NC_MAX;
         for (int ag = 0; ag < agroups; ++ag, ++aidx) {
-          const int s = aidx % C3_ASLOTS;
-          mbar_wait(a_full(s), (aidx / C3_ASLOTS) & 1);
+          const int s = aidx % p.a_slots;
+          mbar_wait(a_full(s), (aidx / p.a_slots) & 1);
           tc_fence_after();
           const uint32_t a_lo0 = (((a_base + s * C3_A_SLOT) & 0x3FFFF) >> 4) | lo_tag;
           // K = 16 steps that hold real channels in this chunk (a 16-channel layer needs 1 of the 4: the rest of the box is TMA
@@ -176,21 +180,38 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const int kci = ag / p.kd;
           const int rem = kci < p.kc0 ? p.c0 - kci * 64 : p.c1 - (kci - p.kc0) * 64;
           const int ksn = rem >= 64 ? 4 : (rem + 15) >> 4;
+          if (p.w_resident) {
+            // weight-stationary: no per-tap handshake - the 9 x ksn MMAs of this A tile go out back to back from one elected lane
+            if (elect_one()) {
+              const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | lo_tag;
+              const uint32_t b_tap = (uint32_t)p.nc * 8;            // (nc * 128 bytes) >> 4 per tap tile
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * C3_TW + tap % 3) * 8);
+                const uint32_t b_lo = b_lo0 + tap * b_tap;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
+              }
+            }
+            __syncwarp();
+          } else {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bidx) {
             const int bs = bidx % C3_BSLOTS;
-            if (!p.w_resident) { mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1); tc_fence_after(); }
+            mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1);
+            tc_fence_after();
             const int dy = tap / 3, dx = tap - dy * 3;
             const uint32_t a_lo = a_lo0 + (uint32_t)((dy * C3_TW + dx) * 8);
-            const uint32_t b_addr = p.w_resident ? b_base + tap * p.nc * 128 : b_base + bs * C3_B_SLOT;
-            const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | lo_tag;
+            const uint32_t b_lo = (((b_base + bs * C3_B_SLOT) & 0x3FFFF) >> 4) | lo_tag;
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
-              if (!p.w_resident) umma_commit(b_empty(bs));
+              umma_commit(b_empty(bs));
             }
             __syncwarp();
+          }
           }
           if (elect_one()) umma_commit(a_empty(s));
           __syncwarp();
@@ -356,8 +377,8 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
     KD_CUDA(cudaGetDevice(&dev));
     KD_CUDA(cudaDeviceGetAttribute(&g_c3_sms, cudaDevAttrMultiProcessorCount, dev));
     g_c3_sms = sm_limit(g_c3_sms);
-    KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
-    KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
+    KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_MAX));
+    KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_MAX));
   }
   const Epilogue& e = op.epi;
   C3Params p;
@@ -372,6 +393,14 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   KD_CHECK(p.items < (1L << 24), "conv3x3_tc: too many tiles (%ld)", p.items);
   p.has_res = e.res != nullptr; p.relu = e.relu;
   p.w_resident = (op.kd == 1 && p.kc0 + p.kc1 == 1 && n_chunks == 1 && 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT) ? 1 : 0;
+  p.a_slots = C3_ASLOTS; p.b_bytes = C3_BSLOTS * C3_B_SLOT;
+  uint32_t smem = C3_SMEM;
+  if (p.w_resident) {   // resident weights take 9 * nc * 128 bytes; the rest of the per-tap ring deepens the A ring
+    p.b_bytes = (9u * nc * 128 + 1023u) & ~1023u;
+    const uint32_t fixed = p.b_bytes + C3_NSLAB * C3_SLAB + 1024 + 512;
+    p.a_slots = (int)std::min<uint32_t>(C3_ASLOTS_MAX, (C3_SMEM_MAX - fixed) / C3_A_SLOT);
+    smem = p.a_slots * C3_A_SLOT + fixed;
+  }
   p.inv_n_chunks = 1.0f / (float)n_chunks; p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.inv_D = 1.0f / (float)(op.D > 0 ? op.D : 1);
   p.epi = e;
@@ -419,8 +448,8 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   const int grid = (int)(p.items < (long)g_c3_sms ? p.items : (long)g_c3_sms);
   const double rows = (double)op.nimg * op.H * op.W, ktot = 9.0 * op.kd * (op.c0 + op.c1);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * e.N * ktot, 2.0 * (rows * (op.c0 + op.c1 + e.N * (e.res ? 2 : 1)) + e.N * ktot));
-  if (fast) k_conv3_tc<1><<<grid, C3_THREADS, C3_SMEM, s>>>(ma0, ma1, mw, mout, mres, p);
-  else k_conv3_tc<0><<<grid, C3_THREADS, C3_SMEM, s>>>(ma0, ma1, mw, mout, mres, p);
+  if (fast) k_conv3_tc<1><<<grid, C3_THREADS, smem, s>>>(ma0, ma1, mw, mout, mres, p);
+  else k_conv3_tc<0><<<grid, C3_THREADS, smem, s>>>(ma0, ma1, mw, mout, mres, p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -1,4 +1,5 @@
-"""conv3x3_tc on ASDQE / KDLAE shapes with the KDLAE_C3_DEBUG bring-up switches: where does the per-tile time go?"""
+"""conv3x3_tc on ASDQE / KDLAE shapes: us, clocks per 120-pixel tile, TFLOP/s (see profiles/r01_summary.md for the bring-up
+bisection that used temporary KDLAE_C3_DEBUG switches: skip stores / epilogue math / MMAs / roles)."""
 import os, sys, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rethink_acoustic_image_enhancement_b200 import _lib
