@@ -18,7 +18,7 @@ namespace {
 
 constexpr int C3_TW = 32, C3_OW = 30, C3_OH = 4, C3_IH = 6;
 constexpr int C3_NC_MAX = 256;
-constexpr int C3_ASLOTS = 2, C3_ASLOTS_MAX = 4, C3_BSLOTS = 3, C3_NSLAB = 4;   // A ring: 2 slots, up to 4 in weight-stationary mode
+constexpr int C3_ASLOTS = 2, C3_ASLOTS_MAX = 4, C3_BSLOTS = 3, C3_BSLOTS_MAX = 8, C3_NSLAB = 4;   // A ring: 2 slots, up to 4 in weight-stationary mode
 constexpr uint32_t C3_A_BYTES = C3_TW * C3_IH * 128;          // 24576
 constexpr uint32_t C3_A_SLOT = C3_A_BYTES + 1024;             // shifted reads run 2 pixels past the tile
 constexpr uint32_t C3_B_SLOT = C3_NC_MAX * 128;               // 32768
@@ -39,6 +39,8 @@ struct C3Params {
   int has_res, relu;
   int a_slots;               // depth of the activation-tile ring (weight-stationary mode: the freed weight-ring space deepens it)
   uint32_t b_bytes;          // bytes of the weight region
+  int b_group, b_slots;      // streaming mode: taps per weight load (3 = one kernel row, or 1) and ring depth
+  uint32_t b_slot;           // bytes per weight-ring slot
   int w_resident;            // 1: all 9 tap tiles of the (single) K chunk fit the weight ring -> loaded once per CTA
   float inv_n_chunks, inv_tiles_x, inv_tiles_y, inv_D;
   Epilogue epi;
@@ -79,8 +81,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (C3_ASLOTS_MAX + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + C3_BSLOTS + s); };
-  const uint32_t bar2 = bar_base + 8u * (2 * C3_ASLOTS_MAX + 2 * C3_BSLOTS);
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + C3_BSLOTS_MAX + s); };
+  const uint32_t bar2 = bar_base + 8u * (2 * C3_ASLOTS_MAX + 2 * C3_BSLOTS_MAX);
   auto tfull_bar = [&](int a) { return bar2 + 8u * a; };
   auto tempty_bar = [&](int a) { return bar2 + 8u * (2 + a); };
   auto sfull_bar = [&](int b) { return bar2 + 8u * (4 + b); };
@@ -95,7 +97,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     if (p.kc1 > 0) prefetch_tmap(&map_a1);
     if (FAST) { prefetch_tmap(&map_out); if (p.has_res) prefetch_tmap(&map_res); }
     for (int s = 0; s < C3_ASLOTS_MAX; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < C3_BSLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < C3_BSLOTS_MAX; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), C3_EPI_WARPS); }
     for (int b = 0; b < C3_NSLAB; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,8 +123,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       if (p.w_resident) {          // weight-stationary: 9 x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
         if (elect_one()) {
           mbar_expect_tx(b_full(0), 9u * (uint32_t)p.nc * 128);
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), (int)(tap * p.w_tap_ld), 0, 0);
+          for (int tap = 0; tap < 9; tap += p.b_group)
+            tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), 0, 0, tap);
         }
         __syncwarp();
       }
@@ -143,13 +145,12 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
               else tma_load_4d(a_base + s * C3_A_SLOT, ma, a_full(s), cc, t.x0 - 1, t.y0 - 1, t.img);
             }
             __syncwarp();
-            for (int tap = 0; tap < 9 && !p.w_resident; ++tap, ++bidx) {
-              const int bs = bidx % C3_BSLOTS;
-              mbar_wait_relaxed(b_empty(bs), ((bidx / C3_BSLOTS) & 1) ^ 1);
+            for (int tap = 0; tap < 9 && !p.w_resident; tap += p.b_group, ++bidx) {
+              const int bs = bidx % p.b_slots;
+              mbar_wait_relaxed(b_empty(bs), ((bidx / p.b_slots) & 1) ^ 1);
               if (elect_one()) {
-                mbar_expect_tx(b_full(bs), (uint32_t)p.nc * 128);
-                const int wk = (int)((td * 9 + tap) * p.w_tap_ld) + (src1 ? p.c0 : 0) + cc;
-                tma_load_3d(b_base + bs * C3_B_SLOT, &map_w, b_full(bs), wk, t.nchunk * p.nc, 0);
+                mbar_expect_tx(b_full(bs), (uint32_t)p.b_group * p.nc * 128);
+                tma_load_3d(b_base + bs * p.b_slot, &map_w, b_full(bs), (src1 ? p.c0 : 0) + cc, t.nchunk * p.nc, td * 9 + tap);
               }
               __syncwarp();
             }
@@ -197,17 +198,26 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             __syncwarp();
           } else {
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++bidx) {
-            const int bs = bidx % C3_BSLOTS;
-            mbar_wait(b_full(bs), (bidx / C3_BSLOTS) & 1);
+          for (int tap0 = 0; tap0 < 9; tap0 += p.b_group, ++bidx) {     // one weight load = b_group taps (a kernel row, or one tap)
+            const int bs = bidx % p.b_slots;
+            mbar_wait(b_full(bs), (bidx / p.b_slots) & 1);
             tc_fence_after();
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_lo = a_lo0 + (uint32_t)((dy * C3_TW + dx) * 8);
-            const uint32_t b_lo = (((b_base + bs * C3_B_SLOT) & 0x3FFFF) >> 4) | lo_tag;
+            // taps tap0 .. tap0 + b_group - 1 share the kernel row: descriptor offsets are computed in warp-uniform code, outside
+            // the elected region (inside it ptxas falls back to per-thread values and R2UR wrappers around every MMA)
+            const uint32_t a_row = a_lo0 + (uint32_t)(((tap0 / 3) * C3_TW + tap0 % 3) * 8);
+            const uint32_t b_lo0 = (((b_base + bs * p.b_slot) & 0x3FFFF) >> 4) | lo_tag;
+            const uint32_t b_tap = (uint32_t)p.nc * 8;
+            const int ng = p.b_group;
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
+              for (int tt = 0; tt < 3; ++tt) {
+                if (tt < ng) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (ks < ksn)
+                      umma_bf16_lohi(d_tmem, a_row + tt * 8 + ks * 2, b_lo0 + tt * b_tap + ks * 2, desc_hi, idesc, (ag | (tap0 + tt) | ks) != 0 ? 1u : 0u);
+                }
+              }
               umma_commit(b_empty(bs));
             }
             __syncwarp();
@@ -394,6 +404,9 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   p.has_res = e.res != nullptr; p.relu = e.relu;
   p.w_resident = (op.kd == 1 && p.kc0 + p.kc1 == 1 && n_chunks == 1 && 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT) ? 1 : 0;
   p.a_slots = C3_ASLOTS; p.b_bytes = C3_BSLOTS * C3_B_SLOT;
+  p.b_group = (2u * 3u * nc * 128 <= p.b_bytes) ? 3 : 1;      // a kernel row of taps per weight load when two such slots fit
+  p.b_slot = (uint32_t)p.b_group * nc * 128;
+  p.b_slots = (int)std::min<uint32_t>(C3_BSLOTS, p.b_bytes / p.b_slot);     // deeper weight rings measured slower (they delay the A loads)
   uint32_t smem = C3_SMEM;
   if (p.w_resident) {   // resident weights take 9 * nc * 128 bytes; the rest of the per-tap ring deepens the A ring
     p.b_bytes = (9u * nc * 128 + 1023u) & ~1023u;
@@ -439,10 +452,11 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
     mout = ma0; mres = ma0;
   }
   {
+    // weights [n][tap][c] seen as {c within a tap, n, tap}: one box = b_group consecutive taps of nc rows, each a [nc][64] K-major tile
     const int taps = 9 * op.kd;
-    const cuuint64_t dims[3] = {(cuuint64_t)((long)taps * op.w_tap_ld), (cuuint64_t)e.N, 1};
-    const cuuint64_t str[2] = {(cuuint64_t)op.w_ld * 2, (cuuint64_t)op.w_ld * 2 * e.N};
-    const cuuint32_t box[3] = {64, (cuuint32_t)nc, 1};
+    const cuuint64_t dims[3] = {(cuuint64_t)op.w_tap_ld, (cuuint64_t)e.N, (cuuint64_t)taps};
+    const cuuint64_t str[2] = {(cuuint64_t)op.w_ld * 2, (cuuint64_t)op.w_tap_ld * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)nc, (cuuint32_t)p.b_group};
     KD_TRY(make_map(&mw, op.w, 3, dims, str, box));
   }
   const int grid = (int)(p.items < (long)g_c3_sms ? p.items : (long)g_c3_sms);
