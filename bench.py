@@ -246,7 +246,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its banner ("NCCL version ...") straight to the process's stdout when the communicator is created; stdout
+        # carries exactly one JSON line (the contract), so fd 1 points at stderr while NCCL initialises
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                       # creates the communicator (lazy) while stdout is still redirected
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     B, S = args.batch, args.size
     model = pk.KDLAE_teacher(**MODEL_KW)
