@@ -90,7 +90,6 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
 
   if (warp == 0) {
     // ---- TMA producer: q and k channel atoms of 64 pixels per stage (warp-uniform loop, elected issuer: see elect_one()) ----
-    const int cq = head * ch, ck = C + head * ch;
     for (int i = 0; i < nchunks; ++i) {
       const int s = i % GR_STAGES;
       mbar_wait(empty_bar(s), ((i / GR_STAGES) & 1) ^ 1);
@@ -98,11 +97,11 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
       const int p = p_begin + i * GR_PIX;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), 2 * natoms * GR_ATOM);
-        tma_load_3d(dst, &map, full_bar(s), cq, p, img);
-        tma_load_3d(dst + natoms * GR_ATOM, &map, full_bar(s), ck, p, img);
+        tma_load_4d(dst, &map, full_bar(s), 0, head, p, img);
+        tma_load_4d(dst + natoms * GR_ATOM, &map, full_bar(s), 0, heads + head, p, img);
         if (natoms == 2) {
-          tma_load_3d(dst + GR_ATOM, &map, full_bar(s), cq + 64, p, img);
-          tma_load_3d(dst + 3 * GR_ATOM, &map, full_bar(s), ck + 64, p, img);
+          tma_load_4d(dst + GR_ATOM, &map, full_bar(s), 64, head, p, img);
+          tma_load_4d(dst + 3 * GR_ATOM, &map, full_bar(s), 64, heads + head, p, img);
         }
       }
       __syncwarp();
@@ -180,10 +179,12 @@ int mdta_gram_tc(const bf16* qk, long ld, int nimg, int HW, int C, int heads, in
     attr = true;
   }
   CUtensorMap map;
-  const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)HW, (cuuint64_t)nimg};
-  const cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * HW};
-  const cuuint32_t box[3] = {64, GR_PIX, 1};
-  KD_TRY(make_map(&map, qk, 3, dims, str, box));
+  // {channel within a head, head slot (q heads then k heads), pixel, image}: the 64-channel box of a 48-channel head is clipped at
+  // the head boundary (zero fill, nothing fetched) instead of pulling the neighbouring head's / v's channels through HBM
+  const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)(2 * heads), (cuuint64_t)HW, (cuuint64_t)nimg};
+  const cuuint64_t str[3] = {(cuuint64_t)ch * 2, (cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * HW};
+  const cuuint32_t box[4] = {64, 1, GR_PIX, 1};
+  KD_TRY(make_map(&map, qk, 4, dims, str, box));
   int per = (HW + splits - 1) / splits;
   per = (per + GR_PIX - 1) / GR_PIX * GR_PIX;   // split boundaries on 64-pixel chunks; the tail is TMA zero fill
   ProfScope prof(PC_MDTA_GRAM, s, 2.0 * nimg * HW * C * ch + 4.0 * nimg * HW * C,
