@@ -9,9 +9,14 @@ A step = one KDLAE-T bf16 forward (hq 512x512 + sr 1024x1024) over a batch of 64
   value    : whole-job images/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e      : same metric through the drop-in nn.Module with pinned-HOST inputs/outputs (H2D + forward + D2H timed)
   roofline : dominant kernel class, algorithmic bytes-or-flops / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (torch CPU restatement of the reference forward) timed on the host cores
---impl reference times that CPU implementation as the reference arm (the reference is pure PyTorch-CPU-capable
-code; its own modules cannot travel to the GPU box, the oracle is pinned to them by tests/golden).
+  parity   : PSNR (device reduction, kdlae_psnr) of image 0 of the timed batch against one live CPU-oracle forward of the same
+             1x512x512 image - the metric is "images/s; PSNR vs ref"
+  strong_scaling : the same global batch of 64 split over the N ranks (BASELINE configs[1] read literally: 64 / N per GPU)
+  other_configs  : BASELINE configs[2] (KDLAE-S-FLS, 128 stacks of 5x512x512) and configs[3] (1024 images through KDLAE-S-US
+             stacks and ASDQE scoring), sharded over the N ranks, each with its own roofline
+  cpu_baseline : the reference algorithm on the host cores: the unmodified reference module when baseline/_ref/ holds it
+             (kind "reference"), else the CPU oracle port pinned to it by tests/golden (kind "port")
+--impl reference times that CPU implementation as the reference arm.
 """
 from __future__ import annotations
 
@@ -80,22 +85,61 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(size: int, threads: int, repeats: int = 1):
-    """images/s-equivalent of the CPU oracle: one fp32 forward at size x size, scaled by (size/512)^2 (FLOPs ~ H*W)."""
+_REF_MODEL = None
+
+
+def reference_teacher():
+    """The UNMODIFIED reference KDLAE_teacher when an install / copy of the reference lives under baseline/_ref/ (git-ignored;
+    BASELINE.md section 3), else None.  /root/reference itself is never read: it does not exist on the GPU box."""
+    global _REF_MODEL
+    if _REF_MODEL is not None:
+        return _REF_MODEL or None
+    _REF_MODEL = False
+    base = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(base):
+        for dirpath, _dirs, files in os.walk(base):
+            if "KDLAE_model.py" in files:
+                try:
+                    sys.path.insert(0, dirpath)
+                    from KDLAE_model import KDLAE_teacher  # type: ignore
+                    from oracle import synth
+                    m = KDLAE_teacher(**MODEL_KW)
+                    m.load_state_dict(synth.teacher_state_dict(seed=0, **{k: v for k, v in MODEL_KW.items() if k != "params"}),
+                                      strict=True)
+                    _REF_MODEL = m.eval()
+                except Exception as e:      # a broken copy must not take the bench down: fall back to the pinned port
+                    print(f"[bench] baseline/_ref present but unusable ({e!r}); using the oracle port", file=sys.stderr)
+                break
+    return _REF_MODEL or None
+
+
+def cpu_kind() -> str:
+    return "reference" if reference_teacher() is not None else "port"
+
+
+def cpu_oracle_rate(size: int, threads: int, repeats: int = 1, img=None, rate_value: float = 0.6):
+    """images/s-equivalent of the reference algorithm on the CPU: one fp32 forward at size x size, scaled by (size/512)^2
+    (FLOPs ~ H*W).  Returns (rate, seconds, (hq, sr) of the last forward)."""
     import oracle
     from oracle import synth
     torch.set_num_threads(threads)
     sd = synth.teacher_state_dict(seed=0, **{k: v for k, v in MODEL_KW.items() if k != "params"})
-    img = synth.seeded_tensor("bench.cpu.img", (1, 1, size, size), 0)
-    rate = torch.full((1, 1, size, size), 0.6)
-    best = float("inf")
+    if img is None:
+        img = synth.seeded_tensor("bench.cpu.img", (1, 1, size, size), 0)
+    rate = torch.full((1, 1, size, size), rate_value)
+    ref = reference_teacher()
+    best, out = float("inf"), None
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            oracle.teacher_forward(sd, img, rate)
+            if ref is not None:
+                o = ref({"img": img, "denoise_rate": rate})
+                out = (o["hq"], o["sr"])
+            else:
+                out = oracle.teacher_forward(sd, img, rate)
             best = min(best, time.perf_counter() - t0)
     scale = (size * size) / (512.0 * 512.0)
-    return scale / best, best
+    return scale / best, best, out
 
 
 def time_uint8_pipeline(pk, model, dev, B, S):
@@ -144,36 +188,87 @@ def time_uint8_pipeline(pk, model, dev, B, S):
             "d2h_bytes_per_step": int(hq_h.numel() + sr_h.numel())}
 
 
-def time_other_models(pk, synth, dev, pk_):
-    """Device-resident throughput of the other two forwards of the path (BASELINE configs 3 and 4 shapes, bf16)."""
-    def timeit(f, n=3):
+def roofline_of(prof, pk_):
+    """Roofline object of the kernel class with the largest share of a profiled pass (CUDA events per launch, kdlae_profile_*)."""
+    tot = sum(v["ms"] for v in prof.values())
+    name, v = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    per = v["ms"] / 1e3 / v["launches"]
+    gbs, tfl = v["bytes"] / v["launches"] / per / 1e9, v["flops"] / v["launches"] / per / 1e12
+    hbm_frac, tensor_frac = gbs / pk_["hbm_gbs"], (tfl / pk_["bf16_tflops"] if "tcgen05" in name else 0.0)
+    if hbm_frac >= tensor_frac:
+        r = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
+    else:
+        r = {"kernel": name, "bound": "tensor", "achieved": tfl, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": tensor_frac}
+    r.update(hbm_frac=hbm_frac, tensor_frac=tensor_frac, avg_launch_ms=per * 1e3, share_of_step=v["ms"] / tot, traffic=None,
+             algorithmic_bytes_per_launch=v["bytes"] / v["launches"], algorithmic_flops_per_launch=v["flops"] / v["launches"])
+    return r
+
+
+def time_other_configs(pk, synth, dev, pk_, world, rank, barrier, max_over_ranks):
+    """BASELINE configs[2] and configs[3] at their own batch sizes, sharded over the ranks (no collective), device-resident,
+    bf16: (3) KDLAE-S-FLS, 128 stacks of 5x512x512; (4) 1024 single-channel 512x512 images -> KDLAE-S-US on 5-frame stacks ->
+    ASDQE scores of the (origin, denoised) pairs with the channel replicated to 3 (ASDQE_test.py:60-61 `.convert('RGB')`)."""
+    from rethink_acoustic_image_enhancement_b200 import _lib
+    from rethink_acoustic_image_enhancement_b200.sharding import shard_slice
+
+    def timed(f, n=3):
         for _ in range(2):
             f()
-        torch.cuda.synchronize()
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(n):
             f()
         b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / n
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / n)
+
     out = {}
     with torch.no_grad():
-        s = pk.KDLAE_student(residual=True)
-        s.load_state_dict(synth.student_state_dict())
-        s = s.to(dev).eval().set_precision("bf16")
-        x = torch.rand(32, 5, 512, 512, device=dev)
-        ms = timeit(lambda: s(x))
-        out["KDLAE-S 5x512x512 stacks/s"] = {"value": 32 / ms * 1e3, "batch": 32, "tflops": 32 * 1.4881e11 / ms / 1e9,
-                                             "tensor_frac": 32 * 1.4881e11 / ms / 1e9 / pk_["bf16_tflops"]}
-        del s, x
-        a = pk.DenoiseRatePredictor()
-        a.load_state_dict(synth.asdqe_state_dict(), strict=False)
-        a = a.to(dev).eval().set_precision("bf16")
-        lq, gt = torch.rand(64, 3, 512, 512, device=dev), torch.rand(64, 3, 512, 512, device=dev)
-        ms = timeit(lambda: a(lq, gt))
-        out["ASDQE 3x512x512 pairs/s"] = {"value": 64 / ms * 1e3, "batch": 64, "tflops": 64 * 2.1368e11 / ms / 1e9,
-                                          "tensor_frac": 64 * 2.1368e11 / ms / 1e9 / pk_["bf16_tflops"]}
+        stu = pk.KDLAE_student(residual=True)
+        stu.load_state_dict(synth.student_state_dict())
+        stu = stu.to(dev).eval().set_precision("bf16")
+        # ---- configs[2]
+        sl = shard_slice(128, rank, world)
+        n3 = sl.stop - sl.start
+        x = torch.rand(n3, 5, 512, 512, device=dev)
+        ms = timed(lambda: stu(x))
+        entry = {"metric": "KDLAE-S-FLS 5x512x512 stacks/sec", "value": 128 / ms * 1e3, "unit": "stacks/s", "global_batch": 128,
+                 "per_gpu_batch": n3, "ms_per_step": ms, "dtype": "bf16",
+                 "model_tflops_per_gpu": n3 * 1.4881e11 / ms / 1e9, "model_tensor_frac": n3 * 1.4881e11 / ms / 1e9 / pk_["bf16_tflops"]}
+        if rank == 0:
+            _lib.profile_begin(); stu(x); entry["roofline"] = roofline_of(_lib.profile_end(), pk_)
+        barrier()
+        out["configs[2]"] = entry
+        del x
+        # ---- configs[3]
+        asd = pk.DenoiseRatePredictor()
+        asd.load_state_dict(synth.asdqe_state_dict(), strict=False)
+        asd = asd.to(dev).eval().set_precision("bf16")
+        sl = shard_slice(1024, rank, world)
+        n4 = sl.stop - sl.start
+        nst = (n4 + 4) // 5
+        frames = torch.rand(nst, 5, 512, 512, device=dev)
+
+        def pipeline():
+            den = stu(frames)
+            lq = frames.view(nst * 5, 1, 512, 512)[:n4].expand(n4, 3, 512, 512)
+            gt = den.view(nst * 5, 1, 512, 512)[:n4].expand(n4, 3, 512, 512)
+            return asd(lq, gt)
+
+        ms = timed(pipeline, n=2)
+        flops = nst * 1.4881e11 + n4 * 2.1368e11
+        entry = {"metric": "ASDQE-scored images/sec (KDLAE-S-US denoise + ASDQE score)", "value": 1024 / ms * 1e3, "unit": "images/s",
+                 "global_batch": 1024, "per_gpu_batch": n4, "stacks_per_gpu": nst, "ms_per_step": ms, "dtype": "bf16",
+                 "model_tflops_per_gpu": flops / ms / 1e9, "model_tensor_frac": flops / ms / 1e9 / pk_["bf16_tflops"]}
+        asd_ms = timed(lambda: asd(frames.view(nst * 5, 1, 512, 512)[:n4].expand(n4, 3, 512, 512),
+                                   frames.view(nst * 5, 1, 512, 512)[:n4].expand(n4, 3, 512, 512)), n=2)
+        entry["asdqe_only_pairs_per_s"] = 1024 / asd_ms * 1e3
+        entry["asdqe_only_tensor_frac"] = n4 * 2.1368e11 / asd_ms / 1e9 / pk_["bf16_tflops"]
+        if rank == 0:
+            _lib.profile_begin(); pipeline(); entry["roofline"] = roofline_of(_lib.profile_end(), pk_)
+        barrier()
+        out["configs[3]"] = entry
     return out
 
 
@@ -183,9 +278,9 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count() or 1
     # size the per-step sample so the whole run stays within a few minutes
-    _, t64 = cpu_oracle_rate(64, cores)           # also the warm-up of the thread pool
-    _, t128 = cpu_oracle_rate(128, cores)
-    budget = 150.0 / max(1, args.steps + args.warmup)
+    cpu_oracle_rate(64, cores)                    # also the warm-up of the thread pool
+    _, t128, _ = cpu_oracle_rate(128, cores)
+    budget = 240.0 / max(1, args.steps + args.warmup)
     size = 128
     for cand in (512, 256):
         if t128 * (cand / 128.0) ** 2 <= budget:
@@ -202,9 +297,11 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "KDLAE-T forward, 1x512x512 images, CPU oracle (reference algorithm, torch CPU ops)",
-                       "per_gpu_batch": args.batch, "size": args.size},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "KDLAE-T forward, 1x512x512 images, reference algorithm on the host CPU (torch CPU ops): "
+                                   + ("unmodified reference module from baseline/_ref" if cpu_kind() == "reference" else
+                                      "CPU oracle port pinned to the reference by tests/golden"),
+                       "per_gpu_batch": args.batch, "size": args.size, "sample_size": size, "same_size_as_metric": size == 512},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(), "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -224,7 +321,9 @@ def main():
     ap.add_argument("--profile-only", action="store_true",
                     help="for ncu launch lists: warm-up + timed device steps only (no e2e leg, no CPU baseline, no event profile); "
                          "the printed line is not a bench value")
-    ap.add_argument("--extras", action="store_true", help="also time KDLAE-S (config 3) and ASDQE (config 4) on rank 0")
+    ap.add_argument("--extras", action="store_true", help="also time the uint8 pre/post pipeline (SURVEY 8f N2) on rank 0")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[2] / configs[3] (KDLAE-S, ASDQE)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (global batch 64 split over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -270,7 +369,9 @@ def main():
 
     g = torch.Generator().manual_seed(1234 + rank)
     img_h = torch.rand(B, 1, S, S, generator=g).pin_memory()
-    rate_h = torch.rand(B, 1, 1, 1, generator=g).expand(B, 1, S, S).contiguous().pin_memory()
+    # denoise_rate: one value per image (KDLAE_T.ipynb cell 5, paired_image_dataset.py:961); the drop-in module takes it as
+    # [B,1,1,1] and broadcasts inside its kernel, so the H x W map is never built or copied
+    rate_h = torch.rand(B, 1, 1, 1, generator=g).pin_memory()
     img_d, rate_d = img_h.to(dev), rate_h.to(dev)
     hq_h = torch.empty(B, 1, S, S).pin_memory()
     sr_h = torch.empty(B, 1, 2 * S, 2 * S).pin_memory()
@@ -336,6 +437,29 @@ def main():
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- strong scaling: BASELINE configs[1] read literally - ONE batch of 64 split over the ranks (64 / N images per GPU) ----
+    strong = None
+    if not args.no_strong and not args.profile_only:
+        from rethink_acoustic_image_enhancement_b200.sharding import shard_slice
+        sl = shard_slice(B, rank, world)
+        si, sr_ = img_d[sl.start:sl.stop], rate_d[sl.start:sl.stop]
+
+        def step_strong():
+            with torch.no_grad():
+                return model({"img": si, "denoise_rate": sr_})
+        for _ in range(3):
+            step_strong()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            step_strong()
+        g1.record()
+        barrier()
+        ms_strong = max_over_ranks(g0.elapsed_time(g1))
+        strong = {"value": B * args.steps / (ms_strong / 1e3), "unit": UNIT, "scaling": "strong", "global_batch": B,
+                  "per_gpu_batch": sl.stop - sl.start, "ms_per_step": ms_strong / args.steps}
+
     if args.profile_only:
         if rank == 0:
             print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "gpu_launches": int(launches)}))
@@ -364,12 +488,19 @@ def main():
         prof = _lib.profile_end()
     barrier()
 
+    pk_ = peaks()
+    other = None
+    if not args.no_other_configs and S == 512:
+        im_d.clear(); rt_d.clear()
+        model._engine._ws.clear()           # hand the teacher's workspace back before the student / ASDQE batches
+        torch.cuda.empty_cache()
+        other = time_other_configs(pk, synth, dev, pk_, world, rank, barrier, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk_ = peaks()
     imgs = B * world * args.steps
     value = imgs / (ms_total / 1e3)
     e2e_value = imgs / (ms_e2e / 1e3)
@@ -392,9 +523,23 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": tv["flops"] / tv["launches"] / per_launch_s / 1e12,
                 "peak": pk_["bf16_tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["hbm_frac"], roof["tensor_frac"] = classes[top]["hbm_frac"], classes[top]["tensor_frac"]
     roof["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
+    roof["algorithmic_flops_per_launch"] = tv["flops"] / tv["launches"]
     roof["traffic"] = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write per launch, from an ncu capture
+    # what ncu says limits the class (issue slots / FMA pipe of the CUDA-core depthwise + GELU code), from the committed
+    # `--set full` capture of the same command (profiles/r02_issue.json, written by scripts/ncu_issue.py)
+    ipath = os.path.join(ROOT, "profiles", "r02_issue.json")
+    if os.path.exists(ipath):
+        with open(ipath) as fh:
+            ij = json.load(fh)
+        if top in ij:
+            roof["issue"] = ij[top]
+            if max(roof["hbm_frac"], roof["tensor_frac"] or 0.0) < 0.5 and ij[top].get("issue_frac", 0.0) >= 0.5:
+                roof["bound"] = "issue"       # neither roofline binds: instruction issue does (see roof["issue"])
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")   # dram__bytes_read+write per launch, from an ncu capture
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and S == 512:
         with open(tpath) as fh:
             tj = json.load(fh)
@@ -422,6 +567,7 @@ def main():
                    "per_gpu_batch": B, "global_batch": B * world, "size": S, "micro_batch": model.micro_batch or "auto",
                    "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "working set per step (>8 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
+        "strong_scaling": strong,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + rate_h.numel() * 4),
                 "d2h_bytes_per_step": int(hq_h.numel() * 4 + sr_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -431,15 +577,29 @@ def main():
         "model_tflops_per_gpu": whole_tflops,
         "model_tensor_frac": whole_tflops / pk_["bf16_tflops"],
     }
+    if other is not None:
+        line["other_configs"] = other
     if args.extras:
-        line["other_models"] = time_other_models(pk, synth, dev, pk_)
-        line["other_models"]["KDLAE-T uint8 pipeline e2e images/s"] = time_uint8_pipeline(pk, model, dev, B, S)
+        line["uint8_pipeline_e2e"] = time_uint8_pipeline(pk, model, dev, B, S)
     if not args.no_cpu_baseline:
+        # one live forward of the reference algorithm on image 0 of the timed batch: the CPU baseline AND the parity reference
+        from rethink_acoustic_image_enhancement_b200 import metrics as pm
         cores = os.cpu_count() or 1
         cpu_oracle_rate(64, cores)
-        v, t = cpu_oracle_rate(256 if cores >= 8 else 128, cores)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"one fp32 oracle forward of 1x1x{256 if cores >= 8 else 128}^2 ({t:.1f} s), scaled by H*W to 512x512 equivalents"}
+        csize = S if cores >= 8 else min(S, 128)
+        img0 = img_h[:1, :, :csize, :csize].contiguous()
+        v, t, (hq_ref, sr_ref) = cpu_oracle_rate(csize, cores, img=img0, rate_value=float(rate_h[0]))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                                "sample": f"one fp32 forward of the reference algorithm on image 0 of the batch at 1x{csize}x{csize} "
+                                          f"({t:.1f} s)" + ("" if csize == 512 else ", scaled by H*W to 512x512 equivalents")}
+        with torch.no_grad():
+            got = model({"img": img0.to(dev), "denoise_rate": rate_d[:1]})
+            p_hq = float(pm.psnr_batch(got["hq"], hq_ref.to(dev))[0])
+            p_sr = float(pm.psnr_batch(got["sr"], sr_ref.to(dev))[0])
+            finite = bool(torch.isfinite(got["hq"]).all() and torch.isfinite(got["sr"]).all())
+        line["parity"] = {"psnr_hq": p_hq, "psnr_sr": p_sr, "shape": f"1x{csize}x{csize}", "gate_db": 50.0, "finite": finite,
+                          "reference": cpu_kind(), "how": "device PSNR (kdlae_psnr) of the bf16 CUDA forward of image 0 of the "
+                                                          "timed batch vs one live CPU forward of the reference algorithm"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KDLAE_ABI_VERSION 1
+#define KDLAE_ABI_VERSION 2
 #define KDLAE_PREC_FP32 0
 #define KDLAE_PREC_BF16 1
 
@@ -68,11 +68,14 @@ int kdlae_teacher_pack(const kdlae_teacher_cfg* cfg, const float* const* tensors
 size_t kdlae_teacher_workspace_bytes(const kdlae_teacher_cfg* cfg, int micro_batch, int H, int W, int precision);
 /* Replaces KDLAE_teacher.forward (KDLAE_model.py:270-336).
  *   img  [B, inp_channels, H, W] fp32, H % 8 == 0 and W % 8 == 0 (else error, like pixel_unshuffle raising)
- *   rate [B, 1, H, W] fp32 (input["denoise_rate"]); may be NULL when params_cat == 0
+ *   rate input["denoise_rate"]: rate_per_image == 0: the [B, 1, H, W] fp32 map the reference concatenates (:316);
+ *        rate_per_image != 0: [B] fp32, one value per image, broadcast inside the dilated conv (the maps the notebook and the
+ *        dataset build are constant per image - KDLAE_T.ipynb cell 5, paired_image_dataset.py:961 - so the H x W map never has to
+ *        exist); may be NULL when params_cat == 0
  *   hq   [B, out_channels, H, W] fp32 out;  sr [B, out_channels, 2H, 2W] fp32 out (NULL iff sr_head == 0)
  * Images are processed `micro_batch` at a time inside the call (workspace is sized for micro_batch). */
-int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, float* hq,
-                          float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes,
+int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, int rate_per_image,
+                          float* hq, float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes,
                           int precision, void* stream);
 
 /* ---- KDLAE-S : KDLAE_student (KDLAE/KDLAE_model.py:340-430) ------------------------------------------ */
@@ -122,20 +125,10 @@ int kdlae_ln_stats(const void* x, int C, long rows, float* rstd, float* mu, int 
 int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H, int W, int C, int gate, int precision,
                     void* stream);
 
-/* Tensor-core depthwise 3x3 (bf16): the conv as 9 tcgen05.mma per 16-channel group with diagonal weight blocks.
- * wtc_scratch: kdlae_dwconv_tc_weight_bytes(C, gate) bytes of device memory (filled here from w9c, then used). */
-size_t kdlae_dwconv_tc_weight_bytes(int C, int gate);
-int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scratch, int nimg, int H, int W, int C, int gate,
-                       void* stream);
-
-/* Fused LayerNorm-folded 1x1 conv -> depthwise 3x3 (-> GELU gate) (KDLAE_model.py:95-104 / :118-119), bf16 tcgen05:
- * out = dw3x3(rstd[p] * (x . w1^T)) [gate: gelu(.[:Nt/2]) * .[Nt/2:]].  x [nimg,H,W,C] bf16, w1 [Nt][C] bf16,
- * w9c [9][Nt] fp32, wtc_scratch kdlae_dwconv_tc_weight_bytes(Nt, gate) bytes, out [nimg,H,W,Nt or Nt/2] bf16. */
-int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* wtc_scratch, void* out, int nimg,
-                  int H, int W, int C, int gate, void* stream);
-
-/* Same fused stage with the depthwise part on the CUDA cores (packed FFMA2; pwdw_f2.cu) - the default schedule of the bf16
- * TransformerBlock when C <= 128 and the LayerNorm is BiasFree.  Bit-identical to kdlae_conv_gemm + kdlae_dwconv3x3. */
+/* Fused LayerNorm-folded 1x1 conv (tcgen05) -> depthwise 3x3 on the CUDA cores (packed FFMA2) (-> GELU gate)
+ * (KDLAE_model.py:95-104 / :118-119): out = dw3x3(rstd[p] * (x . w1^T)) [gate: gelu(.[:Nt/2]) * .[Nt/2:]].
+ * x [nimg,H,W,C] bf16, w1 [Nt][C] bf16 (LayerNorm gamma folded), w9c [9][Nt] fp32, out [nimg,H,W,Nt or Nt/2] bf16.
+ * pwdw_f2.cu: bit-identical to kdlae_conv_gemm + kdlae_dwconv3x3 (the t tile is rounded to bf16 in shared memory). */
 int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
                   int gate, void* stream);
 
@@ -153,6 +146,26 @@ int kdlae_preprocess_u8(const unsigned char* src_hwc, int B, int h, int w, int c
                         int H, int W, void* stream);
 int kdlae_postprocess_u8(const float* pred_nchw, const unsigned char* src_hwc, int B, int h, int w, int c, int Hp, int Wp, int scale,
                          unsigned char* out_hwc, void* stream);
+
+/* ---- validation metric on device (Train/basicsr/metrics/psnr_ssim.py:9-70 calculate_psnr) -------------
+ * img1, img2 [B,C,H,W] fp32 (device).  crop_border pixels are dropped on every edge (:57-59).  as_uint8 != 0 first converts
+ * both images like tensor2img (utils/img_util.py:67-94: clamp(0,1), *255, round) - the `use_image` branch of
+ * nondist_validation (image_restoration_model.py:327-334).  mse_max (device, [B][2] doubles) receives per image the mean
+ * squared error over C x (H-2c) x (W-2c) and max(img1) (the reference picks max_value = 1 if img1.max() <= 1 else 255, :68-69);
+ * the host finishes with 20*log10(max_value / sqrt(mse)).  scratch: kdlae_psnr_scratch_bytes(B) bytes of device memory. */
+size_t kdlae_psnr_scratch_bytes(int B);
+int kdlae_psnr(const float* img1, const float* img2, int B, int C, int H, int W, int crop_border, int as_uint8, double* mse_max,
+               void* scratch, void* stream);
+
+/* ---- training loss (Train/basicsr/models/losses/losses.py:135-194 L1LossSr, reduction='mean') --------
+ * loss[0] = 0.5*lw*mean|hq-hq_gt| + 0.25*lw*mean|sr-sr_gt| + 0.25*lw*(mean|[hq>0.1]-[hq_gt>0.1]| + mean|[sr>0.1]-[sr_gt>0.1]|)
+ * grad_hq / grad_sr (nullable) receive d loss / d pred = 0.5*lw*sign(hq-hq_gt)/n_hq and 0.25*lw*sign(sr-sr_gt)/n_sr (the
+ * binarised "shadow" terms are piecewise constant: zero gradient, exactly as autograd sees torch.where).  sr may be NULL
+ * (pred['sr'] is None, :166-171).  terms (nullable, device [4] doubles): the four means in the order above.
+ * scratch: kdlae_l1_sr_scratch_bytes() bytes of device memory.  Sums are double, combined in a fixed order (deterministic). */
+size_t kdlae_l1_sr_scratch_bytes(void);
+int kdlae_l1_sr_loss(const float* hq, const float* hq_gt, long n_hq, const float* sr, const float* sr_gt, long n_sr,
+                     float loss_weight, float* loss, float* grad_hq, float* grad_sr, double* terms, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

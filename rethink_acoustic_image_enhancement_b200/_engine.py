@@ -31,7 +31,8 @@ class Engine:
     def __init__(self, kind: str):
         self.kind = kind
         self._packed = {}      # (device, prec) -> (signature, uint8 tensor)
-        self._ws = {}          # device -> uint8 tensor
+        self._ws = {}          # (device, stream) -> uint8 tensor
+        self._params = None    # cached parameter / buffer list in state_dict() order
         self._checked = set()
 
     # -- device / library -------------------------------------------------------------------
@@ -76,14 +77,28 @@ class Engine:
 
     def invalidate(self) -> None:
         self._packed.clear()
+        self._params = None
+
+    def tensors(self, module) -> List[Optional[torch.Tensor]]:
+        """The module's parameters and buffers in state_dict() order, cached: walking state_dict() (483 entries for the
+        teacher) on every forward costs more host time than the launch of a small forward.  The cache holds the tensor objects
+        themselves, so in-place updates (optimizer steps) are seen through their version counters; anything that rebinds
+        them (load_state_dict, .to(), _apply) goes through invalidate()."""
+        if self._params is None:
+            self._params = [v for v in module.state_dict(keep_vars=True).values()]
+        return self._params
 
     # -- workspace --------------------------------------------------------------------------
     def workspace(self, device: torch.device, nbytes: int) -> torch.Tensor:
-        ws = self._ws.get(device)
+        """Scratch buffer of the forward, one per (device, stream): two forwards of one module on two streams never share
+        activations (nothing would order the second call's writes against the first call's reads), and a buffer is only ever
+        freed / regrown from the stream it was allocated on, which is the order the caching allocator guarantees."""
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
-            self._ws[device] = None
+            self._ws[key] = None
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self._ws[device] = ws
+            self._ws[key] = ws
         return ws
 
     @staticmethod

@@ -50,7 +50,7 @@ SIGNATURES = {
     "kdlae_teacher_packed_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int]),
     "kdlae_teacher_pack": (C.c_int, [C.POINTER(TeacherCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "kdlae_teacher_workspace_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
-    "kdlae_teacher_forward": (C.c_int, [C.POINTER(TeacherCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    "kdlae_teacher_forward": (C.c_int, [C.POINTER(TeacherCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "kdlae_student_packed_bytes": (C.c_size_t, [C.POINTER(StudentCfg), C.c_int]),
     "kdlae_student_pack": (C.c_int, [C.POINTER(StudentCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
@@ -70,11 +70,6 @@ SIGNATURES = {
     "kdlae_ln_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kdlae_dwconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p]),
-    "kdlae_dwconv_tc_weight_bytes": (C.c_size_t, [C.c_int, C.c_int]),
-    "kdlae_dwconv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p]),
-    "kdlae_pwdw_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "kdlae_pwdw_f2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
     "kdlae_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -83,6 +78,12 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "kdlae_pwdw_t": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
+    "kdlae_psnr_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "kdlae_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                             C.c_void_p]),
+    "kdlae_l1_sr_scratch_bytes": (C.c_size_t, []),
+    "kdlae_l1_sr_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -102,7 +103,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.kdlae_abi_version() != 1:
+    if lib.kdlae_abi_version() != 2:
         raise RuntimeError("libkdlae_b200.so ABI version mismatch")
     _lib = lib
     return lib

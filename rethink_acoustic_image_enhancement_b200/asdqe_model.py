@@ -105,7 +105,7 @@ class DenoiseRatePredictor(_FusedModule):
     def _run(self, lq: torch.Tensor, gt: torch.Tensor, want_feat: bool):
         eng = self._engine
         eng.require_cuda(lq, "DenoiseRatePredictor")
-        self._no_autograd("DenoiseRatePredictor")
+        self._no_autograd("DenoiseRatePredictor", lq, gt)
         if lq.shape != gt.shape or lq.dim() != 4 or lq.shape[1] != self._in_channels:
             raise RuntimeError(f"DenoiseRatePredictor: expected lq/gt [B,{self._in_channels},H,W] of equal shape, got "
                                f"{tuple(lq.shape)} and {tuple(gt.shape)}")
@@ -115,7 +115,7 @@ class DenoiseRatePredictor(_FusedModule):
         with torch.cuda.device(dev):
             lqc = lq.detach().to(torch.float32).contiguous()
             gtc = gt.detach().to(device=dev, dtype=torch.float32).contiguous()
-            tensors = [v if v.is_floating_point() else None for v in self.state_dict(keep_vars=True).values()]
+            tensors = [v if v.is_floating_point() else None for v in eng.tensors(self)]   # num_batches_tracked -> NULL
             nbytes = lib.kdlae_asdqe_packed_bytes(cfg, prec)
 
             def pack(arr, n, blob):

@@ -1,11 +1,33 @@
 // extern "C" boundary (include/kdlae_b200.h): argument checking, precision dispatch, error text.
+#include <mutex>
 #include <vector>
 #include "models.cuh"
 
 namespace kd {
 
 static thread_local char g_err[1024] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
+
+int device_first_use(DeviceOnce& once, bool* first, int* dev) {
+  KD_CUDA(cudaGetDevice(dev));
+  KD_CHECK(*dev >= 0 && *dev < KD_MAX_DEVICES, "device index %d out of range", *dev);
+  *first = !(once.mask.load(std::memory_order_acquire) & (1ull << *dev));
+  return 0;
+}
+int device_sms(int* sms) {
+  static std::atomic<int> cache[KD_MAX_DEVICES];
+  int dev = 0;
+  KD_CUDA(cudaGetDevice(&dev));
+  KD_CHECK(dev >= 0 && dev < KD_MAX_DEVICES, "device index %d out of range", dev);
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    KD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    v = sm_limit(v);
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,7 +39,8 @@ const char* get_error() { return g_err; }
 
 // ---- profiler ----------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;   // launches may come from several host threads (nn.DataParallel replicas)
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_event_pool;
 static size_t g_pool_used = 0;
@@ -34,7 +57,8 @@ static cudaEvent_t prof_event() {
   return g_event_pool[g_pool_used++];
 }
 ProfScope::ProfScope(int cls, cudaStream_t s, double flops, double bytes) : stream(s) {
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   active = true;
   ProfRec r;
   r.a = prof_event(); r.b = prof_event(); r.cls = cls; r.flops = flops; r.bytes = bytes;
@@ -43,7 +67,9 @@ ProfScope::ProfScope(int cls, cudaStream_t s, double flops, double bytes) : stre
   g_recs.push_back(r);
 }
 ProfScope::~ProfScope() {
-  if (active) cudaEventRecord(g_recs[slot].b, stream);
+  if (!active) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_recs.size()) cudaEventRecord(g_recs[slot].b, stream);
 }
 
 }  // namespace kd
@@ -57,7 +83,7 @@ extern "C" {
 
 int kdlae_abi_version(void) { return KDLAE_ABI_VERSION; }
 const char* kdlae_last_error(void) { return kd::get_error(); }
-unsigned long long kdlae_launch_count(void) { return kd::g_launch_count; }
+unsigned long long kdlae_launch_count(void) { return kd::g_launch_count.load(); }
 
 int kdlae_device_check(int device) {
   API_BEGIN();
@@ -81,6 +107,7 @@ int kdlae_profile_num_classes(void) { return kd::PC_COUNT; }
 const char* kdlae_profile_class_name(int cls) { return (cls >= 0 && cls < kd::PC_COUNT) ? kd::kProfNames[cls] : ""; }
 int kdlae_profile_begin(void) {
   API_BEGIN();
+  std::lock_guard<std::mutex> lk(kd::g_prof_mu);
   kd::g_recs.clear();
   kd::g_pool_used = 0;
   kd::g_prof_on = true;
@@ -92,6 +119,7 @@ int kdlae_profile_end(int n_classes, double* ms, double* flops, double* bytes, l
   KD_CHECK(n_classes == kd::PC_COUNT && ms && flops && bytes && launches, "kdlae_profile_end: bad arguments");
   for (int i = 0; i < kd::PC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
   KD_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(kd::g_prof_mu);
   for (const auto& r : kd::g_recs) {
     float t = 0.f;
     KD_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
@@ -123,16 +151,18 @@ size_t kdlae_teacher_workspace_bytes(const kdlae_teacher_cfg* cfg, int micro_bat
   return precision == KDLAE_PREC_BF16 ? kd::teacher_workspace_bytes<bf16>(*cfg, micro_batch, H, W)
                                       : kd::teacher_workspace_bytes<float>(*cfg, micro_batch, H, W);
 }
-int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, float* hq,
-                          float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes, int precision,
-                          void* stream) {
+int kdlae_teacher_forward(const kdlae_teacher_cfg* cfg, const void* packed, const float* img, const float* rate, int rate_per_image,
+                          float* hq, float* sr, int B, int H, int W, int micro_batch, void* workspace, size_t workspace_bytes,
+                          int precision, void* stream) {
   API_BEGIN();
   KD_CHECK(cfg && packed && img && hq && workspace, "kdlae_teacher_forward: NULL argument");
   CHECK_PREC(precision);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return precision == KDLAE_PREC_BF16
-             ? kd::teacher_forward<bf16>(*cfg, packed, img, rate, hq, sr, B, H, W, micro_batch, workspace, workspace_bytes, s)
-             : kd::teacher_forward<float>(*cfg, packed, img, rate, hq, sr, B, H, W, micro_batch, workspace, workspace_bytes, s);
+             ? kd::teacher_forward<bf16>(*cfg, packed, img, rate, rate_per_image, hq, sr, B, H, W, micro_batch, workspace,
+                                         workspace_bytes, s)
+             : kd::teacher_forward<float>(*cfg, packed, img, rate, rate_per_image, hq, sr, B, H, W, micro_batch, workspace,
+                                          workspace_bytes, s);
 }
 
 // ---------------- student ----------------
@@ -269,29 +299,6 @@ int kdlae_dwconv3x3(const void* x, void* out, const float* w9c, int nimg, int H,
                                     W, C, gate, s);
 }
 
-size_t kdlae_dwconv_tc_weight_bytes(int C, int gate) { return kd::dwconv_tc_weight_bytes(C, gate); }
-
-int kdlae_dwconv3x3_tc(const void* x, void* out, const float* w9c, void* wtc_scratch, int nimg, int H, int W, int C, int gate,
-                       void* stream) {
-  API_BEGIN();
-  KD_CHECK(x && out && w9c && wtc_scratch, "kdlae_dwconv3x3_tc: NULL argument");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  KD_TRY(kd::pack_dw_tc(w9c, C, gate, wtc_scratch, s));
-  const long ldo = gate ? C / 2 : C;
-  return kd::dwconv3x3<bf16>(reinterpret_cast<const bf16*>(x), C, reinterpret_cast<bf16*>(out), ldo, w9c, nullptr, nimg, H, W, C,
-                             gate, s, wtc_scratch);
-}
-
-int kdlae_pwdw_tc(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* wtc_scratch, void* out, int nimg,
-                  int H, int W, int C, int gate, void* stream) {
-  API_BEGIN();
-  KD_CHECK(x && rstd && w1 && w9c && wtc_scratch && out, "kdlae_pwdw_tc: NULL argument");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  KD_TRY(kd::pack_dw_tc(w9c, Nt, gate, wtc_scratch, s));
-  return kd::pwdw_tc(reinterpret_cast<const bf16*>(x), C, rstd, reinterpret_cast<const bf16*>(w1), Nt, wtc_scratch,
-                     reinterpret_cast<bf16*>(out), gate ? Nt / 2 : Nt, nimg, H, W, C, gate, s);
-}
-
 int kdlae_pwdw_f2(const void* x, const float* rstd, const void* w1, int Nt, const float* w9c, void* out, int nimg, int H, int W, int C,
                   int gate, void* stream) {
   API_BEGIN();
@@ -320,6 +327,32 @@ int kdlae_postprocess_u8(const float* pred_nchw, const unsigned char* src_hwc, i
   API_BEGIN();
   KD_CHECK(pred_nchw && src_hwc && out_hwc, "kdlae_postprocess_u8: NULL argument");
   return kd::postprocess_u8(pred_nchw, src_hwc, B, h, w, c, Hp, Wp, scale, out_hwc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t kdlae_psnr_scratch_bytes(int B) { return B > 0 ? kd::psnr_scratch_bytes(B) : 0; }
+
+int kdlae_psnr(const float* img1, const float* img2, int B, int C, int H, int W, int crop_border, int as_uint8, double* mse_max,
+               void* scratch, void* stream) {
+  API_BEGIN();
+  KD_CHECK(img1 && img2 && mse_max && scratch, "kdlae_psnr: NULL argument");
+  return kd::psnr_mse(img1, img2, B, C, H, W, crop_border, as_uint8, mse_max, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t kdlae_l1_sr_scratch_bytes(void) { return kd::l1_sr_scratch_bytes(); }
+
+int kdlae_l1_sr_loss(const float* hq, const float* hq_gt, long n_hq, const float* sr, const float* sr_gt, long n_sr,
+                     float loss_weight, float* loss, float* grad_hq, float* grad_sr, double* terms, void* scratch, void* stream) {
+  API_BEGIN();
+  KD_CHECK(hq && hq_gt && loss && scratch && n_hq > 0, "kdlae_l1_sr_loss: NULL argument");
+  KD_CHECK((sr == nullptr) == (sr_gt == nullptr) && (sr == nullptr || n_sr > 0), "kdlae_l1_sr_loss: sr and sr_gt go together");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // 0.5 * lw * L1(hq) + 0.25 * lw * shadow(hq)   [+ 0.25 * lw * L1(sr) + 0.25 * lw * shadow(sr)]
+  KD_TRY(kd::l1_shadow_term(hq, hq_gt, n_hq, 0.5f * loss_weight, 0.25f * loss_weight, 0, loss, grad_hq, terms, scratch, s));
+  if (sr) {
+    KD_TRY(kd::l1_shadow_term(sr, sr_gt, n_sr, 0.25f * loss_weight, 0.25f * loss_weight, 1, loss, grad_sr, terms ? terms + 2 : nullptr,
+                              scratch, s));
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ template <typename T>
 struct AsdqeW {
   struct Stem { float* w1; float* scale1; float* shift1; CBR<T> c2; } stem[3];
   CBR<T> inc[2], d1[2], d2[2], d3[2], u1[2], u2[2], u3[2];
-  T* outc; float* outc_b;
+  T* outc; float* outc_b; float* outc_f;    // outc_f: fp32 [3*dim][64] for the GAP-commuted score path
   float *w1, *b1, *w2, *b2, *w3, *b3;
 };
 
@@ -45,6 +45,7 @@ void layout_asdqe(const kdlae_asdqe_cfg& c, Bump& b, AsdqeW<T>& w) {
   cbr(w.u3[0], 128, 64); cbr(w.u3[1], 64, 64);
   w.outc = b.take<T>((size_t)cc * 64);
   w.outc_b = b.take<float>(cc);
+  w.outc_f = b.take<float>((size_t)cc * 64);
   w.w1 = b.take<float>((size_t)256 * cc); w.b1 = b.take<float>(256);
   w.w2 = b.take<float>(64 * 256); w.b2 = b.take<float>(64);
   w.w3 = b.take<float>(64); w.b3 = b.take<float>(1);
@@ -142,6 +143,7 @@ int asdqe_pack(const kdlae_asdqe_cfg& c, const float* const* t, int n_tensors, v
     p.src = ow; p.n_src = cc; p.c_src = 64; p.taps = 1; p.dst = w.outc; p.n_dst = cc; p.c_dst = 64;
     KD_TRY(pack_weights<T>(p, s));
     KD_TRY(copy_f32(ob, w.outc_b, cc, s));
+    KD_TRY(copy_f32(ow, w.outc_f, (long)cc * 64, s));
   }
   const float* r[6];
   for (int i = 0; i < 6; ++i) { r[i] = cur.next(); KD_CHECK(r[i], "asdqe_pack: missing regressor tensor"); }
@@ -218,15 +220,18 @@ int asdqe_forward(const kdlae_asdqe_cfg& c, const void* packed, const float* lq,
       cur = b[l];
       cur_c = up[j][1].cout;
     }
-    // outc 1x1 64 -> 3*dim (+bias) (:72)
-    {
+    // outc 1x1 64 -> 3*dim (+bias) (:72) followed by AdaptiveAvgPool2d(1) (:168): both are linear, so the score path averages
+    // the 64-channel decoder output first and applies outc to the [n, 64] means in fp32 inside the head kernel - the
+    // 48-channel full-resolution map (a write + a read of HWp * 96 B per image, plus its bf16 rounding in front of the
+    // regressor) is only materialised when the caller asks for `enhanced_feat`
+    KD_TRY(gap_mlp_tanh<T>(b[0], n, (int)HWp, 64, w.outc_f, w.outc_b, cc, w.w1, w.b1, w.w2, w.b2, w.w3, w.b3, score + b0, gap, s));
+    if (feat) {
       ConvOp g;
       g.a0 = b[0]; g.c0 = 64; g.ld0 = 64; g.nimg = n; g.H = Hp; g.W = Wp; g.w = w.outc; g.w_ld = 64; g.w_tap_ld = 64;
       g.epi.col_bias = w.outc_b; g.epi.out = F48; g.epi.out_ld = cc; g.epi.N = cc; g.epi.H = Hp; g.epi.W = Wp;
       KD_TRY(conv_gemm<T>(g, s));
+      KD_TRY(nhwc_to_planar<T>(F48, cc, feat + (long)b0 * cc * HWp, n, (int)HWp, cc, s));
     }
-    KD_TRY(gap_mlp_tanh<T>(F48, n, (int)HWp, cc, w.w1, w.b1, w.w2, w.b2, w.w3, w.b3, score + b0, gap, s));
-    if (feat) KD_TRY(nhwc_to_planar<T>(F48, cc, feat + (long)b0 * cc * HWp, n, (int)HWp, cc, s));
   }
   return 0;
 }

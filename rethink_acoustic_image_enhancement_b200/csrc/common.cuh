@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 
 namespace kd {
 
@@ -43,8 +44,8 @@ const char* get_error();
 #define KD_LAUNCH_CHECK() KD_CUDA(cudaGetLastError())
 
 // ---- launch counter (bench.py reports gpu_launches) -------------------------------------
-extern unsigned long long g_launch_count;
-inline void count_launch() { ++g_launch_count; }
+extern std::atomic<unsigned long long> g_launch_count;
+inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- SM budget of the persistent kernels ---------------------------------------------------
 // KDLAE_SM_LIMIT=n caps the grid of every persistent kernel at n SMs, so two forwards on two streams can run side by side
@@ -68,6 +69,17 @@ struct ProfScope {
   ProfScope(int cls, cudaStream_t s, double flops, double bytes);
   ~ProfScope();
 };
+
+// ---- per-device one-time state ---------------------------------------------------------------
+// cudaFuncSetAttribute and the SM count belong to the CURRENT device, so "done once" flags are kept per device: a module
+// moved from cuda:0 to cuda:1 in one process (or nn.DataParallel threads, one device each) sets its kernels up again there.
+constexpr int KD_MAX_DEVICES = 64;
+struct DeviceOnce { std::atomic<unsigned long long> mask{0}; };
+// *first = the current device has not been marked in `once` yet; *dev = current device
+int device_first_use(DeviceOnce& once, bool* first, int* dev);
+inline void device_mark(DeviceOnce& once, int dev) { once.mask.fetch_or(1ull << dev, std::memory_order_acq_rel); }
+// SM count of the current device after KDLAE_SM_LIMIT (cached per device)
+int device_sms(int* sms);
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

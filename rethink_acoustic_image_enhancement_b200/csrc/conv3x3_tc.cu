@@ -4,7 +4,7 @@
 // gemm_tc.cu's spatial mode re-loaded the activation tile for each of the 9 (27) taps.  Here the halo tile
 // {64 ch, 32 px, 6 rows} is brought in once (TMA, 128B swizzle, row pitch exactly 32 pixels, zero padding = OOB fill) and
 // the 9 spatial taps are 9 shifted shared-memory descriptors over it: start address += (dy*32 + dx) * 128 bytes (the
-// swizzle XOR follows the absolute address, verified by dwconv_tc.cu).  Only the weight tiles stream per tap.
+// swizzle XOR follows the absolute address, verified on B200 in round 1).  Only the weight tiles stream per tap.
 // A tile yields 4 rows x 30 pixels (columns 30,31 of each row are garbage and never stored).
 // Two smem rings: A (2 slots, each consumed by 9 taps) and W (3 slots, one per tap).  TMEM double buffered, epilogues as
 // in gemm_tc.cu: FAST = swizzled slabs + TMA stores/loads (bias, ReLU, residual), generic = epilogue_store8
@@ -376,20 +376,19 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   }
 }
 
-int g_c3_sms = 0;
-
 }  // namespace
 
 // dense 3x3 (kd = 1) or 3x3x3 (kd = 3) conv, dilation 1; called by conv_gemm_tc for every spatial op
 int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
-  if (g_c3_sms == 0) {
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_c3_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_c3_sms = sm_limit(g_c3_sms);
+  static DeviceOnce once;
+  bool first; int dev, g_c3_sms;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_MAX));
     KD_CUDA(cudaFuncSetAttribute(k_conv3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_MAX));
+    device_mark(once, dev);
   }
+  KD_TRY(device_sms(&g_c3_sms));
   const Epilogue& e = op.epi;
   C3Params p;
   memset(&p, 0, sizeof(p));

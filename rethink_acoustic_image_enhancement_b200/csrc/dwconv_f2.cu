@@ -1,7 +1,7 @@
 // Depthwise 3x3 (+ optional GELU gate) for NHWC bf16 on the CUDA cores with packed fp32 FMAs (FFMA2, fma.rn.f32x2)
 //   (KDLAE_model.py:97,103-104 FeedForward.dwconv + gate, :119 Attention.qkv_dwconv).
 //
-// Why not the tensor cores (dwconv_tc.cu): a depthwise conv has no reuse across channels, so the diagonal-weight MMA reads
+// Why not the tensor cores (round-1 dwconv_tc.cu, removed; numbers in profiles/r01_summary.md): a depthwise conv has no reuse across channels, so the diagonal-weight MMA reads
 // its 128 x 16 activation operand from shared memory once per tap - 9x the tile - and ncu shows that kernel pinned on
 // L1/shared-memory throughput (82 %) at ~55 % of the HBM rate.  Here every input value is read from shared memory ~1.9x:
 //   * lane = one bf16x2 channel pair of a 64-channel block (a warp-wide LDS.32 is exactly one pixel's 128-byte row, so
@@ -198,16 +198,17 @@ k_dwconv_f2(const __grid_constant__ CUtensorMap map, const F2Params p) {
   }
 }
 
-int g_f2_sms = 0;
-
 template <int GATE>
 int launch_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, cudaStream_t s) {
   typedef F2Cfg<GATE> Cfg;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  bool first; int dev, g_f2_sms;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_dwconv_f2<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
+    device_mark(once, dev);
   }
+  KD_TRY(device_sms(&g_f2_sms));
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
   const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
@@ -235,12 +236,6 @@ int launch_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, in
 int dwconv3x3_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
                  cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) || ldx % 8 || ldo % 2 || C % (gate ? 16 : 8)) return -1;
-  if (g_f2_sms == 0) {
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_f2_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_f2_sms = sm_limit(g_f2_sms);
-  }
   return gate ? launch_f2<1>(x, ldx, out, ldo, w9c, nimg, H, W, C, s) : launch_f2<0>(x, ldx, out, ldo, w9c, nimg, H, W, C, s);
 }
 

@@ -426,8 +426,6 @@ int pick_nc(int N, int* n_chunks) {
   return best_nc;
 }
 
-int g_num_sms = 0;
-
 // KDLAE_CONV3X3_LEGACY=1 keeps 3x3 convs on this file's tap-by-tap path (A/B comparison in scripts/time_models.py)
 bool conv3x3_legacy() {
   static int v = -1;
@@ -462,13 +460,14 @@ bool conv_gemm_tc_eligible(const ConvOp& op) {
 
 int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   KD_CHECK(conv_gemm_tc_eligible(op), "conv_gemm_tc: shape not eligible");
-  if (g_num_sms == 0) {
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_num_sms = sm_limit(g_num_sms);
+  static DeviceOnce once;
+  bool first; int dev, g_num_sms;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(set_smem_attr());
+    device_mark(once, dev);
   }
+  KD_TRY(device_sms(&g_num_sms));
   if (op.kh == 3 && op.dil == 1 && op.epi.row_scale == nullptr && op.epi.row_mu == nullptr && op.epi.stat_rstd == nullptr &&
       !conv3x3_legacy()) {
     int n_chunks = 1;

@@ -123,39 +123,14 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const T* __restrict__ x, long
   }
 }
 
-int dwconv3x3_tma(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
-                  cudaStream_t s);
-
-int dwconv3x3_tc(const bf16* x, long ldx, bf16* out, long ldo, const void* wtc, int nimg, int H, int W, int C, int gate,
-                 cudaStream_t s);
-
 int dwconv3x3_f2(const bf16* x, long ldx, bf16* out, long ldo, const float* w9c, int nimg, int H, int W, int C, int gate,
                  cudaStream_t s);
 
-// KDLAE_DW selects the bf16 depthwise kernel: "f2" (default: packed-FFMA2 CUDA-core kernel, dwconv_f2.cu), "tc"
-// (tensor-core diagonal-weight kernel, dwconv_tc.cu), "tma" (first TMA-tiled CUDA-core kernel, dwconv_tma.cu)
-static int dw_mode() {
-  static int m = -1;
-  if (m < 0) {
-    const char* e = getenv("KDLAE_DW");
-    m = (e && !strcmp(e, "tc")) ? 0 : (e && !strcmp(e, "tma")) ? 2 : 1;
-  }
-  return m;
-}
-
 template <typename T>
 int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias, int nimg, int H, int W, int C,
-              int gate, cudaStream_t s, const void* wtc) {
-  if (std::is_same<T, bf16>::value && bias == nullptr && dw_mode() == 1) {
+              int gate, cudaStream_t s) {
+  if (std::is_same<T, bf16>::value && bias == nullptr) {   // packed-FFMA2 TMA-staged kernel (dwconv_f2.cu); < 0: shape not eligible
     const int r = dwconv3x3_f2(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, w9c, nimg, H, W, C, gate, s);
-    if (r >= 0) return r;
-  }
-  if (std::is_same<T, bf16>::value && bias == nullptr && wtc != nullptr && dw_mode() != 2) {   // tensor-core kernel (diagonal-weight implicit GEMM)
-    const int r = dwconv3x3_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, wtc, nimg, H, W, C, gate, s);
-    if (r >= 0) return r;
-  }
-  if (std::is_same<T, bf16>::value && bias == nullptr) {   // TMA-staged CUDA-core tile kernel
-    const int r = dwconv3x3_tma(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, w9c, nimg, H, W, C, gate, s);
     if (r >= 0) return r;
   }
   KD_CHECK(C % (gate ? 16 : 8) == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dwconv3x3: C=%d ldx=%ld ldo=%ld alignment", C, ldx, ldo);
@@ -167,8 +142,8 @@ int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const fl
   KD_LAUNCH_CHECK();
   return 0;
 }
-template int dwconv3x3<float>(const float*, long, float*, long, const float*, const float*, int, int, int, int, int, cudaStream_t, const void*);
-template int dwconv3x3<bf16>(const bf16*, long, bf16*, long, const float*, const float*, int, int, int, int, int, cudaStream_t, const void*);
+template int dwconv3x3<float>(const float*, long, float*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
+template int dwconv3x3<bf16>(const bf16*, long, bf16*, long, const float*, const float*, int, int, int, int, int, cudaStream_t);
 
 // =====================================================================================
 // MDTA reductions (KDLAE_model.py:134-137): partial Gram q k^T + squared L2 norms over pixels
@@ -272,11 +247,12 @@ int mdta_gram(const T* qk, long ld, int nimg, int HW, int C, int heads, int spli
   }
   KD_CHECK(C % heads == 0 && ch % 8 == 0 && ch <= 128 && 2 * ch <= 256, "mdta_gram: unsupported channels/head %d", ch);
   const size_t smem = sizeof(float) * (size_t)max(2 * GRAM_PT * ch, ch * ch);
-  static bool attr_f = false, attr_b = false;
-  bool& attr = std::is_same<T, float>::value ? attr_f : attr_b;
-  if (!attr) {
+  static DeviceOnce once;     // one per instantiation (T)
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_mdta_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    device_mark(once, dev);
   }
   dim3 grid(splits, heads, nimg);
   ProfScope prof(PC_MDTA_GRAM, s, 2.0 * nimg * HW * C * ch + 4.0 * nimg * HW * C,
@@ -362,11 +338,12 @@ template <typename T>
 int mdta_fold(float* part, int nimg, int C, int heads, int splits, const float* temperature, const float* wproj, T* mb,
               long mb_ld, long mb_img_stride, cudaStream_t s) {
   const int ch = C / heads;
-  static bool attr_f = false, attr_b = false;
-  bool& attr = std::is_same<T, float>::value ? attr_f : attr_b;
-  if (!attr) {
+  static DeviceOnce once;     // one per instantiation (T)
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_mdta_project<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    device_mark(once, dev);
   }
   ProfScope prof(PC_MDTA_FOLD, s, 2.0 * nimg * C * C * ch, 4.0 * nimg * heads * splits * (ch * ch + 2 * ch) + (double)nimg * C * C * (4 + sizeof(T)));
   k_mdta_softmax<<<dim3(cdiv(ch, 8), heads, nimg), 256, sizeof(float) * (9 * ch + 8), s>>>(part, C, heads, splits, temperature);
@@ -436,7 +413,7 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
                   t = __ldg(op.in0 + o);
                   if (op.sub0) t -= __ldg(op.sub0 + o);
                 } else {
-                  t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp);
+                  t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp * op.in1_px);
                 }
               }
               v[q] = t;
@@ -700,17 +677,24 @@ __global__ void __launch_bounds__(256) k_gap_partial(const T* __restrict__ f, in
   }
 }
 // regressor (ASDQE_model.py:143-154): mean -> Linear(C,256) ReLU -> Linear(256,64) ReLU -> Linear(64,1) -> tanh
-__global__ void __launch_bounds__(256) k_mlp_tanh(const float* __restrict__ scratch, int chunks, int C, float inv_hw,
+__global__ void __launch_bounds__(256) k_mlp_tanh(const float* __restrict__ scratch, int chunks, int C0, float inv_hw,
+                                                  const float* __restrict__ outc_w, const float* __restrict__ outc_b, int C,
                                                   const float* __restrict__ w1, const float* __restrict__ b1,
                                                   const float* __restrict__ w2, const float* __restrict__ b2,
                                                   const float* __restrict__ w3, const float* __restrict__ b3,
                                                   float* __restrict__ score) {
-  __shared__ float f[64], h1[256], h2[64];
+  __shared__ float g[64], f[64], h1[256], h2[64];
   const int img = blockIdx.x, tid = threadIdx.x;
-  if (tid < C) {
+  if (tid < C0) {
     float t = 0.f;
-    for (int k = 0; k < chunks; ++k) t += scratch[((long)img * chunks + k) * C + tid];
-    f[tid] = t * inv_hw;
+    for (int k = 0; k < chunks; ++k) t += scratch[((long)img * chunks + k) * C0 + tid];
+    g[tid] = t * inv_hw;
+  }
+  __syncthreads();
+  if (tid < C) {                       // outc on the channel means (mean and the 1x1 conv commute)
+    float t = outc_b[tid];
+    for (int c = 0; c < C0; ++c) t = fmaf(outc_w[tid * C0 + c], g[c], t);
+    f[tid] = t;
   }
   __syncthreads();
   {
@@ -732,23 +716,24 @@ __global__ void __launch_bounds__(256) k_mlp_tanh(const float* __restrict__ scra
   }
 }
 template <typename T>
-int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* w1, const float* b1, const float* w2, const float* b2,
-                 const float* w3, const float* b3, float* score, float* scratch, cudaStream_t s) {
-  KD_CHECK(C <= 64, "gap_mlp_tanh: C=%d > 64", C);
+int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* outc_w, const float* outc_b, int Cf, const float* w1,
+                 const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, float* score, float* scratch,
+                 cudaStream_t s) {
+  KD_CHECK(C <= 64 && Cf <= 64 && 256 % C == 0, "gap_mlp_tanh: C=%d Cf=%d unsupported", C, Cf);
   const int chunks = 64;
   ProfScope prof(PC_HEAD, s, 0.0, (double)nimg * HW * C * sizeof(T));
   k_gap_partial<T><<<dim3(chunks, nimg), 256, 0, s>>>(feat, HW, C, chunks, scratch);
   count_launch();
   KD_LAUNCH_CHECK();
-  k_mlp_tanh<<<nimg, 256, 0, s>>>(scratch, chunks, C, 1.f / (float)HW, w1, b1, w2, b2, w3, b3, score);
+  k_mlp_tanh<<<nimg, 256, 0, s>>>(scratch, chunks, C, 1.f / (float)HW, outc_w, outc_b, Cf, w1, b1, w2, b2, w3, b3, score);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;
 }
-template int gap_mlp_tanh<float>(const float*, int, int, int, const float*, const float*, const float*, const float*, const float*,
-                                 const float*, float*, float*, cudaStream_t);
-template int gap_mlp_tanh<bf16>(const bf16*, int, int, int, const float*, const float*, const float*, const float*, const float*,
-                                const float*, float*, float*, cudaStream_t);
+template int gap_mlp_tanh<float>(const float*, int, int, int, const float*, const float*, int, const float*, const float*, const float*,
+                                 const float*, const float*, const float*, float*, float*, cudaStream_t);
+template int gap_mlp_tanh<bf16>(const bf16*, int, int, int, const float*, const float*, int, const float*, const float*, const float*,
+                                const float*, const float*, const float*, float*, float*, cudaStream_t);
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_nhwc_to_planar(const T* __restrict__ x, long ld, float* __restrict__ out, int HW, int C, long total) {

@@ -172,11 +172,13 @@ k_mdta_gram_tc(const __grid_constant__ CUtensorMap map, int HW, int C, int heads
 int mdta_gram_tc(const bf16* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s) {
   const int ch = C / heads;
   if (ch % 16 || ch > 128 || ch < 16 || ld % 8 || (reinterpret_cast<uintptr_t>(qk) & 15) || C % 8) return -1;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_mdta_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GrCfg<1>::SMEM));
     KD_CUDA(cudaFuncSetAttribute(k_mdta_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GrCfg<2>::SMEM));
-    attr = true;
+    device_mark(once, dev);
   }
   CUtensorMap map;
   // {channel within a head, head slot (q heads then k heads), pixel, image}: the 64-channel box of a 48-channel head is clipped at

@@ -22,8 +22,8 @@ template <typename T> int teacher_pack(const kdlae_teacher_cfg& cfg, const float
 template <typename T> size_t teacher_packed_bytes(const kdlae_teacher_cfg& cfg);
 template <typename T> size_t teacher_workspace_bytes(const kdlae_teacher_cfg& cfg, int mb, int H, int W);
 template <typename T> int teacher_forward(const kdlae_teacher_cfg& cfg, const void* packed, const float* img, const float* rate,
-                                          float* hq, float* sr, int B, int H, int W, int micro_batch, void* ws, size_t ws_bytes,
-                                          cudaStream_t s);
+                                          int rate_per_image, float* hq, float* sr, int B, int H, int W, int micro_batch, void* ws,
+                                          size_t ws_bytes, cudaStream_t s);
 int teacher_num_tensors(const kdlae_teacher_cfg& cfg);
 
 template <typename T> int student_pack(const kdlae_student_cfg& cfg, const float* const* tensors, int n_tensors, void* packed,

@@ -35,21 +35,14 @@ template <typename T> int ln_stats(const T* x, long ld, int C, long rows, float*
 
 // depthwise 3x3 (pad 1) NHWC; w packed [9][C] (fp32).  gate=0: out[...,C]; gate=1: C = 2*hp,
 // out[..., j] = gelu(dw(x)[j]) * dw(x)[hp + j], j < hp
-// wtc (bf16 path only, optional): diagonal weight blocks from pack_dw_tc -> tensor-core kernel (dwconv_tc.cu)
 template <typename T> int dwconv3x3(const T* x, long ldx, T* out, long ldo, const float* w9c, const float* bias,
-                                    int nimg, int H, int W, int C, int gate, cudaStream_t s, const void* wtc = nullptr);
-size_t dwconv_tc_weight_bytes(int C, int gate);
-int pack_dw_tc(const float* w9c, int C, int gate, void* dst, cudaStream_t s);
-// fused LN-folded 1x1 conv -> depthwise 3x3 (-> GELU gate), bf16 tcgen05 (pwdw_tc.cu)
-bool pwdw_tc_eligible(int C, int Nt, int gate);
-// same fusion with the depthwise conv on the CUDA cores (packed FFMA2, pwdw_f2.cu); w9c: fp32 [9][Nt]
+                                    int nimg, int H, int W, int C, int gate, cudaStream_t s);
+// fused LN-folded 1x1 conv (tcgen05) -> depthwise 3x3 on the CUDA cores (packed FFMA2) (-> GELU gate); w9c: fp32 [9][Nt]
 bool pwdw_t_eligible(int C, int Nt, int gate);   // transposed schedule (pwdw_t.cu): depthwise inputs straight from TMEM
 int pwdw_t(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
            int H, int W, int C, int gate, cudaStream_t s);
 bool pwdw_f2_eligible(int C, int Nt, int gate);
 int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
-            int H, int W, int C, int gate, cudaStream_t s);
-int pwdw_tc(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const void* wtc, bf16* out, long ldo, int nimg,
             int H, int W, int C, int gate, cudaStream_t s);
 
 // MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
@@ -65,6 +58,7 @@ template <typename T> int mdta_fold(float* part /* split 0 is overwritten with t
 struct SmallConv {
   const float* in0 = nullptr; long in0_img = 0, in0_ch = 0; int cin0 = 0;   // fp32 planar (NCHW) source
   const float* in1 = nullptr; long in1_img = 0, in1_ch = 0; int cin1 = 0;   // concatenated second planar source
+  int in1_px = 1;                                                           // its pixel stride: 0 = one value per image (broadcast)
   const float* sub0 = nullptr;                                              // optional: value = in0 - sub0 (same strides)
   int nimg = 1, D = 1, H = 1, W = 1, kd = 1, dil = 1;                       // 3x3 (kd=1) or 3x3x3 (kd=3) taps
   const float* w = nullptr;    // [taps][cin][cout] fp32
@@ -95,11 +89,22 @@ int preprocess_u8(const uint8_t* src, int B, int h, int w, int c, const float* r
 int postprocess_u8(const float* pred, const uint8_t* src, int B, int h, int w, int c, int Hp, int Wp, int scale, uint8_t* out,
                    cudaStream_t s);
 
+// validation / training reductions behind the forward (metrics.cu; psnr_ssim.py:9-70, losses.py:135-194)
+size_t psnr_scratch_bytes(int B);
+int psnr_mse(const float* a, const float* b, int B, int C, int H, int W, int crop_border, int as_u8, double* out, void* scratch,
+             cudaStream_t s);
+size_t l1_sr_scratch_bytes();
+int l1_shadow_term(const float* pred, const float* tgt, long n, float w_l1, float w_sh, int accumulate, float* loss, float* grad,
+                   double* terms, void* scratch, cudaStream_t s);
+
 // pooling / resampling / misc glue
 template <typename T> int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s);
 template <typename T> int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s);
-template <typename T> int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* w1, const float* b1, const float* w2,
-                                       const float* b2, const float* w3, const float* b3, float* score, float* scratch, cudaStream_t s);
+// score = tanh(MLP(outc(mean_pixels(feat)))): feat [nimg*HW][C] (C <= 64); outc_w fp32 [Cf][C] + outc_b [Cf] map the channel means
+// to the Cf regressor inputs (GAP commuted through the 1x1 outc conv, ASDQE_model.py:72,168); w1 [256][Cf] ...
+template <typename T> int gap_mlp_tanh(const T* feat, int nimg, int HW, int C, const float* outc_w, const float* outc_b, int Cf,
+                                       const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                                       const float* b3, float* score, float* scratch, cudaStream_t s);
 template <typename T> int nhwc_to_planar(const T* x, long ld, float* out, int nimg, int HW, int C, cudaStream_t s);
 
 // weight packing (once per load_state_dict)

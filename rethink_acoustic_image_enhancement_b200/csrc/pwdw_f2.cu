@@ -356,8 +356,6 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   }
 }
 
-int g_pf_sms = 0;
-
 }  // namespace
 
 bool pwdw_f2_eligible(int C, int Nt, int gate) {
@@ -382,16 +380,15 @@ int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   p.rstd = rstd; p.w9c = w9c; p.out = out; p.ldo = ldo;
   const int NH = gate ? 2 : 1;
   const uint32_t smem = 1024 + p.kc * NH * 8192 + p.kc * PF_XCHUNK + 2 * NH * PF_XCHUNK + 1024;
-  static bool attr = false;
-  if (!attr) {
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_pf_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_pf_sms = sm_limit(g_pf_sms);
+  static DeviceOnce once;
+  bool first; int dev, g_pf_sms;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_f2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_f2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    device_mark(once, dev);
   }
+  KD_TRY(device_sms(&g_pf_sms));
   KD_CHECK(smem <= 232448, "pwdw_f2: shared memory budget exceeded (%u)", smem);
   CUtensorMap map_x, map_w1;
   {

@@ -395,8 +395,6 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   }
 }
 
-int g_pt_sms = 0;
-
 template <int GATE>
 int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg, int H,
               int W, int C, cudaStream_t s) {
@@ -412,11 +410,14 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   const int NH = GATE ? 2 : 1;
   const uint32_t smem = 1024 + p.kc * NH * PT_MB * 128 + p.kc * Cfg::XCHUNK + 2 * Cfg::STAGE + 4 * Cfg::NPX * 4 + 128;
   KD_CHECK(smem <= 232448, "pwdw_t: shared memory budget exceeded (%u)", smem);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  bool first; int dev, g_pt_sms;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
     KD_CUDA(cudaFuncSetAttribute(k_pwdw_t<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    device_mark(once, dev);
   }
+  KD_TRY(device_sms(&g_pt_sms));
   CUtensorMap map_x, map_w1, map_out, map_out_last;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
@@ -461,12 +462,6 @@ int pwdw_t(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, c
   KD_CHECK(!(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && !(reinterpret_cast<uintptr_t>(w1) & 15) &&
                ldx % 8 == 0 && ldo % 8 == 0,
            "pwdw_t: misaligned operands");
-  if (g_pt_sms == 0) {
-    int dev = 0;
-    KD_CUDA(cudaGetDevice(&dev));
-    KD_CUDA(cudaDeviceGetAttribute(&g_pt_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_pt_sms = sm_limit(g_pt_sms);
-  }
   return gate ? launch_pt<1>(x, ldx, rstd, w1, Nt, w9c, out, ldo, nimg, H, W, C, s)
               : launch_pt<0>(x, ldx, rstd, w1, Nt, w9c, out, ldo, nimg, H, W, C, s);
 }

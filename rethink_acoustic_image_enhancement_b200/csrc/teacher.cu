@@ -19,7 +19,6 @@ struct BlockW {
   int C, heads, h, hp;
   T* wqkv; float* qkv_s1; float* qkv_s2;   // [3C][C] (+ WithBias column vectors)
   float* wdw_qkv;                          // [9][3C]
-  uint8_t* wdw_qkv_tc; uint8_t* wdw_ffn_tc; // bf16 path: diagonal weight blocks for the tensor-core depthwise kernel
   float* wproj;                            // [C][C] fp32 (consumed by mdta_fold)
   float* temp;                             // [heads]
   T* win; float* in_s1; float* in_s2;      // [2hp][C]
@@ -45,15 +44,12 @@ void layout_block(Bump& b, BlockW<T>& w, int C, int heads, int hidden, bool lnb)
   w.qkv_s1 = lnb ? b.take<float>(3 * C) : nullptr;
   w.qkv_s2 = lnb ? b.take<float>(3 * C) : nullptr;
   w.wdw_qkv = b.take<float>((size_t)9 * 3 * C);
-  const bool tc = std::is_same<T, bf16>::value;
-  w.wdw_qkv_tc = tc ? b.take<uint8_t>(dwconv_tc_weight_bytes(3 * C, 0)) : nullptr;
   w.wproj = b.take<float>((size_t)C * C);
   w.temp = b.take<float>(heads);
   w.win = b.take<T>((size_t)2 * w.hp * C);
   w.in_s1 = lnb ? b.take<float>(2 * w.hp) : nullptr;
   w.in_s2 = lnb ? b.take<float>(2 * w.hp) : nullptr;
   w.wdw_ffn = b.take<float>((size_t)9 * 2 * w.hp);
-  w.wdw_ffn_tc = tc ? b.take<uint8_t>(dwconv_tc_weight_bytes(2 * w.hp, 1)) : nullptr;
   w.wout = b.take<T>((size_t)C * w.hp);
 }
 
@@ -120,7 +116,6 @@ int pack_block(const BlockW<T>& w, Cursor& cur, bool lnb, cudaStream_t s) {
   KD_TRY(pack_weights<T>(p, s));
   if (lnb) KD_TRY(pack_ln_cols<T>(p, ln1b, w.qkv_s1, w.qkv_s2, s));
   KD_TRY(pack_dw(qkv_dw, 3 * C, 0, 0, w.wdw_qkv, 3 * C, s));
-  if (w.wdw_qkv_tc) KD_TRY(pack_dw_tc(w.wdw_qkv, 3 * C, 0, w.wdw_qkv_tc, s));
   KD_TRY(copy_f32(proj, w.wproj, (long)C * C, s));
   KD_TRY(copy_f32(temp, w.temp, w.heads, s));
   // project_in: the two chunk(2) halves of h rows are each padded to hp (127 -> 128 ...) so both start 8-aligned
@@ -130,7 +125,6 @@ int pack_block(const BlockW<T>& w, Cursor& cur, bool lnb, cudaStream_t s) {
   KD_TRY(pack_weights<T>(p, s));
   if (lnb) KD_TRY(pack_ln_cols<T>(p, ln2b, w.in_s1, w.in_s2, s));
   KD_TRY(pack_dw(dw, 2 * w.h, w.h, w.hp, w.wdw_ffn, 2 * w.hp, s));
-  if (w.wdw_ffn_tc) KD_TRY(pack_dw_tc(w.wdw_ffn, 2 * w.hp, 1, w.wdw_ffn_tc, s));
   p = PackOp();
   p.src = pout; p.n_src = C; p.c_src = w.h; p.taps = 1; p.mode = PACK_HALVES; p.halves_on_k = 1; p.h = w.h; p.hp = w.hp;
   p.dst = w.wout; p.n_dst = C; p.c_dst = w.hp;
@@ -168,8 +162,6 @@ struct Scratch {
 // x: residual stream (in place, row stride ldx); the block's result goes to xout (row stride ldo).
 // KDLAE_FUSE_PWDW (read per forward) picks the schedule of the two "1x1 conv -> depthwise 3x3" pairs of a block:
 //   0  unfused (conv_gemm + dwconv3x3);
-//   1  both pairs through the all-tensor-core fused kernel pwdw_tc.cu, 2 only the qkv pair (bit-identical to each other;
-//      no faster than unfused: bound by the tensor core's shared-memory operand reads of the 9-tap depthwise MMAs);
 //   3  both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
 //      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn;
 //   6  both pairs through pwdw_t.cu (transposed GEMM, depthwise inputs read from TMEM in fp32), 7 (default) qkv via pwdw_t +
@@ -200,8 +192,6 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
   const int fmode = fuse_pwdw_mode();
   const bool f2ok = std::is_same<T, bf16>::value && !lnb && pwdw_f2_eligible(C, 3 * C, 0) && pwdw_f2_eligible(C, 2 * w.hp, 1);
-  const bool fuse = (fmode == 1 || fmode == 2) && std::is_same<T, bf16>::value && !lnb && w.wdw_qkv_tc != nullptr && w.wdw_ffn_tc != nullptr &&
-                    pwdw_tc_eligible(C, 3 * C, 0) && pwdw_tc_eligible(C, 2 * w.hp, 1);
   ConvOp g;
   if (f2ok && fuse_t_qkv(fmode)) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
@@ -209,16 +199,13 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   } else if (f2ok && fuse_f2_qkv(fmode)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
                    reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
-  } else if (fuse) {
-    KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv_tc,
-                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
   } else {
     g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
     g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
     g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.qkv_s1; g.epi.col_bias = w.qkv_s2;
     g.epi.out = sc.bufA; g.epi.out_ld = 3 * C; g.epi.N = 3 * C; g.epi.H = H; g.epi.W = W;
     KD_TRY(conv_gemm<T>(g, s));
-    KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s, w.wdw_qkv_tc));
+    KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s));
   }
   const int splits = mdta_gram_splits(HW, nimg * w.heads);
   KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
@@ -237,9 +224,6 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   } else if (f2ok && fuse_f2_ffn(fmode)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                    reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
-  } else if (fuse && fmode == 1) {
-    KD_TRY(pwdw_tc(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn_tc,
-                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else {
     g = ConvOp();
     g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
@@ -247,7 +231,7 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
     g.epi.row_scale = sc.rstd; g.epi.row_mu = lnb ? sc.mu : nullptr; g.epi.col_s1 = w.in_s1; g.epi.col_bias = w.in_s2;
     g.epi.out = sc.bufA; g.epi.out_ld = 2 * w.hp; g.epi.N = 2 * w.hp; g.epi.H = H; g.epi.W = W;
     KD_TRY(conv_gemm<T>(g, s));
-    KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s, w.wdw_ffn_tc));
+    KD_TRY(dwconv3x3<T>(sc.bufA, 2 * w.hp, sc.bufB, w.hp, w.wdw_ffn, nullptr, nimg, H, W, 2 * w.hp, 1, s));
   }
   g = ConvOp();
   g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
@@ -346,6 +330,9 @@ WsLayout ws_layout(const kdlae_teacher_cfg& c, int mb, int H, int W) {
   upd(P1, d, hp1); upd(P1 / 4, 2 * d, hp2); upd(P1 / 16, 4 * d, hp3); upd(P1 / 64, 8 * d, hp4);
   upd(P1, 2 * d, hp2);
   if (sr) upd(P1 * 4, d, hp1);
+  // conv_to_planar borrows bufA for the nine per-tap fp32 partial planes of the output convs (9 * oc floats per pixel, at
+  // 2H x 2W for the SR head): a small-dim / many-output-channel config needs more than the qkv / project_in sizing above
+  a = std::max(a, ((sr ? 4 : 1) * P1 * 9 * (size_t)c.out_channels * sizeof(float) + sizeof(T) - 1) / sizeof(T));
   L.bufA = off(a, sizeof(T));
   L.bufB = off(bb, sizeof(T));
   L.o1 = off(P1 * c.out_channels, sizeof(float));
@@ -445,8 +432,8 @@ size_t teacher_workspace_bytes(const kdlae_teacher_cfg& cfg, int mb, int H, int 
 }
 
 template <typename T>
-int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float* img, const float* rate, float* hq, float* sr,
-                    int B, int H, int W, int micro_batch, void* ws, size_t ws_bytes, cudaStream_t s) {
+int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float* img, const float* rate, int rate_per_image,
+                    float* hq, float* sr, int B, int H, int W, int micro_batch, void* ws, size_t ws_bytes, cudaStream_t s) {
   KD_CHECK(H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
            "KDLAE_teacher: H and W must be multiples of 8 (got %dx%d) - pixel_unshuffle expects divisible sizes", H, W);
   KD_CHECK(B >= 1 && micro_batch >= 1, "KDLAE_teacher: bad batch %d / micro_batch %d", B, micro_batch);
@@ -478,7 +465,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
   for (int b0 = 0; b0 < B; b0 += micro_batch) {
     const int n = std::min(micro_batch, B - b0);
     const float* img_b = img + (long)b0 * ic * HW;
-    const float* rate_b = rate ? rate + (long)b0 * HW : nullptr;
+    const float* rate_b = rate ? rate + (rate_per_image ? (long)b0 : (long)b0 * HW) : nullptr;
     float* hq_b = hq + (long)b0 * oc * HW;
     float* sr_b = sr ? sr + (long)b0 * oc * HW * 4 : nullptr;
 
@@ -526,7 +513,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, w.output, w.output_tc, oc, n, H, W, nullptr, 0, 0, o1, oc * HW, HW, reinterpret_cast<float*>(sc.bufA), s));
       fi = SmallConv();
       fi.in0 = o1; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc;
-      fi.in1 = rate_b; fi.in1_img = HW; fi.in1_ch = HW; fi.cin1 = 1;
+      fi.in1 = rate_b; fi.in1_img = rate_per_image ? 1 : HW; fi.in1_ch = 0; fi.cin1 = 1; fi.in1_px = rate_per_image ? 0 : 1;
       fi.nimg = n; fi.H = H; fi.W = W; fi.dil = 2; fi.w = w.output_param; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
       KD_TRY(conv_few_in<T>(fi, s));
       KD_TRY(run_blocks<T>(w.refine_out, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
@@ -553,7 +540,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
   template size_t teacher_packed_bytes<T>(const kdlae_teacher_cfg&);                                                         \
   template int teacher_pack<T>(const kdlae_teacher_cfg&, const float* const*, int, void*, size_t, cudaStream_t);              \
   template size_t teacher_workspace_bytes<T>(const kdlae_teacher_cfg&, int, int, int);                                       \
-  template int teacher_forward<T>(const kdlae_teacher_cfg&, const void*, const float*, const float*, float*, float*, int,    \
+  template int teacher_forward<T>(const kdlae_teacher_cfg&, const void*, const float*, const float*, int, float*, float*, int, \
                                   int, int, int, void*, size_t, cudaStream_t);
 INST(float)
 INST(bf16)

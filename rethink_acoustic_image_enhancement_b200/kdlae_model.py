@@ -131,11 +131,19 @@ class _FusedModule(nn.Module):
         self._engine.invalidate()
         return super()._apply(fn, *args, **kwargs)
 
-    def _no_autograd(self, name: str) -> None:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+    def _no_autograd(self, name: str, *inputs: Optional[torch.Tensor]) -> None:
+        """The fused forward records no autograd graph.  Refuse loudly wherever the reference would have propagated a
+        gradient: training mode with trainable parameters, or (in any mode, e.g. a frozen teacher used as a loss term on a
+        student's output) an input that requires grad - silently returning a constant would zero that gradient."""
+        if not torch.is_grad_enabled():
+            return
+        wants_param_grad = self.training and any(p.requires_grad for p in self.parameters())
+        wants_input_grad = any(t is not None and t.requires_grad for t in inputs)
+        if wants_param_grad or wants_input_grad:
             raise NotImplementedError(
                 f"{name}: the fused CUDA forward has no backward yet (training step = SURVEY.md section 8f N1); "
-                "call it under torch.no_grad() / model.eval() for inference and validation")
+                "call it under torch.no_grad() (and model.eval()) for inference and validation, and detach inputs that "
+                "require grad")
 
 
 # ------------------------------------------------------------------------------------------
@@ -212,7 +220,7 @@ class KDLAE_teacher(_FusedModule):
         denoise_rate = input["denoise_rate"]
         eng = self._engine
         eng.require_cuda(inp_img, "KDLAE_teacher")
-        self._no_autograd("KDLAE_teacher")
+        self._no_autograd("KDLAE_teacher", inp_img, denoise_rate)
         if inp_img.dim() != 4 or inp_img.shape[1] != self._io[0]:
             raise RuntimeError(f"KDLAE_teacher: expected img [B,{self._io[0]},H,W], got {tuple(inp_img.shape)}")
         B, _, H, W = inp_img.shape
@@ -222,10 +230,18 @@ class KDLAE_teacher(_FusedModule):
         prec = _lib.PRECISIONS[self.precision]
         with torch.cuda.device(dev):
             img = inp_img.detach().to(torch.float32).contiguous()
-            rate = None
+            rate, per_image = None, 0
             if cfg.params_cat:
-                rate = denoise_rate.detach().to(device=dev, dtype=torch.float32).expand(B, 1, H, W).contiguous()
-            tensors = [v for v in self.state_dict(keep_vars=True).values()]
+                dr = denoise_rate.detach()
+                if dr.dim() != 4 or dr.shape[1] != 1:
+                    raise RuntimeError(f"KDLAE_teacher: expected denoise_rate [B,1,H,W] (or [B,1,1,1]), got {tuple(dr.shape)}")
+                # one value per image ([B,1,1,1], or a map expanded from it): hand the kernel B floats, never the H x W map
+                if dr.shape[2:] == (1, 1) or (dr.stride(2) == 0 and dr.stride(3) == 0):
+                    rate = dr[:, 0, 0, 0].to(device=dev, dtype=torch.float32).expand(B).contiguous()
+                    per_image = 1
+                else:
+                    rate = dr.to(device=dev, dtype=torch.float32).expand(B, 1, H, W).contiguous()
+            tensors = eng.tensors(self)
             nbytes = lib.kdlae_teacher_packed_bytes(cfg, prec)
 
             def pack(arr, n, blob):
@@ -240,9 +256,12 @@ class KDLAE_teacher(_FusedModule):
             ws = eng.workspace(dev, ws_bytes)
             hq = torch.empty((B, self._io[1], H, W), dtype=torch.float32, device=dev)
             sr = torch.empty((B, self._io[1], 2 * H, 2 * W), dtype=torch.float32, device=dev) if cfg.sr_head else None
-            _lib.check(lib.kdlae_teacher_forward(cfg, packed.data_ptr(), img.data_ptr(), _ptr(rate), hq.data_ptr(), _ptr(sr),
-                                                 B, H, W, mb, ws.data_ptr(), ws.numel(), prec, eng.stream()),
+            _lib.check(lib.kdlae_teacher_forward(cfg, packed.data_ptr(), img.data_ptr(), _ptr(rate), per_image, hq.data_ptr(),
+                                                 _ptr(sr), B, H, W, mb, ws.data_ptr(), ws.numel(), prec, eng.stream()),
                        "kdlae_teacher_forward")
+            if inp_img.dtype != torch.float32 and inp_img.is_floating_point():   # the reference returns the input's dtype
+                hq = hq.to(inp_img.dtype)
+                sr = sr.to(inp_img.dtype) if sr is not None else None
         return {"hq": hq, "sr": sr}
 
 
@@ -295,7 +314,7 @@ class KDLAE_student(_FusedModule):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         eng = self._engine
         eng.require_cuda(x, "KDLAE_student")
-        self._no_autograd("KDLAE_student")
+        self._no_autograd("KDLAE_student", x)
         if x.dim() != 4:
             raise RuntimeError(f"KDLAE_student: expected x [B,F,H,W], got {tuple(x.shape)}")
         B, F, H, W = x.shape
@@ -305,7 +324,7 @@ class KDLAE_student(_FusedModule):
         prec = _lib.PRECISIONS[self.precision]
         with torch.cuda.device(dev):
             xin = x.detach().to(torch.float32).contiguous()
-            tensors = [v for v in self.state_dict(keep_vars=True).values()]
+            tensors = eng.tensors(self)
             nbytes = lib.kdlae_student_packed_bytes(cfg, prec)
 
             def pack(arr, n, blob):
@@ -319,6 +338,8 @@ class KDLAE_student(_FusedModule):
             y = torch.empty_like(xin)
             _lib.check(lib.kdlae_student_forward(cfg, packed.data_ptr(), xin.data_ptr(), y.data_ptr(), B, F, H, W, mb,
                                                  ws.data_ptr(), ws.numel(), prec, eng.stream()), "kdlae_student_forward")
+            if x.dtype != torch.float32 and x.is_floating_point():
+                y = y.to(x.dtype)
         return y
 
 

@@ -24,8 +24,9 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def preprocess_u8(images: torch.Tensor, denoise_rate: Union[float, torch.Tensor], multiple: int = 8):
-    """images [B,h,w,c] uint8 (CUDA, HWC) -> (img [B,c,H,W] fp32, rate_map [B,1,H,W] fp32)."""
+def preprocess_u8(images: torch.Tensor, denoise_rate: Union[float, torch.Tensor], multiple: int = 8, rate_map: bool = False):
+    """images [B,h,w,c] uint8 (CUDA, HWC) -> (img [B,c,H,W] fp32, rate): rate is the [B,1,1,1] per-image value the drop-in
+    teacher broadcasts inside its kernel, or with rate_map=True the materialised [B,1,H,W] map the reference module needs."""
     if images.dtype != torch.uint8 or images.dim() != 4 or not images.is_cuda:
         raise RuntimeError("preprocess_u8: expected a CUDA uint8 tensor [B,h,w,c] (there is no CPU fallback)")
     images = images.contiguous()
@@ -40,10 +41,10 @@ def preprocess_u8(images: torch.Tensor, denoise_rate: Union[float, torch.Tensor]
     rates = rates.contiguous()
     with torch.cuda.device(dev):
         img = torch.empty((B, c, H, W), dtype=torch.float32, device=dev)
-        rate_map = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-        _lib.check(_lib.load().kdlae_preprocess_u8(images.data_ptr(), B, h, w, c, rates.data_ptr(), img.data_ptr(), rate_map.data_ptr(),
-                                                   H, W, _stream()), "kdlae_preprocess_u8")
-    return img, rate_map
+        rmap = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if rate_map else None
+        _lib.check(_lib.load().kdlae_preprocess_u8(images.data_ptr(), B, h, w, c, rates.data_ptr(), img.data_ptr(),
+                                                   None if rmap is None else rmap.data_ptr(), H, W, _stream()), "kdlae_preprocess_u8")
+    return img, (rmap if rate_map else rates.view(B, 1, 1, 1))
 
 
 def postprocess_u8(pred: torch.Tensor, images: torch.Tensor, scale: int = 1) -> torch.Tensor:
@@ -64,9 +65,9 @@ def postprocess_u8(pred: torch.Tensor, images: torch.Tensor, scale: int = 1) -> 
 def teacher_infer_uint8(model, images: torch.Tensor, denoise_rate: Union[float, torch.Tensor] = 1.0,
                         multiple: int = 8) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """uint8 in, uint8 out: (hq [B,h,w,c], sr [B,2h,2w,c] or None) exactly as KDLAE_T.ipynb cell 5 produces them."""
-    img, rate_map = preprocess_u8(images, denoise_rate, multiple)
+    img, rate = preprocess_u8(images, denoise_rate, multiple)
     with torch.no_grad():
-        pred = model({"img": img, "denoise_rate": rate_map})
+        pred = model({"img": img, "denoise_rate": rate})
     hq = postprocess_u8(pred["hq"], images, 1)
     sr = postprocess_u8(pred["sr"], images, 2) if pred.get("sr") is not None else None
     return hq, sr

@@ -2,8 +2,10 @@
 fixtures frozen from the reference and against the CPU oracle on the same seeded inputs.
 
 Bars (BASELINE.json north_star): fp32 path <= 1e-4 max-abs on outputs in [0,1]; bf16 path >= 50 dB PSNR;
-ASDQE scores within 1e-3 (fp32 path; bf16 path reported and held to 1e-2).
+ASDQE scores within 1e-3 (both paths).
 """
+import os
+
 import pytest
 import torch
 
@@ -55,6 +57,8 @@ def test_teacher_matches_reference_fixture(name, precision, manifest):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_teacher_128_against_oracle_and_batch_invariance(precision):
+    """A mixed-rate batch: EVERY image is compared with the oracle, and results do not depend on batch position /
+    micro-batch size (bit-exact)."""
     kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
     sd = synth.teacher_state_dict(seed=7, temp_scale=5.0, **kw)
     m = pk.KDLAE_teacher(**kw)
@@ -63,29 +67,142 @@ def test_teacher_128_against_oracle_and_batch_invariance(precision):
     img = synth.seeded_tensor("t128.img", (3, 1, 128, 128), 7, "sonar")
     rate = torch.tensor([0.6, 0.1, 0.9]).view(3, 1, 1, 1).expand(3, 1, 128, 128).contiguous()
     with torch.no_grad():
-        hq_ref, sr_ref = oracle.teacher_forward(sd, img[:1], rate[:1])
+        hq_ref, sr_ref = oracle.teacher_forward(sd, img, rate)
         m.micro_batch = 2  # 3 images as micro-batches of 2 + 1
-        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})                       # materialised [B,1,H,W] map
+        bc = m({"img": img.to(DEV), "denoise_rate": rate[:, :, :1, :1].contiguous().to(DEV)})   # [B,1,1,1]: broadcast in the kernel
         m.micro_batch = 1
         one = m({"img": img[2:3].to(DEV), "denoise_rate": rate[2:3].to(DEV)})
     torch.cuda.synchronize()
     hq, sr = out["hq"].cpu(), out["sr"].cpu()
-    e1, e2 = (hq[:1] - hq_ref).abs().max().item(), (sr[:1] - sr_ref).abs().max().item()
-    p1, p2 = synth.psnr(hq[:1], hq_ref), synth.psnr(sr[:1], sr_ref)
-    print(f"teacher128 {precision}: hq max|d|={e1:.3e} psnr={p1:.2f}; sr max|d|={e2:.3e} psnr={p2:.2f}")
-    if precision == "fp32":
-        assert e1 <= FP32_TOL and e2 <= FP32_TOL
-    else:
-        assert p1 >= BF16_PSNR and p2 >= BF16_PSNR
+    for b in range(3):
+        e1, e2 = (hq[b] - hq_ref[b]).abs().max().item(), (sr[b] - sr_ref[b]).abs().max().item()
+        p1, p2 = synth.psnr(hq[b], hq_ref[b]), synth.psnr(sr[b], sr_ref[b])
+        print(f"teacher128 {precision} image {b}: hq max|d|={e1:.3e} psnr={p1:.2f}; sr max|d|={e2:.3e} psnr={p2:.2f}")
+        if precision == "fp32":
+            assert e1 <= FP32_TOL and e2 <= FP32_TOL
+        else:
+            assert p1 >= BF16_PSNR and p2 >= BF16_PSNR
     # images are independent: result must not depend on batch position or micro-batch size (bit-exact)
     assert torch.equal(out["hq"][2:3], one["hq"]) and torch.equal(out["sr"][2:3], one["sr"])
+    # a per-image rate handed over as [B,1,1,1] gives the same bits as the expanded map
+    assert torch.equal(out["hq"], bc["hq"]) and torch.equal(out["sr"], bc["sr"])
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5", "6", "7", "8"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_spatially_varying_rate_map(precision):
+    """denoise_rate is a [B,1,H,W] map in the reference (KDLAE_model.py:316): a map that varies per pixel (ramp + noise)
+    must go through the dilated output_param conv exactly like the oracle's cat([out, rate])."""
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+    sd = synth.teacher_state_dict(seed=9, temp_scale=4.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision(precision)
+    img = synth.seeded_tensor("tvar.img", (2, 1, 64, 96), 9, "sonar")
+    ramp = torch.linspace(0, 1, 96).view(1, 1, 1, 96) * torch.linspace(1, 0.2, 64).view(1, 1, 64, 1)
+    rate = (ramp + 0.3 * synth.seeded_tensor("tvar.rate", (2, 1, 64, 96), 9)).clamp(0, 1)
+    with torch.no_grad():
+        hq_ref, sr_ref = oracle.teacher_forward(sd, img, rate)
+        hq_const, _ = oracle.teacher_forward(sd, img, torch.full_like(rate, float(rate.mean())))
+        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+    assert (hq_ref - hq_const).abs().max().item() > 1e-3          # the map really matters for the result
+    for got, ref, key in ((out["hq"].cpu(), hq_ref, "hq"), (out["sr"].cpu(), sr_ref, "sr")):
+        err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+        print(f"teacher varying-rate {precision} {key}: max|d|={err:.3e} psnr={p:.2f}")
+        assert (err <= FP32_TOL) if precision == "fp32" else (p >= BF16_PSNR)
+
+
+# ---- the benchmark shape (BASELINE configs[0]/[1]): 1x1x512x512, BiasFree, static='train', sonar-like input, temperatures x4 ----
+_BENCH_KW = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+
+
+@pytest.fixture(scope="module")
+def bench_shape_oracle():
+    """One live oracle forward at 512x512 on the box's host cores (~13 s on 16 cores), shared by both precisions."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.teacher_state_dict(seed=0, temp_scale=4.0, **_BENCH_KW)
+    img = synth.seeded_tensor("bench512.img", (1, 1, 512, 512), 0, "sonar")
+    rate = torch.full((1, 1, 512, 512), 0.6)
+    with torch.no_grad():
+        hq_ref, sr_ref = oracle.teacher_forward(sd, img, rate)
+    return sd, img, rate, hq_ref, sr_ref
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_benchmark_shape_512_against_oracle(precision, bench_shape_oracle):
+    """Everything that only happens at the benchmark size: Gram over K = 262 144 (1 048 576 in `enhance`) with the split cap,
+    multi-wave persistent tiles, 24-bit tile decode, the SR head at 1024^2, conv_to_planar's partial planes."""
+    sd, img, rate, hq_ref, sr_ref = bench_shape_oracle
+    m = pk.KDLAE_teacher(**_BENCH_KW)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision(precision)
+    with torch.no_grad():
+        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+        # the same image inside a micro-batch of 4 (the bench runs micro-batches of 16): bit-identical
+        four = m({"img": img.expand(4, 1, 512, 512).contiguous().to(DEV), "denoise_rate": torch.full((4, 1, 1, 1), 0.6, device=DEV)})
+    torch.cuda.synchronize()
+    for key, ref in (("hq", hq_ref), ("sr", sr_ref)):
+        got = out[key].cpu()
+        assert got.shape == ref.shape and torch.isfinite(got).all()
+        err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+        print(f"teacher 512x512 {precision} {key}: max|d|={err:.3e} psnr={p:.2f} dB")
+        if precision == "fp32":
+            assert err <= FP32_TOL, f"{key}: {err}"
+        else:
+            assert p >= BF16_PSNR, f"{key}: {p} dB"
+        assert torch.equal(four[key][3:4], out[key]), f"{key}: batch of 4 differs from the single image"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_256_withbias_3ch_against_oracle(precision):
+    """The constructor-default LayerNorm (WithBias) with the pretrained 3-channel layout at 256x256 (unfused-pair schedule)."""
+    kw = dict(inp_channels=3, out_channels=3, LayerNorm_type="WithBias", static="train")
+    sd = synth.teacher_state_dict(seed=5, temp_scale=4.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision(precision)
+    img = synth.seeded_tensor("wb256.img", (1, 3, 256, 256), 5, "sonar")
+    rate = torch.full((1, 1, 256, 256), 0.35)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        hq_ref, sr_ref = oracle.teacher_forward(sd, img, rate)
+        out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+    for got, ref, key in ((out["hq"].cpu(), hq_ref, "hq"), (out["sr"].cpu(), sr_ref, "sr")):
+        err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+        print(f"teacher WithBias 3ch 256x256 {precision} {key}: max|d|={err:.3e} psnr={p:.2f}")
+        assert (err <= FP32_TOL) if precision == "fp32" else (p >= BF16_PSNR)
+
+
+def test_two_devices_in_one_process():
+    """Per-device kernel set-up (cudaFuncSetAttribute / SM count): a forward on cuda:0, then the same module moved to cuda:1."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+    m = _teacher(kw, 3, 2.0, "bf16")
+    x = synth.seeded_tensor("two.img", (1, 1, 64, 64), 3)
+    r = torch.full((1, 1, 1, 1), 0.5)
+    with torch.no_grad():
+        a = m({"img": x.to("cuda:0"), "denoise_rate": r.to("cuda:0")})
+        m = m.to("cuda:1")
+        b = m({"img": x.to("cuda:1"), "denoise_rate": r.to("cuda:1")})
+    assert b["hq"].device.index == 1
+    assert torch.equal(a["hq"].cpu(), b["hq"].cpu()) and torch.equal(a["sr"].cpu(), b["sr"].cpu())
+
+
+def test_grad_requiring_input_is_refused_in_eval_mode():
+    m = _teacher(dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no"), 0, 1.0, "bf16")
+    x = torch.rand(1, 1, 16, 16, device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="no backward"):
+        m({"img": x, "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)})
+    out = m({"img": x.detach().half(), "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)})   # eval + no grad needed: fine
+    assert out["hq"].dtype == torch.float16 and out["sr"] is None                                    # output follows the input dtype
+
+
+@pytest.mark.parametrize("mode", ["3", "4", "5", "6", "7", "8", "9"])
 def test_teacher_fused_conv1x1_dwconv_schedule_matches_reference(mode, manifest, monkeypatch):
-    """KDLAE_FUSE_PWDW: every schedule of the 1x1 -> depthwise pairs (unfused 0, all-tensor-core fused 1/2, tcgen05 + FFMA2
-    fused 3/4/5, transposed-GEMM fused 6/7/8 with 7 the default) must hold the parity gate; 3/4/5 are bit-identical to the
-    unfused schedule (6/7/8 keep the intermediate in fp32 instead of rounding it to bf16)."""
+    """KDLAE_FUSE_PWDW: every schedule of the 1x1 -> depthwise pairs (unfused 0, tcgen05 + FFMA2 fused 3/4/5, transposed-GEMM
+    fused 6/7/8/9 with 7 the default) must hold the parity gate; 3/4/5 are bit-identical to the unfused schedule (6-9 keep
+    the intermediate in fp32 instead of rounding it to bf16)."""
     monkeypatch.setenv("KDLAE_FUSE_PWDW", mode)
     name = "teacher_c1_biasfree_64"
     case, g = manifest[name], load_golden(name)
@@ -178,7 +295,7 @@ def test_asdqe_matches_reference_fixture(name, precision, manifest):
     if precision == "fp32":
         assert es <= 1e-3 and ef <= 1e-3 * max(1.0, g["feat"].abs().max().item())
     else:
-        assert es <= 1e-2 and rel <= 5e-2
+        assert es <= 1e-3 and rel <= 5e-2
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -225,4 +342,4 @@ def test_minimum_and_ragged_sizes_against_oracle(precision):
             got = a(lq.to(DEV), gt.to(DEV)).cpu()
         err = (got - ref).abs().max().item()
         print(f"asdqe {h}x{w} {precision}: score max|d|={err:.3e}")
-        assert err <= (1e-3 if precision == "fp32" else 1e-2)
+        assert err <= 1e-3

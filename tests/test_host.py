@@ -19,7 +19,7 @@ def test_header_symbols_are_all_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libkdlae_b200.so"
-    assert lib.kdlae_abi_version() == 1
+    assert lib.kdlae_abi_version() == 2
 
 
 def test_teacher_state_dict_layout_matches_reference_layout():
@@ -98,12 +98,12 @@ def test_size_queries_scale_and_reject_bad_shapes(lib):
     # forward argument validation happens before any CUDA call, so it is testable without a GPU
     import ctypes as C
     buf = C.create_string_buffer(64)
-    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, buf, buf, 1, 36, 64, 1, buf, 64, 1, None)
+    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, 0, buf, buf, 1, 36, 64, 1, buf, 64, 1, None)
     assert st != 0 and b"multiples of 8" in lib.kdlae_last_error()
     s = pk.KDLAE_student()
     st = lib.kdlae_student_forward(s._cfg, buf, buf, buf, 1, 5, 18, 16, 1, buf, 64, 1, None)
     assert st != 0 and b"multiples of 4" in lib.kdlae_last_error()
-    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, buf, buf, 1, 64, 64, 1, buf, 64, 7, None)
+    st = lib.kdlae_teacher_forward(m._cfg, buf, buf, buf, 0, buf, buf, 1, 64, 64, 1, buf, 64, 7, None)
     assert st != 0 and b"precision" in lib.kdlae_last_error()
 
 

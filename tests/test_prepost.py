@@ -45,8 +45,10 @@ def test_prepost_kernels_bit_exact(shape):
     rates = np.linspace(0.1, 0.9, B).astype(np.float32)
     x_ref, a_ref = op.preprocess_u8(img, rates)
     img_d = torch.from_numpy(img).to(DEV)
-    x, a = pk.preprocess_u8(img_d, torch.from_numpy(rates))
+    x, a = pk.preprocess_u8(img_d, torch.from_numpy(rates), rate_map=True)
     assert torch.equal(x.cpu(), x_ref) and torch.equal(a.cpu(), a_ref)
+    x2, r2 = pk.preprocess_u8(img_d, torch.from_numpy(rates))        # default: per-image rates, no H x W map
+    assert torch.equal(x2, x) and r2.shape == (B, 1, 1, 1) and torch.equal(r2.cpu().view(-1), torch.from_numpy(rates))
     for scale in (1, 2):
         g = torch.Generator().manual_seed(5 + scale)
         pred = torch.rand(B, c, x.shape[2] * scale, x.shape[3] * scale, generator=g) * 1.4 - 0.2
