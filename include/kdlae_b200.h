@@ -147,6 +147,13 @@ int kdlae_preprocess_u8(const unsigned char* src_hwc, int B, int h, int w, int c
 int kdlae_postprocess_u8(const float* pred_nchw, const unsigned char* src_hwc, int B, int h, int w, int c, int Hp, int Wp, int scale,
                          unsigned char* out_hwc, void* stream);
 
+/* ---- debug: stage-by-stage checksums of the KDLAE-T forward (two runs that should be bit-identical can be diffed) --------
+ * begin: start recording; every stage of kdlae_teacher_forward then appends {sum, position-weighted sum} of its output words.
+ * end:   synchronise, copy up to max_points pairs into `sums` (host, 2*max_points entries) and the newline-separated stage tags
+ *        into `tags`; returns the number of points.  Costs one small kernel per stage while enabled; off by default. */
+int kdlae_debug_trace_begin(void);
+int kdlae_debug_trace_end(unsigned long long* sums, int max_points, char* tags, int tags_bytes);
+
 /* ---- validation metric on device (Train/basicsr/metrics/psnr_ssim.py:9-70 calculate_psnr) -------------
  * img1, img2 [B,C,H,W] fp32 (device).  crop_border pixels are dropped on every edge (:57-59).  as_uint8 != 0 first converts
  * both images like tensor2img (utils/img_util.py:67-94: clamp(0,1), *255, round) - the `use_image` branch of

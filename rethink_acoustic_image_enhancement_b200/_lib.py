@@ -78,6 +78,8 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "kdlae_pwdw_t": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
+    "kdlae_debug_trace_begin": (C.c_int, []),
+    "kdlae_debug_trace_end": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int, C.c_char_p, C.c_int]),
     "kdlae_psnr_scratch_bytes": (C.c_size_t, [C.c_int]),
     "kdlae_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                              C.c_void_p]),

@@ -1,6 +1,8 @@
 // extern "C" boundary (include/kdlae_b200.h): argument checking, precision dispatch, error text.
 #include <mutex>
+#include <string>
 #include <vector>
+#include <algorithm>
 #include "models.cuh"
 
 namespace kd {
@@ -70,6 +72,35 @@ ProfScope::~ProfScope() {
   if (!active) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (slot < (int)g_recs.size()) cudaEventRecord(g_recs[slot].b, stream);
+}
+
+// ---- debug trace -------------------------------------------------------------------------
+static bool g_trace_on = false;
+static unsigned long long* g_trace_dev = nullptr;
+static std::vector<std::string> g_trace_tags;
+constexpr int TRACE_MAX = 8192;
+
+__global__ void k_trace_checksum(const uint8_t* __restrict__ p, long rows, long row_words, long ld_bytes, unsigned long long* slot) {
+  unsigned long long a = 0, b = 0;
+  const long total = rows * row_words;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / row_words, c = i - r * row_words;
+    const unsigned int w = *reinterpret_cast<const unsigned int*>(p + r * ld_bytes + c * 4);
+    a += w;
+    b += (unsigned long long)w * (unsigned long long)(i % 65521 + 1);
+  }
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(slot, a); atomicAdd(slot + 1, b); }
+}
+
+void trace_point(const char* tag, const void* ptr, long rows, long row_bytes, long ld_bytes, cudaStream_t s) {
+  if (!g_trace_on || (int)g_trace_tags.size() >= TRACE_MAX || ptr == nullptr || rows <= 0 || row_bytes < 4) return;
+  const long row_words = row_bytes / 4;
+  const long total = rows * row_words;
+  const int blocks = (int)std::min<long>(2048, (total + 255) / 256);
+  k_trace_checksum<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(ptr), rows, row_words, ld_bytes,
+                                          g_trace_dev + 2 * g_trace_tags.size());
+  g_trace_tags.emplace_back(tag);
 }
 
 }  // namespace kd
@@ -353,6 +384,29 @@ int kdlae_l1_sr_loss(const float* hq, const float* hq_gt, long n_hq, const float
                               scratch, s));
   }
   return 0;
+}
+
+int kdlae_debug_trace_begin(void) {
+  API_BEGIN();
+  if (!kd::g_trace_dev) KD_CUDA(cudaMalloc(&kd::g_trace_dev, sizeof(unsigned long long) * 2 * kd::TRACE_MAX));
+  KD_CUDA(cudaMemset(kd::g_trace_dev, 0, sizeof(unsigned long long) * 2 * kd::TRACE_MAX));
+  kd::g_trace_tags.clear();
+  kd::g_trace_on = true;
+  return 0;
+}
+
+int kdlae_debug_trace_end(unsigned long long* sums, int max_points, char* tags, int tags_bytes) {
+  API_BEGIN();
+  kd::g_trace_on = false;
+  KD_CUDA(cudaDeviceSynchronize());
+  const int n = (int)std::min<size_t>(kd::g_trace_tags.size(), (size_t)std::max(0, max_points));
+  if (n > 0 && sums) KD_CUDA(cudaMemcpy(sums, kd::g_trace_dev, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost));
+  if (tags && tags_bytes > 0) {
+    std::string all;
+    for (int i = 0; i < n; ++i) { all += kd::g_trace_tags[i]; all += '\n'; }
+    snprintf(tags, (size_t)tags_bytes, "%s", all.c_str());
+  }
+  return n;
 }
 
 }  // extern "C"

@@ -81,6 +81,10 @@ inline void device_mark(DeviceOnce& once, int dev) { once.mask.fetch_or(1ull << 
 // SM count of the current device after KDLAE_SM_LIMIT (cached per device)
 int device_sms(int* sms);
 
+// ---- debug trace (kdlae_debug_trace_begin/end): an order-independent checksum of a stage's output rows after each launch,
+// so two forwards that should be bit-identical can be compared stage by stage.  Off unless enabled through the C ABI.
+void trace_point(const char* tag, const void* ptr, long rows, long row_bytes, long ld_bytes, cudaStream_t s);
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -279,6 +279,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
     const bool last_g = (g == NG - 1);
     const int gw = (GATE && last_g) ? OW - s0 : GW;     // output columns of this group (gate: 8, 6; otherwise 10 each)
     uint32_t n = 0;
+    uint32_t nstored = 0;                         // items this warp has stored: picks its staging block (see below)
     for (int i = 0; i < ntiles; ++i) {
       int img, y0, x0;
       tile_xy(i, img, y0, x0);
@@ -307,11 +308,16 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
           for (int t = 0; t < 9; ++t) w[h][t] = splat2(ch_ok ? __ldg(p.w9c + (long)t * p.Nt + h * hp + ch) : 0.f);
         mbar_wait_relaxed(d_full(b), (n >> 1) & 1);
         tc_fence_after();
-        // this warp's staging block b was handed to TMA two items ago: wait until that store has read it
+        // The staging block alternates with the items this warp STORES (not with the item index: a warp that skips the partial
+        // channel block of every tile would otherwise reuse the same block for consecutive stores while `wait_group.read 1` still
+        // allows the previous store to be reading it - a timing-dependent corruption seen on cold first launches).  Block sb was
+        // handed to TMA two stores ago: wait until that store has read it.
+        const uint32_t sb = nstored & 1;
+        ++nstored;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         const uint32_t trow = tmem_base + b * 256 + ((uint32_t)(quarter * 32) << 16) + s0;
-        uint8_t* st = stage_gen + b * STAGE + dwp * WSTAGE + lane * 2;
+        uint8_t* st = stage_gen + sb * STAGE + dwp * WSTAGE + lane * 2;
         u64 acc[NH][3][GP];
 #pragma unroll
         for (int ir = 0; ir < PT_IH; ++ir) {
@@ -376,7 +382,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         if (lane == 0) {
           const CUtensorMap* mo = (GATE && last_g) ? &map_out_last : &map_out;
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                       ::"l"(mo), "r"(stage_base + b * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + lq * 32), "r"(x0 + s0), "r"(y0), "r"(img)
+                       ::"l"(mo), "r"(stage_base + sb * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + lq * 32), "r"(x0 + s0), "r"(y0), "r"(img)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }

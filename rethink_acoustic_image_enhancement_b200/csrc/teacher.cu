@@ -189,6 +189,8 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   const bool fused_stats = epilogue_emits_stats<T>(C);
   // ---- x = x + project_out(attn(norm1(x))) ----
   if (!(have_stats && fused_stats)) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  trace_point("blk.in", x, rows, (long)C * sizeof(T), ldx * sizeof(T), s);
+  trace_point("blk.rstd1", sc.rstd, 1, rows * 4, rows * 4, s);
   // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
   const int fmode = fuse_pwdw_mode();
   const bool f2ok = std::is_same<T, bf16>::value && !lnb && pwdw_f2_eligible(C, 3 * C, 0) && pwdw_f2_eligible(C, 2 * w.hp, 1);
@@ -208,16 +210,21 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
     KD_TRY(dwconv3x3<T>(sc.bufA, 3 * C, sc.bufB, 3 * C, w.wdw_qkv, nullptr, nimg, H, W, 3 * C, 0, s));
   }
   const int splits = mdta_gram_splits(HW, nimg * w.heads);
+  trace_point("blk.qkv_dw", sc.bufB, rows, 3L * C * sizeof(T), 3L * C * sizeof(T), s);
   KD_TRY(mdta_gram<T>(sc.bufB, 3 * C, nimg, HW, C, w.heads, splits, sc.gram, s));
+  trace_point("blk.gram", sc.gram, 1, (long)nimg * w.heads * splits * ((C / w.heads) * (C / w.heads) + 2 * (C / w.heads)) * 4, 0, s);
   KD_TRY(mdta_fold<T>(sc.gram, nimg, C, w.heads, splits, w.temp, w.wproj, sc.mb, C, (long)C * C, s));
+  trace_point("blk.mb", sc.mb, 1, (long)nimg * C * C * sizeof(T), 0, s);
   g = ConvOp();
   g.a0 = sc.bufB + 2 * C; g.c0 = C; g.ld0 = 3 * C; g.nimg = nimg; g.H = H; g.W = W;
   g.w = sc.mb; g.w_ld = C; g.w_tap_ld = C; g.groups = nimg; g.w_group_stride = (long)C * C;
   g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = x; g.epi.out_ld = ldx; g.epi.N = C; g.epi.H = H; g.epi.W = W;
   if (fused_stats) { g.epi.stat_rstd = sc.rstd; g.epi.stat_mu = lnb ? sc.mu : nullptr; }
   KD_TRY(conv_gemm<T>(g, s));
+  trace_point("blk.attn_out", x, rows, (long)C * sizeof(T), ldx * sizeof(T), s);
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
+  trace_point("blk.rstd2", sc.rstd, 1, rows * 4, rows * 4, s);
   if (f2ok && fuse_t_ffn(fmode)) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
@@ -235,10 +242,12 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   }
   g = ConvOp();
   g.a0 = sc.bufB; g.c0 = w.hp; g.ld0 = w.hp; g.nimg = nimg; g.H = H; g.W = W;
+  trace_point("blk.gated", sc.bufB, rows, (long)w.hp * sizeof(T), (long)w.hp * sizeof(T), s);
   g.w = w.wout; g.w_ld = w.hp; g.w_tap_ld = w.hp;
   g.epi.res = x; g.epi.res_ld = ldx; g.epi.out = xout; g.epi.out_ld = ldo; g.epi.N = C; g.epi.H = H; g.epi.W = W;
   if (fused_stats && emit_next_stats) { g.epi.stat_rstd = sc.rstd; g.epi.stat_mu = lnb ? sc.mu : nullptr; }
   KD_TRY(conv_gemm<T>(g, s));
+  trace_point("blk.out", xout, rows, (long)C * sizeof(T), ldo * sizeof(T), s);
   return 0;
 }
 
@@ -474,17 +483,22 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
     fi.in0 = img_b; fi.in0_img = ic * HW; fi.in0_ch = HW; fi.cin0 = ic; fi.nimg = n; fi.H = H; fi.W = W;
     fi.w = w.patch_embed; fi.cout = d; fi.out = x1; fi.out_ld = d;
     KD_TRY(conv_few_in<T>(fi, s));
+    trace_point("patch_embed", x1, (long)n * HW, (long)d * sizeof(T), (long)d * sizeof(T), s);
     // 2. encoder level 1; its last block writes the skip straight into the concat slot d1[..., d:2d]
     KD_TRY(run_blocks<T>(w.enc1, lnb, x1, d, d1 + d, 2 * d, n, H, W, sc, s));
     // 3. down1_2 (conv d -> d/2 + PixelUnshuffle) and level 2
     KD_TRY(conv3x3<T>(d1 + d, d, 2 * d, w.down1, d / 2, n, H, W, OUT_PIXEL_UNSHUFFLE, x2, 2 * d, 0, s));
+    trace_point("down1", x2, (long)n * HW / 4, 2L * d * sizeof(T), 2L * d * sizeof(T), s);
     KD_TRY(run_blocks<T>(w.enc2, lnb, x2, 2 * d, x2, 2 * d, n, H / 2, W / 2, sc, s));
     KD_TRY(conv3x3<T>(x2, 2 * d, 2 * d, w.down2, d, n, H / 2, W / 2, OUT_PIXEL_UNSHUFFLE, x3, 4 * d, 0, s));
+    trace_point("down2", x3, (long)n * HW / 16, 4L * d * sizeof(T), 4L * d * sizeof(T), s);
     KD_TRY(run_blocks<T>(w.enc3, lnb, x3, 4 * d, x3, 4 * d, n, H / 4, W / 4, sc, s));
     KD_TRY(conv3x3<T>(x3, 4 * d, 4 * d, w.down3, 2 * d, n, H / 4, W / 4, OUT_PIXEL_UNSHUFFLE, x4, 8 * d, 0, s));
+    trace_point("down3", x4, (long)n * HW / 64, 8L * d * sizeof(T), 8L * d * sizeof(T), s);
     KD_TRY(run_blocks<T>(w.latent, lnb, x4, 8 * d, x4, 8 * d, n, H / 8, W / 8, sc, s));
     // 4. up4_3 (conv 8d -> 16d + PixelShuffle) -> cat with enc3 -> reduce_chan_level3 (dual-source 1x1)
     KD_TRY(conv3x3<T>(x4, 8 * d, 8 * d, w.up4, 16 * d, n, H / 8, W / 8, OUT_PIXEL_SHUFFLE, sc.bufB, 4 * d, 0, s));
+    trace_point("up4", sc.bufB, (long)n * HW / 16, 4L * d * sizeof(T), 4L * d * sizeof(T), s);
     {
       ConvOp g;
       g.a0 = sc.bufB; g.c0 = 4 * d; g.ld0 = 4 * d; g.a1 = x3; g.c1 = 4 * d; g.ld1 = 4 * d;
@@ -493,7 +507,9 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       KD_TRY(conv_gemm<T>(g, s));
     }
     KD_TRY(run_blocks<T>(w.dec3, lnb, d3, 4 * d, d3, 4 * d, n, H / 4, W / 4, sc, s));
+    trace_point("dec3", d3, (long)n * HW / 16, 4L * d * sizeof(T), 4L * d * sizeof(T), s);
     KD_TRY(conv3x3<T>(d3, 4 * d, 4 * d, w.up3, 8 * d, n, H / 4, W / 4, OUT_PIXEL_SHUFFLE, sc.bufB, 2 * d, 0, s));
+    trace_point("up3", sc.bufB, (long)n * HW / 4, 2L * d * sizeof(T), 2L * d * sizeof(T), s);
     {
       ConvOp g;
       g.a0 = sc.bufB; g.c0 = 2 * d; g.ld0 = 2 * d; g.a1 = x2; g.c1 = 2 * d; g.ld1 = 2 * d;
@@ -504,6 +520,7 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
     KD_TRY(run_blocks<T>(w.dec2, lnb, d2, 2 * d, d2, 2 * d, n, H / 2, W / 2, sc, s));
     // 5. up2_1 writes channels [0, d) of d1 (the skip already sits in [d, 2d)); no reduce conv at level 1 (:245)
     KD_TRY(conv3x3<T>(d2, 2 * d, 2 * d, w.up2, 4 * d, n, H / 2, W / 2, OUT_PIXEL_SHUFFLE, d1, 2 * d, 0, s));
+    trace_point("up2+skip", d1, (long)n * HW, 2L * d * sizeof(T), 2L * d * sizeof(T), s);
     KD_TRY(run_blocks<T>(w.dec1, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
     KD_TRY(run_blocks<T>(w.refine, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
     // 6. output 3x3 2d -> oc ; denoise-rate tail (:314-321)
@@ -516,21 +533,27 @@ int teacher_forward(const kdlae_teacher_cfg& c, const void* packed, const float*
       fi.in1 = rate_b; fi.in1_img = rate_per_image ? 1 : HW; fi.in1_ch = 0; fi.cin1 = 1; fi.in1_px = rate_per_image ? 0 : 1;
       fi.nimg = n; fi.H = H; fi.W = W; fi.dil = 2; fi.w = w.output_param; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
       KD_TRY(conv_few_in<T>(fi, s));
+      trace_point("output", o1, 1, (long)n * oc * HW * 4, 0, s);
+      trace_point("output_param", d1, (long)n * HW, 2L * d * sizeof(T), 2L * d * sizeof(T), s);
       KD_TRY(run_blocks<T>(w.refine_out, lnb, d1, 2 * d, d1, 2 * d, n, H, W, sc, s));
       last_w = w.output2; last_w_tc = w.output2_tc;
     }
     // out_hq = out + inp_img (:321)
     KD_TRY(conv_to_planar<T>(d1, 2 * d, 2 * d, last_w, last_w_tc, oc, n, H, W, img_b, ic * HW, HW, hq_b, oc * HW, HW, reinterpret_cast<float*>(sc.bufA), s));
+    trace_point("hq", hq_b, 1, (long)n * oc * HW * 4, 0, s);
     // 7. SR head (:324-329): cen -> upen (PixelShuffle) -> enhance -> outputen
     if (c.sr_head) {
       fi = SmallConv();
       fi.in0 = hq_b; fi.in0_img = oc * HW; fi.in0_ch = HW; fi.cin0 = oc; fi.nimg = n; fi.H = H; fi.W = W;
       fi.w = w.cen; fi.cout = 2 * d; fi.out = d1; fi.out_ld = 2 * d;
       KD_TRY(conv_few_in<T>(fi, s));
+      trace_point("cen", d1, (long)n * HW, 2L * d * sizeof(T), 2L * d * sizeof(T), s);
       KD_TRY(conv3x3<T>(d1, 2 * d, 2 * d, w.upen, 4 * d, n, H, W, OUT_PIXEL_SHUFFLE, s0, d, 0, s));
+      trace_point("upen", s0, (long)n * HW * 4, (long)d * sizeof(T), (long)d * sizeof(T), s);
       KD_TRY(run_blocks<T>(w.enhance, lnb, s0, d, s0, d, n, 2 * H, 2 * W, sc, s));
       KD_TRY(conv_to_planar<T>(s0, d, d, w.outputen, w.outputen_tc, oc, n, 2 * H, 2 * W, nullptr, 0, 0, sr_b, oc * HW * 4, HW * 4,
                                reinterpret_cast<float*>(sc.bufA), s));
+      trace_point("sr", sr_b, 1, (long)n * oc * HW * 4 * 4, 0, s);
     }
   }
   return 0;
