@@ -42,6 +42,9 @@ int kdlae_profile_begin(void);
 /* stop, synchronise the device and return per class: summed kernel milliseconds, algorithmic FLOPs, algorithmic
  * bytes (inputs + outputs + weights of each launch) and the launch count. Arrays have kdlae_profile_num_classes() entries. */
 int kdlae_profile_end(int n_classes, double* ms, double* flops, double* bytes, long long* launches);
+/* per-launch records since kdlae_profile_begin(), in launch order (call BEFORE kdlae_profile_end): class index, kernel
+ * milliseconds, algorithmic FLOPs and bytes of up to max_launches launches; returns the number written. */
+int kdlae_profile_launches(int max_launches, int* cls, double* ms, double* flops, double* bytes);
 
 /* ---- KDLAE-T : KDLAE_teacher (KDLAE/KDLAE_model.py:204-336), alias RestormerSuperResolutionParam2 ------ */
 typedef struct kdlae_teacher_cfg {

@@ -46,6 +46,8 @@ SIGNATURES = {
     "kdlae_profile_begin": (C.c_int, []),
     "kdlae_profile_end": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_longlong)]),
+    "kdlae_profile_launches": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]),
     "kdlae_teacher_num_tensors": (C.c_int, [C.POINTER(TeacherCfg)]),
     "kdlae_teacher_packed_bytes": (C.c_size_t, [C.POINTER(TeacherCfg), C.c_int]),
     "kdlae_teacher_pack": (C.c_int, [C.POINTER(TeacherCfg), _PP, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
@@ -123,6 +125,15 @@ def launch_count() -> int:
 
 def profile_begin() -> None:
     check(load().kdlae_profile_begin(), "kdlae_profile_begin")
+
+
+def profile_launches(max_launches: int = 1 << 16) -> list:
+    """[(class name, ms, flops, bytes)] per launch since profile_begin(), in launch order; call before profile_end()."""
+    lib = load()
+    cls = (C.c_int * max_launches)()
+    ms, fl, by = (C.c_double * max_launches)(), (C.c_double * max_launches)(), (C.c_double * max_launches)()
+    n = lib.kdlae_profile_launches(max_launches, cls, ms, fl, by)
+    return [(lib.kdlae_profile_class_name(cls[i]).decode(), ms[i], fl[i], by[i]) for i in range(n)]
 
 
 def profile_end() -> dict:

@@ -144,6 +144,21 @@ int kdlae_profile_begin(void) {
   kd::g_prof_on = true;
   return 0;
 }
+int kdlae_profile_launches(int max_launches, int* cls, double* ms, double* flops, double* bytes) {
+  API_BEGIN();
+  KD_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(kd::g_prof_mu);
+  const int n = (int)std::min<size_t>(kd::g_recs.size(), (size_t)std::max(0, max_launches));
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, kd::g_recs[i].a, kd::g_recs[i].b) != cudaSuccess) { (void)cudaGetLastError(); t = -1.f; }
+    if (cls) cls[i] = kd::g_recs[i].cls;
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = kd::g_recs[i].flops;
+    if (bytes) bytes[i] = kd::g_recs[i].bytes;
+  }
+  return n;
+}
 int kdlae_profile_end(int n_classes, double* ms, double* flops, double* bytes, long long* launches) {
   API_BEGIN();
   kd::g_prof_on = false;

@@ -170,6 +170,9 @@ struct Epilogue {
   void* out = nullptr;
   long out_ld = 0;                   // destination row stride in elements
   int out_coff = 0;                  // destination channel offset
+  long out_y_ld = 0, res_y_ld = 0;   // tcgen05 spatial path, IDENTITY mode: element stride between image rows of the destination /
+                                     // residual (0 = W * ld).  Lets a conv write every other row of a 2x larger map (ConvTranspose
+                                     // 2x2 stride 2 = two 1x1 GEMMs, one per output-row phase, KDLAE-S upconv)
   int mode = OUT_IDENTITY;
   int cq = 0;                        // PIXEL_SHUFFLE: channels per sub-pixel (N = 4*cq, packed sub-pixel major)
   int H = 0, W = 0;                  // conv-output pixel grid (per image/frame)

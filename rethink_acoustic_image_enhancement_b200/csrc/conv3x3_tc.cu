@@ -22,7 +22,7 @@ constexpr int C3_ASLOTS = 2, C3_ASLOTS_MAX = 4, C3_BSLOTS = 3, C3_BSLOTS_MAX = 8
 constexpr uint32_t C3_A_BYTES = C3_TW * C3_IH * 128;          // 24576
 constexpr uint32_t C3_A_SLOT = C3_A_BYTES + 1024;             // shifted reads run 2 pixels past the tile
 constexpr uint32_t C3_B_SLOT = C3_NC_MAX * 128;               // 32768
-constexpr uint32_t C3_SLAB = 16384;                           // 120 px x 128 B used
+constexpr uint32_t C3_SLAB = 15360;                           // 120 px x 128 B
 constexpr int C3_EPI_WARPS = 16;
 constexpr int C3_THREADS = (2 + C3_EPI_WARPS + 2) * 32;
 constexpr uint32_t C3_SMEM = C3_ASLOTS * C3_A_SLOT + C3_BSLOTS * C3_B_SLOT + C3_NSLAB * C3_SLAB + 1024 + 512;   // streaming layout
@@ -41,7 +41,10 @@ struct C3Params {
   uint32_t b_bytes;          // bytes of the weight region
   int b_group, b_slots;      // streaming mode: taps per weight load (3 = one kernel row, or 1) and ring depth
   uint32_t b_slot;           // bytes per weight-ring slot
-  int w_resident;            // 1: all 9 tap tiles of the (single) K chunk fit the weight ring -> loaded once per CTA
+  int w_resident;            // 1: all 9 (27) tap tiles of the (single) K chunk fit shared memory -> loaded once per CTA
+  int w_tiles;               // weight tiles held in resident mode (9 * kd, or xconv_tiles() for an x-packed conv)
+  int xpack_cin;             // x-packed narrow conv: channels per pixel (16 / 32), 0 = ordinary conv (see ConvOp::xpack_cin)
+  int nslab;                 // output slab ring depth (4; 2 when the resident weights leave no room)
   float inv_n_chunks, inv_tiles_x, inv_tiles_y, inv_D;
   Epilogue epi;
 };
@@ -77,7 +80,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   const uint32_t a_base = sbase;
   const uint32_t b_base = a_base + p.a_slots * C3_A_SLOT;
   const uint32_t slab_base = b_base + p.b_bytes;
-  const uint32_t bar_base = slab_base + C3_NSLAB * C3_SLAB;
+  const uint32_t bar_base = slab_base + p.nslab * C3_SLAB;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (C3_ASLOTS_MAX + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * C3_ASLOTS_MAX + s); };
@@ -120,10 +123,10 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     // (warp-uniform loop, one elected lane issues - see elect_one())
     {
       uint32_t aidx = 0, bidx = 0;
-      if (p.w_resident) {          // weight-stationary: 9 x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
+      if (p.w_resident) {          // weight-stationary: 9 (27) x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
         if (elect_one()) {
-          mbar_expect_tx(b_full(0), 9u * (uint32_t)p.nc * 128);
-          for (int tap = 0; tap < 9; tap += p.b_group)
+          mbar_expect_tx(b_full(0), (uint32_t)p.w_tiles * (uint32_t)p.nc * 128);
+          for (int tap = 0; tap < p.w_tiles; tap += p.b_group)
             tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), 0, 0, tap);
         }
         __syncwarp();
@@ -181,11 +184,34 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const int kci = ag / p.kd;
           const int rem = kci < p.kc0 ? p.c0 - kci * 64 : p.c1 - (kci - p.kc0) * 64;
           const int ksn = rem >= 64 ? 4 : (rem + 15) >> 4;
-          if (p.w_resident) {
+          if (p.xpack_cin) {
+            // x-packed narrow conv, weight-stationary: per kernel row ty the centre tile (4 K steps on the super-pixel itself)
+            // and the two halo slots (kpc K steps each: the right neighbour's first pixel, the left neighbour's last pixel).
+            // A and B descriptors advance independently, so the halo slots are packed densely in their tiles.
+            if (elect_one()) {
+              const uint32_t b_tap = (uint32_t)p.nc * 8;
+              const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | lo_tag;
+              const int kpc = p.xpack_cin >> 4, hpt = (64 / p.xpack_cin) >> 1;
+              const int td = ag % p.kd;
+#pragma unroll
+              for (int ty = 0; ty < 3; ++ty) {
+                const int h = td * 3 + ty;
+                const uint32_t a_row = a_lo0 + (uint32_t)(ty * C3_TW * 8);
+                const uint32_t b_c = b_lo0 + (uint32_t)h * b_tap;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16_lohi(d_tmem, a_row + 8 + ks * 2, b_c + ks * 2, desc_hi, idesc, (ag | ty | ks) != 0 ? 1u : 0u);
+                const uint32_t b_h = b_lo0 + (uint32_t)(3 * p.kd + h / hpt) * b_tap + (uint32_t)((h % hpt) * 2 * kpc * 2);
+                for (int ks = 0; ks < kpc; ++ks) umma_bf16_lohi(d_tmem, a_row + 16 + ks * 2, b_h + ks * 2, desc_hi, idesc, 1u);
+                for (int ks = 0; ks < kpc; ++ks) umma_bf16_lohi(d_tmem, a_row + (4 - kpc + ks) * 2, b_h + (kpc + ks) * 2, desc_hi, idesc, 1u);
+              }
+            }
+            __syncwarp();
+          } else if (p.w_resident) {
             // weight-stationary: no per-tap handshake - the 9 x ksn MMAs of this A tile go out back to back from one elected lane
             if (elect_one()) {
-              const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | lo_tag;
               const uint32_t b_tap = (uint32_t)p.nc * 8;            // (nc * 128 bytes) >> 4 per tap tile
+              // single K chunk: the A group index is the frame tap, whose 9 spatial tap tiles start at 9 * td
+              const uint32_t b_lo0 = (((b_base & 0x3FFFF) >> 4) | lo_tag) + (uint32_t)(ag % p.kd) * 9u * b_tap;
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * C3_TW + tap % 3) * 8);
@@ -253,8 +279,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       if (FAST) {
         const float* __restrict__ bias_p = p.epi.col_bias;
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
-          const int b = slab_ctr % C3_NSLAB;
-          const uint32_t sph = (slab_ctr / C3_NSLAB) & 1;
+          const int b = slab_ctr % p.nslab;
+          const uint32_t sph = (slab_ctr / p.nslab) & 1;
           if (p.has_res) mbar_wait_relaxed(sfull_bar(b), sph);
           else mbar_wait_relaxed(sempty_bar(b), sph ^ 1);
           const int col0 = j * 64 + cq * 16;
@@ -337,8 +363,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const C3Tile t = c3_tile(p, item);
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
-          const int b = slab_ctr % C3_NSLAB;
-          mbar_wait_relaxed(sempty_bar(b), ((slab_ctr / C3_NSLAB) & 1) ^ 1);
+          const int b = slab_ctr % p.nslab;
+          mbar_wait_relaxed(sempty_bar(b), ((slab_ctr / p.nslab) & 1) ^ 1);
           mbar_expect_tx(sfull_bar(b), C3_OW * C3_OH * 128);
           tma_load_4d(slab_base + b * C3_SLAB, &map_res, sfull_bar(b), t.nchunk * p.nc + j * 64, t.x0, t.y0, t.img);
         }
@@ -351,15 +377,22 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const C3Tile t = c3_tile(p, item);
         for (int j = 0; j < nslabs; ++j, ++slab_ctr) {
-          const int b = slab_ctr % C3_NSLAB;
+          const int b = slab_ctr % p.nslab;
           named_bar_sync(1 + b, C3_STORE_BAR_THREADS);
           if (lane == 0) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(&map_out), "r"(slab_base + b * C3_SLAB), "r"(t.nchunk * p.nc + j * 64), "r"(t.x0), "r"(t.y0), "r"(t.img)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-            if (slab_ctr >= 2) mbar_arrive(sempty_bar((slab_ctr - 2) % C3_NSLAB));
+            // a slab is handed back once its store has been read out of shared memory; the number of stores left in flight is
+            // the ring depth minus two (the slab being written and the one just committed)
+            if (p.nslab >= 4) {
+              asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+              if (slab_ctr >= 2) mbar_arrive(sempty_bar((slab_ctr - 2) % p.nslab));
+            } else {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              mbar_arrive(sempty_bar(slab_ctr % p.nslab));
+            }
           }
           __syncwarp();
         }
@@ -401,15 +434,32 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   p.items = (long)op.nimg * p.tiles_x * p.tiles_y * n_chunks;
   KD_CHECK(p.items < (1L << 24), "conv3x3_tc: too many tiles (%ld)", p.items);
   p.has_res = e.res != nullptr; p.relu = e.relu;
-  p.w_resident = (op.kd == 1 && p.kc0 + p.kc1 == 1 && n_chunks == 1 && 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT) ? 1 : 0;
+  // weight-stationary when every tap tile of a single-K-chunk conv fits next to two activation slots: all 2-D layers with
+  // N <= 64 and the 3x3x3 layers of KDLAE-S up to 32 output channels (27 * 32 * 128 B = 108 KB).  Streaming the 27 tap tiles
+  // per output tile (9 dependent TMA round trips of ~1 us) made the 16 -> 16 layer at 512^2 take 8500 clk per 120-pixel tile.
+  p.xpack_cin = op.xpack_cin;
+  p.w_tiles = op.xpack_cin ? xconv_tiles(op.kd, op.xpack_cin) : 9 * op.kd;
+  p.nslab = C3_NSLAB;
+  const uint32_t w_res_bytes = ((uint32_t)p.w_tiles * nc * 128 + 1023u) & ~1023u;
+  p.w_resident = (p.kc0 + p.kc1 == 1 && n_chunks == 1 &&
+                  w_res_bytes + C3_ASLOTS * C3_A_SLOT + C3_NSLAB * C3_SLAB + 1024 + 512 <= C3_SMEM_MAX &&
+                  (op.kd == 3 || op.xpack_cin || 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT)) ? 1 : 0;
+  if (op.xpack_cin) {
+    KD_CHECK((op.xpack_cin == 16 || op.xpack_cin == 32) && op.c0 == 64 && op.c1 == 0 && n_chunks == 1 && nc % 16 == 0 && op.w_tap_ld == 64,
+             "conv3x3_tc: bad x-packed conv (cin %d, c0 %d, N %d)", op.xpack_cin, op.c0, e.N);
+    // a two-deep slab ring leaves the room to an extra activation slot (3x3x3 tiles of a 64-wide output take 112-144 KB)
+    p.nslab = 2;
+    p.w_resident = (w_res_bytes + C3_ASLOTS * C3_A_SLOT + 2 * C3_SLAB + 1024 + 512 <= C3_SMEM_MAX) ? 1 : 0;
+    KD_CHECK(p.w_resident, "conv3x3_tc: x-packed weights (%u bytes) do not fit shared memory", w_res_bytes);
+  }
   p.a_slots = C3_ASLOTS; p.b_bytes = C3_BSLOTS * C3_B_SLOT;
-  p.b_group = (2u * 3u * nc * 128 <= p.b_bytes) ? 3 : 1;      // a kernel row of taps per weight load when two such slots fit
+  p.b_group = (2u * 3u * nc * 128 <= p.b_bytes && !op.xpack_cin) ? 3 : 1;      // a kernel row of taps per weight load when two such slots fit
   p.b_slot = (uint32_t)p.b_group * nc * 128;
   p.b_slots = (int)std::min<uint32_t>(C3_BSLOTS, p.b_bytes / p.b_slot);     // deeper weight rings measured slower (they delay the A loads)
   uint32_t smem = C3_SMEM;
-  if (p.w_resident) {   // resident weights take 9 * nc * 128 bytes; the rest of the per-tap ring deepens the A ring
-    p.b_bytes = (9u * nc * 128 + 1023u) & ~1023u;
-    const uint32_t fixed = p.b_bytes + C3_NSLAB * C3_SLAB + 1024 + 512;
+  if (p.w_resident) {   // resident weights take 9 * kd * nc * 128 bytes; the rest of the per-tap ring deepens the A ring
+    p.b_bytes = w_res_bytes;
+    const uint32_t fixed = p.b_bytes + p.nslab * C3_SLAB + 1024 + 512;
     p.a_slots = (int)std::min<uint32_t>(C3_ASLOTS_MAX, (C3_SMEM_MAX - fixed) / C3_A_SLOT);
     smem = p.a_slots * C3_A_SLOT + fixed;
   }
@@ -452,15 +502,18 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   }
   {
     // weights [n][tap][c] seen as {c within a tap, n, tap}: one box = b_group consecutive taps of nc rows, each a [nc][64] K-major tile
-    const int taps = 9 * op.kd;
+    const int taps = op.xpack_cin ? p.w_tiles : 9 * op.kd;
     const cuuint64_t dims[3] = {(cuuint64_t)op.w_tap_ld, (cuuint64_t)e.N, (cuuint64_t)taps};
     const cuuint64_t str[2] = {(cuuint64_t)op.w_ld * 2, (cuuint64_t)op.w_tap_ld * 2};
     const cuuint32_t box[3] = {64, (cuuint32_t)nc, (cuuint32_t)p.b_group};
     KD_TRY(make_map(&mw, op.w, 3, dims, str, box));
   }
   const int grid = (int)(p.items < (long)g_c3_sms ? p.items : (long)g_c3_sms);
-  const double rows = (double)op.nimg * op.H * op.W, ktot = 9.0 * op.kd * (op.c0 + op.c1);
-  ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * e.N * ktot, 2.0 * (rows * (op.c0 + op.c1 + e.N * (e.res ? 2 : 1)) + e.N * ktot));
+  // algorithmic work: an x-packed conv does the FLOPs of the cin -> N/P conv it stands for (rows are super-pixels of P pixels)
+  const double rows = (double)op.nimg * op.H * op.W;
+  const double ktot = op.xpack_cin ? 9.0 * op.kd * op.xpack_cin : 9.0 * op.kd * (op.c0 + op.c1);
+  const double nalg = op.xpack_cin ? (double)e.N : (double)e.N;
+  ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * nalg * ktot, 2.0 * (rows * (op.c0 + op.c1 + e.N * (e.res ? 2 : 1)) + e.N * ktot));
   if (fast) k_conv3_tc<1><<<grid, C3_THREADS, smem, s>>>(ma0, ma1, mw, mout, mres, p);
   else k_conv3_tc<0><<<grid, C3_THREADS, smem, s>>>(ma0, ma1, mw, mout, mres, p);
   count_launch();

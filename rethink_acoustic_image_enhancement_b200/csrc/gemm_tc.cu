@@ -453,7 +453,10 @@ bool conv_gemm_tc_eligible(const ConvOp& op) {
   if (op.c1 > 0 && (op.c1 % 8 || op.ld1 % 8 || (reinterpret_cast<uintptr_t>(op.a1) & 15))) return false;
   if (op.w_ld % 8 || op.w_tap_ld % 8 || (reinterpret_cast<uintptr_t>(op.w) & 15) || op.w_group_stride % 8) return false;
   if ((k33 || k333) && op.groups != 1) return false;
-  if (k11 && op.epi.mode != OUT_IDENTITY && op.epi.mode != OUT_PLANAR_F32) return false;
+  // 1x1 with PixelShuffle addressing (ConvTranspose 2x2 stride 2 of KDLAE-S = 1x1 GEMM with 4 phases): runs on the spatial
+  // (y, x)-tiled path with a single tap, generic epilogue
+  if (k11 && op.epi.mode == OUT_PIXEL_UNSHUFFLE) return false;
+  if (k11 && op.epi.mode == OUT_PIXEL_SHUFFLE && (op.groups != 1 || op.epi.row_scale != nullptr)) return false;
   if (op.epi.mode == OUT_PIXEL_SHUFFLE && (op.epi.cq % 8 != 0)) return false;
   return true;
 }
@@ -476,7 +479,7 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.spatial = (op.kh == 3) ? 1 : 0;
+  p.spatial = (op.kh == 3 || op.epi.mode == OUT_PIXEL_SHUFFLE || op.epi.out_y_ld != 0) ? 1 : 0;
   p.taps = op.kd * op.kh * op.kw;
   p.kw = op.kw;
   p.kd = op.kd; p.D = op.D; p.inv_D = 1.0f / (float)(op.D > 0 ? op.D : 1);
@@ -495,16 +498,18 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
                     (e.res == nullptr || (e.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(e.res) & 15) == 0)) &&
                     (e.col_bias == nullptr || (reinterpret_cast<uintptr_t>(e.col_bias) & 15) == 0);
 
+  KD_CHECK(e.out_y_ld == 0 || (fast && op.kh == 1), "conv_gemm_tc: a destination row stride needs the FAST 1x1 epilogue");
   KD_CHECK(e.stat_rstd == nullptr || (fast && p.n_chunks == 1 && !p.spatial),
            "conv_gemm_tc: LayerNorm statistics need the FAST 1x1 epilogue with N in one chunk (N=%d)", e.N);
   CUtensorMap ma0, ma1, mw, mout, mres;
   const long rows = (long)op.nimg * op.H * op.W;
   long tiles_m;
   // activation-like maps (A sources, output, residual): {channels, pixels...}
-  auto act_map = [&](CUtensorMap* m, const void* base, int ch, long ld, int box_ch) -> int {
+  auto act_map = [&](CUtensorMap* m, const void* base, int ch, long ld, int box_ch, long y_ld = 0) -> int {
     if (p.spatial) {
+      if (y_ld == 0) y_ld = ld * op.W;
       const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.nimg};
-      const cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * op.W, (cuuint64_t)ld * 2 * op.W * op.H};
+      const cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)y_ld * 2, (cuuint64_t)y_ld * 2 * op.H};
       const cuuint32_t box[4] = {(cuuint32_t)box_ch, TC_TW, TC_TH, 1};
       return make_map(m, base, 4, dims, str, box);
     }
@@ -535,8 +540,8 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   if (op.c1 > 0) KD_TRY(act_map(&ma1, op.a1, op.c1, op.ld1, TC_BK));
   else ma1 = ma0;
   if (fast) {
-    KD_TRY(act_map(&mout, reinterpret_cast<const bf16*>(e.out) + e.out_coff, e.N, e.out_ld, 64));
-    if (e.res) KD_TRY(act_map(&mres, e.res, e.N, e.res_ld, 64));
+    KD_TRY(act_map(&mout, reinterpret_cast<const bf16*>(e.out) + e.out_coff, e.N, e.out_ld, 64, e.out_y_ld));
+    if (e.res) KD_TRY(act_map(&mres, e.res, e.N, e.res_ld, 64, e.res_y_ld));
     else mres = mout;
   } else {
     mout = ma0; mres = ma0;

@@ -366,10 +366,11 @@ template int mdta_fold<bf16>(float*, int, int, int, int, const float*, const flo
 // predicated loads), the [taps*CIN][cout] weights sit in shared memory.
 // PXF = consecutive output pixels per thread: one weight fetch feeds PXF pixels (wide outputs: the weight LDS traffic is the
 // limiter); narrow outputs (ASDQE stems, 16 channels) keep PXF = 1 so a warp's input loads stay contiguous.
-template <typename T, int CIN, int KD, int PXF>
+template <typename T, int CIN, int KD, int PXF, int DIL>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
   extern __shared__ __align__(16) float wsm_in[];   // [KD*9*CIN][cout]
   constexpr int TAPS = KD * 9;
+  constexpr int RW = PXF + 2 * DIL;                 // input columns one thread needs per (frame, row, channel)
   for (int e = threadIdx.x; e < TAPS * CIN * op.cout; e += blockDim.x) wsm_in[e] = op.w[e];
   __syncthreads();
   const unsigned cgroups = op.cout / 8;
@@ -395,38 +396,41 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
       const long im = (long)b * op.D + dd;
 #pragma unroll
       for (int ty = 0; ty < 3; ++ty) {
-        const int yy = y + (ty - 1) * op.dil;
+        const int yy = y + (ty - 1) * DIL;
         const bool y_ok = d_ok && yy >= 0 && yy < Hin;
 #pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
+        for (int c = 0; c < CIN; ++c) {
+          // the RW input columns of this (frame, row, channel) are loaded once and feed the three horizontal taps of all PXF
+          // pixels (the first version re-loaded every tap: 3 * PXF loads for 8 * 3 * PXF FMAs)
+          float r[RW];
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) {
-            float v[PXF];
-#pragma unroll
-            for (int q = 0; q < PXF; ++q) {
-              const int xx = x0 + q + (tx - 1) * op.dil;
-              float t = 0.f;
-              if (y_ok && xx >= 0 && xx < Win) {
-                const long sp = (long)yy * Win + xx;
-                if (c < op.cin0) {
-                  const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
-                  t = __ldg(op.in0 + o);
-                  if (op.sub0) t -= __ldg(op.sub0 + o);
-                } else {
-                  t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp * op.in1_px);
-                }
+          for (int j = 0; j < RW; ++j) {
+            const int xx = x0 - DIL + j;
+            float t = 0.f;
+            if (y_ok && xx >= 0 && xx < Win) {
+              const long sp = (long)yy * Win + xx;
+              if (c < op.cin0) {
+                const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
+                t = __ldg(op.in0 + o);
+                if (op.sub0) t -= __ldg(op.sub0 + o);
+              } else {
+                t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp * op.in1_px);
               }
-              v[q] = t;
             }
+            r[j] = t;
+          }
+#pragma unroll
+          for (int tx = 0; tx < 3; ++tx) {
             const float* wp = wsm_in + (((td * 3 + ty) * 3 + tx) * CIN + c) * op.cout + cg * 8;
             const float4 wa = *reinterpret_cast<const float4*>(wp);
             const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
             for (int q = 0; q < PXF; ++q) {
-              acc[q][0] = fmaf(v[q], wa.x, acc[q][0]); acc[q][1] = fmaf(v[q], wa.y, acc[q][1]);
-              acc[q][2] = fmaf(v[q], wa.z, acc[q][2]); acc[q][3] = fmaf(v[q], wa.w, acc[q][3]);
-              acc[q][4] = fmaf(v[q], wb.x, acc[q][4]); acc[q][5] = fmaf(v[q], wb.y, acc[q][5]);
-              acc[q][6] = fmaf(v[q], wb.z, acc[q][6]); acc[q][7] = fmaf(v[q], wb.w, acc[q][7]);
+              const float v = r[q + tx * DIL];
+              acc[q][0] = fmaf(v, wa.x, acc[q][0]); acc[q][1] = fmaf(v, wa.y, acc[q][1]);
+              acc[q][2] = fmaf(v, wa.z, acc[q][2]); acc[q][3] = fmaf(v, wa.w, acc[q][3]);
+              acc[q][4] = fmaf(v, wb.x, acc[q][4]); acc[q][5] = fmaf(v, wb.y, acc[q][5]);
+              acc[q][6] = fmaf(v, wb.z, acc[q][6]); acc[q][7] = fmaf(v, wb.w, acc[q][7]);
             }
           }
         }
@@ -451,7 +455,8 @@ int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   KD_CHECK(op.cout % 8 == 0 && op.out_ld % 8 == 0, "conv_few_in: cout=%d must be a multiple of 8", op.cout);
   const int cin = op.cin0 + op.cin1;
   KD_CHECK(cin >= 1 && cin <= 4 && (op.kd == 1 || (op.kd == 3 && cin == 1)), "conv_few_in: unsupported cin=%d kd=%d", cin, op.kd);
-  const int pxf = (op.kd == 1 && op.cout >= 48) ? 4 : 1;
+  KD_CHECK(op.dil == 1 || (op.dil == 2 && op.kd == 1), "conv_few_in: unsupported dilation %d", op.dil);
+  const int pxf = (op.W >= 16) ? 4 : 1;
   const long total = (long)op.H * ((op.W + pxf - 1) / pxf) * (op.cout / 8);
   KD_CHECK((long)op.H * op.W * (op.cout / 8) < (1L << 31) && op.nimg <= 65535, "conv_few_in: image too large");
   const double fi_pix = (double)op.nimg * op.H * op.W;
@@ -460,13 +465,15 @@ int conv_few_in_sized(const SmallConv& op, int Hin, int Win, cudaStream_t s) {
   const dim3 grid((unsigned)std::min<long>(cdiv(total, 128), std::max<long>(1, 148L * 16 / op.nimg)), op.nimg);
   const size_t smem = sizeof(float) * (size_t)op.kd * 9 * cin * op.cout;
   KD_CHECK(smem <= 48 * 1024, "conv_few_in: weights do not fit shared memory");
-#define KD_FEW_IN(CI, KDD) do { if (pxf == 4) k_conv_few_in<T, CI, KDD, 4><<<grid, 128, smem, s>>>(op, Hin, Win); \
-                                else k_conv_few_in<T, CI, KDD, 1><<<grid, 128, smem, s>>>(op, Hin, Win); } while (0)
-  if (op.kd == 3) k_conv_few_in<T, 1, 3, 1><<<grid, 128, smem, s>>>(op, Hin, Win);
-  else if (cin == 1) KD_FEW_IN(1, 1);
-  else if (cin == 2) KD_FEW_IN(2, 1);
-  else if (cin == 3) KD_FEW_IN(3, 1);
-  else KD_FEW_IN(4, 1);
+#define KD_FEW_IN(CI, KDD, DL) do { if (pxf == 4) k_conv_few_in<T, CI, KDD, 4, DL><<<grid, 128, smem, s>>>(op, Hin, Win); \
+                                    else k_conv_few_in<T, CI, KDD, 1, DL><<<grid, 128, smem, s>>>(op, Hin, Win); } while (0)
+#define KD_FEW_IN_D(CI) do { if (op.dil == 2) KD_FEW_IN(CI, 1, 2); else KD_FEW_IN(CI, 1, 1); } while (0)
+  if (op.kd == 3) KD_FEW_IN(1, 3, 1);
+  else if (cin == 1) KD_FEW_IN_D(1);
+  else if (cin == 2) KD_FEW_IN_D(2);
+  else if (cin == 3) KD_FEW_IN_D(3);
+  else KD_FEW_IN_D(4);
+#undef KD_FEW_IN_D
 #undef KD_FEW_IN
   count_launch();
   KD_LAUNCH_CHECK();

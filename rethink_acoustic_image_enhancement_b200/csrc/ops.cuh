@@ -16,6 +16,10 @@ struct ConvOp {
   int dil = 1;                  // spatial dilation (padding = dil*(k/2), zero fill)
   const void* w = nullptr;      // weights: element (n, tap, c) at w[n*w_ld + tap*w_tap_ld + c]
   long w_ld = 0, w_tap_ld = 0;
+  // x-packed narrow conv (conv3x3_tc.cu): a0 is an NHWC tensor of xpack_cin (16 or 32) channels viewed as [.., W/P, 64] with
+  // P = 64 / xpack_cin pixels per 128-byte "super-pixel"; W, c0 = 64, ld0 = 64 and epi.N = P * cout are given in super-pixel
+  // units and w comes from pack_xconv (centre + halo tiles).  0 = ordinary conv.
+  int xpack_cin = 0;
   int groups = 1;               // >1: per-image weights (w + g*w_group_stride), rows split evenly
   long w_group_stride = 0;
   Epilogue epi;
@@ -124,6 +128,10 @@ template <typename T> int pack_weights(const PackOp& op, cudaStream_t s);
 // WithBias-LN fold column vectors of a packed 1x1 weight: s1[n] = sum_k W'[n][k], s2[n] = sum_k lnb[k]*W[src(n)][k]
 template <typename T> int pack_ln_cols(const PackOp& op, const float* lnb, float* s1, float* s2, cudaStream_t s);
 // depthwise weights [C][1][3][3] -> [9][Cdst] fp32 (optionally with the HALVES channel map)
+// x-packed 3x3 / 3x3x3 conv weights (see ConvOp::xpack_cin): src [cout][cin][kd*9] -> dst [P*cout][xconv_tiles][64] bf16
+// (centre tiles: block-Toeplitz over the P pixels of a super-pixel; halo tiles: the neighbours' edge pixels), bias replicated P x
+int xconv_tiles(int kd, int cin);
+int pack_xconv(const float* src, const float* nscale, int cout, int cin, int kd, bf16* dst, cudaStream_t s);
 int pack_dw(const float* src, int c_src, int h, int hp, float* dst, int c_dst, cudaStream_t s);
 int pack_dw_bias(const float* src, int c_src, int h, int hp, float* dst, int c_dst, cudaStream_t s);
 // small-conv weights [Cout][Cin][taps] -> [taps][Cin][Cout] fp32 (few-in) ; -> [Cout][taps][Cin] (few-out)

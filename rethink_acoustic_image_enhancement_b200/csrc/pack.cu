@@ -49,6 +49,49 @@ int pack_weights(const PackOp& op, cudaStream_t s) {
 template int pack_weights<float>(const PackOp&, cudaStream_t);
 template int pack_weights<bf16>(const PackOp&, cudaStream_t);
 
+// ---- x-packed narrow conv (ConvOp::xpack_cin, conv3x3_tc.cu) -------------------------------------------------------------
+// P = 64 / cin pixels form one 64-channel super-pixel.  Output row n = j*cout + co (pixel j of the super-pixel), K column
+// k = i*cin + ci (pixel i).  Tile h = td*3 + ty (< 3*kd) is the centre tile of that (frame, row) tap: W[co][ci][h][dx = i - j]
+// for |i - j| <= 1.  Halo tiles follow: each holds P/2 (frame, row) taps with two cin-wide slots per tap - slot 2u: the right
+// neighbour's pixel 0 feeding output pixel P-1 (dx = +1), slot 2u+1: the left neighbour's pixel P-1 feeding output pixel 0.
+int xconv_tiles(int kd, int cin) {
+  const int hpt = (64 / cin) / 2;
+  return 3 * kd + (3 * kd + hpt - 1) / hpt;
+}
+__global__ void __launch_bounds__(256) k_pack_xconv(const float* __restrict__ src, const float* __restrict__ nscale, int cout, int cin,
+                                                    int kd, bf16* __restrict__ dst) {
+  const int P = 64 / cin, taps = kd * 9, nh = 3 * kd, hpt = P / 2;
+  const int ntiles = nh + (nh + hpt - 1) / hpt;
+  const long total = (long)P * cout * ntiles * 64;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % 64);
+  const int tile = (int)((idx / 64) % ntiles);
+  const int n = (int)(idx / (64L * ntiles));
+  const int j = n / cout, co = n % cout;
+  float v = 0.f;
+  if (tile < nh) {
+    const int i = k / cin, ci = k % cin, dx = i - j;
+    if (dx >= -1 && dx <= 1) v = src[((long)co * cin + ci) * taps + tile * 3 + dx + 1];
+  } else {
+    const int slot = k / cin, ci = k % cin;
+    const int h = (tile - nh) * hpt + slot / 2;
+    if (h < nh) {
+      if ((slot & 1) == 0) { if (j == P - 1) v = src[((long)co * cin + ci) * taps + h * 3 + 2]; }
+      else { if (j == 0) v = src[((long)co * cin + ci) * taps + h * 3 + 0]; }
+    }
+  }
+  if (nscale) v *= nscale[co];
+  dst[idx] = __float2bfloat16_rn(v);
+}
+int pack_xconv(const float* src, const float* nscale, int cout, int cin, int kd, bf16* dst, cudaStream_t s) {
+  KD_CHECK((cin == 16 || cin == 32) && (kd == 1 || kd == 3) && cout % 8 == 0, "pack_xconv: unsupported cin=%d kd=%d cout=%d", cin, kd, cout);
+  const long total = (long)(64 / cin) * cout * xconv_tiles(kd, cin) * 64;
+  k_pack_xconv<<<cdiv(total, 256), 256, 0, s>>>(src, nscale, cout, cin, kd, dst);
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
 // WithBias-LN fold column vectors for a packed 1x1 weight (taps == 1, PLAIN or HALVES-on-N):
 //   s1[n] = sum_k W'[n][k] (packed, already rounded to T),  s2[n] = sum_k lnb[k] * W[src(n)][k]
 template <typename T>

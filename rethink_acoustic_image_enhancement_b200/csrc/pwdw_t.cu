@@ -8,15 +8,18 @@
 // register pairs), and runs the 3x3 taps as packed FFMA2 over pixel pairs with the tap weight broadcast.
 // Compared with pwdw_f2.cu (GEMM in the usual orientation, bf16 t tile in shared memory, channel-pair lanes) this removes the
 // TMEM->bf16->smem conversion pass, the t tile, the LDS + bf16 unpack of every input (which was ~40 % of the issue slots)
-// and keeps t in fp32.  LayerNorm's rstd[pixel] is a per-column scale here: a helper warp stages the tile's rstd values
-// (0 outside the image = the conv's zero padding of t) in shared memory, pair-aligned twice (even / odd columns).
+// and keeps t in fp32.  LayerNorm's rstd[pixel] is applied to the x tile BEFORE the GEMM: two helper warps rescale the TMA-staged
+// bf16 tile in place (x^ = bf16(x * rstd), one extra rounding of the GEMM input; a pixel row is 128 contiguous bytes of the
+// swizzled tile, so the pass is linear), which costs C values per pixel instead of the 3C / 2h accumulator values the depthwise
+// warps used to scale (2 FMUL2 + 2 LDS.64 of every 13 issue slots per output pair).  Pixels outside the image are TMA
+// zero fill, so t is exactly 0 there = the conv's zero padding of t.
 // Results leave through per-warp [pixel][32 ch] bf16 staging blocks and one small TMA store per warp and item (TMA clips at
 // the image edge), so the depthwise warps never synchronise with each other: with CTA-wide barriers per item they ran in
 // lockstep, all in their FFMA2 bursts at once (ncu: math-pipe throttle on top) and all idle together in the store phase.
 //   GATE = 0: tile = 8 x 32 pixels (6 x 30 outputs), item = (tile, 128 channels), D = 256 TMEM columns, double buffered.
 //   GATE = 1: tile = 8 x 16 pixels (6 x 14 outputs), item = (tile, 128 gated channels): x1 rows -> columns [0,128),
 //             x2 rows -> columns [128,256), double buffered.
-// Warps: 0 TMA producer, 1 MMA issuer, 2 rstd staging, 3 idle, 4.. depthwise (TMEM lane quarter = warp % 4).
+// Warps: 0 TMA producer, 1 MMA issuer, 2-3 x-tile rescale, 4.. depthwise (TMEM lane quarter = warp % 4).
 #include <algorithm>
 #include "sm100.cuh"
 
@@ -52,11 +55,6 @@ __device__ __forceinline__ u64 pack2u(uint32_t lo, uint32_t hi) {
   return r;
 }
 __device__ __forceinline__ u64 splat2(float c) { return pack2f(c, c); }
-__device__ __forceinline__ u64 lds64(uint32_t addr) {
-  u64 v;
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
-  return v;
-}
 // gelu(a) * b on a packed pair (identical to dwconv_f2.cu / pwdw_f2.cu)
 __device__ __forceinline__ u64 gelu_gate2(u64 a, u64 b) {
   // gelu(x) = x * Phi(x) with Phi(x) = 1 / (1 + 2^(x * Q(x^2))):  Q = -2 log2(e) * P and P(x^2) ~ atanh(erf(x / sqrt2)) / x is a
@@ -126,20 +124,20 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   constexpr uint32_t W1CHUNK = PT_MB * 128;          // 128 rows x 64 channels of one chunk(2) half
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // smem (1024-aligned): W1 [kc][NH] chunks | x chunks | staging[2] | rs[2][NPX] (even pairs) + rsb[2][NPX] (odd pairs) | barriers
+  // smem (1024-aligned): W1 [kc][NH] chunks | x chunks | staging[2] | barriers
   const uint32_t w1_base = sbase;
   const uint32_t x_base = w1_base + p.kc * NH * W1CHUNK;
   const uint32_t stage_base = x_base + p.kc * XCHUNK;
-  const uint32_t rs_base = stage_base + 2 * STAGE;
-  const uint32_t bar_base = rs_base + 4 * NPX * 4;
+  const uint32_t bar_base = stage_base + 2 * STAGE;
   const uint32_t w_full = bar_base, w_empty = bar_base + 8, x_full = bar_base + 16, x_empty = bar_base + 24;
+  // (Handing D[b] over in two-row chunks - the GEMM of item n+2 refilling rows the depthwise warps have moved past - was measured
+  // 8-35 % SLOWER: four N = 64 MMAs re-read the A operand four times and every chunk costs each warp a tcgen05 fence pair.)
   auto d_full = [&](int b) { return bar_base + 32 + 8u * b; };
   auto d_empty = [&](int b) { return bar_base + 48 + 8u * b; };
-  auto rs_full = [&](int b) { return bar_base + 64 + 8u * b; };
-  auto rs_empty = [&](int b) { return bar_base + 80 + 8u * b; };
+  const uint32_t x_scaled = bar_base + 64;
   const uint32_t tmem_slot = bar_base + 96;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* rs_gen = reinterpret_cast<float*>(smem_raw + (rs_base - smem_u32(smem_raw)));
+  uint8_t* x_gen = smem_raw + (x_base - smem_u32(smem_raw));
   uint8_t* stage_gen = smem_raw + (stage_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,10 +149,8 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out); prefetch_tmap(&map_out_last);
     mbar_init(w_full, 1); mbar_init(w_empty, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(d_full(b), 1); mbar_init(d_empty(b), Cfg::NDW);
-      mbar_init(rs_full(b), 1); mbar_init(rs_empty(b), Cfg::NDW);
-    }
+    mbar_init(x_scaled, 2);
+    for (int b = 0; b < 2; ++b) { mbar_init(d_full(b), 1); mbar_init(d_empty(b), Cfg::NDW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -222,9 +218,9 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
       for (int i = 0; i < ntiles; ++i) {
         for (int cb = 0; cb < ncb; ++cb, ++n) {
           const int b = n & 1;
-          mbar_wait_lazy(d_empty(b), ((n >> 1) & 1) ^ 1);   // depthwise warps have drained D[b] (item n-2)
+          mbar_wait_relaxed(d_empty(b), ((n >> 1) & 1) ^ 1);   // depthwise warps have drained D[b] (item n-2): on the critical path
           mbar_wait_relaxed(w_full, n & 1);
-          if (cb == 0) mbar_wait_relaxed(x_full, i & 1);
+          if (cb == 0) mbar_wait_relaxed(x_scaled, i & 1);   // x tile landed and rescaled by rstd
           tc_fence_after();
           if (elect_one()) {
             for (int h = 0; h < NH; ++h) {
@@ -243,32 +239,47 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== rstd staging: rs[p] = rstd of halo-tile pixel p (0 outside the image), rsb[p] = rs[p+1] ==========
+  } else if (warp == 2 || warp == 3) {
+    // ===================== x-tile rescale: x^[p][:] = bf16(x[p][:] * rstd[p]) in place (BiasFree LayerNorm folded) ==========
+    // A pixel row is 128 contiguous bytes per 64-channel chunk (the 128B swizzle only permutes the 16-byte pieces inside it), so
+    // thread t owns the physical 16-byte piece (t & 7) of pixels (t >> 3) + 8 m.
+    const int t64 = (warp - 2) * 32 + lane;
+    const int pc = t64 & 7, p0 = t64 >> 3;
     for (int i = 0; i < ntiles; ++i) {
-      const int b = i & 1;
       int img, y0, x0;
       tile_xy(i, img, y0, x0);
-      float v[NPX / 32];
+      float rsv[NPX / 8];
 #pragma unroll
-      for (int j = 0; j < NPX / 32; ++j) {
-        const int pix = j * 32 + lane;
+      for (int m = 0; m < NPX / 8; ++m) {
+        const int pix = p0 + 8 * m;
         const int y = y0 - 1 + pix / PITCH, x = x0 - 1 + pix % PITCH;
         const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W;
-        v[j] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;
+        rsv[m] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;
       }
-      mbar_wait_lazy(rs_empty(b), ((i >> 1) & 1) ^ 1);
-      float* rs = rs_gen + b * NPX;
-      float* rsb = rs_gen + (2 + b) * NPX;
+      mbar_wait_relaxed(x_full, i & 1);
+      for (int k = 0; k < p.kc; ++k) {
+        const int vch = min(8, (p.C - k * 64 + 7) >> 3);          // 16-byte pieces of this chunk that hold channels
 #pragma unroll
-      for (int j = 0; j < NPX / 32; ++j) {
-        const int pix = j * 32 + lane;
-        rs[pix] = v[j];
-        if (pix > 0) rsb[pix - 1] = v[j];
+        for (int m = 0; m < NPX / 8; ++m) {
+          const int pix = p0 + 8 * m;
+          if ((pc ^ (pix & 7)) < vch) {
+            uint4* q = reinterpret_cast<uint4*>(x_gen + k * XCHUNK + pix * 128 + pc * 16);
+            uint4 v = *q;
+            const u64 r2 = splat2(rsv[m]);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = as_float2(fmul2(pack2u(w[e] << 16, w[e] & 0xffff0000u), r2));
+              __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *q = v;
+          }
+        }
       }
-      if (lane == 31) rsb[NPX - 1] = 0.f;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA's operand reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(rs_full(b));
+      if (lane == 0) mbar_arrive(x_scaled);
     }
   } else if (warp >= 4) {
     // ===================== depthwise warps =====================
@@ -283,9 +294,6 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
     for (int i = 0; i < ntiles; ++i) {
       int img, y0, x0;
       tile_xy(i, img, y0, x0);
-      mbar_wait_relaxed(rs_full(i & 1), (i >> 1) & 1);
-      const uint32_t rs_a = rs_base + ((i & 1) * NPX + s0) * 4;
-      const uint32_t rs_b = rs_base + ((2 + (i & 1)) * NPX + s0) * 4;
       for (int cb = 0; cb < ncb; ++cb, ++n) {
         const int b = n & 1;
         // logical quarter of this warp in the item's channel block (partial blocks are rotated by the tile index); warps whose
@@ -341,9 +349,9 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             u64 va[GP + 1], vb[GP];
 #pragma unroll
-            for (int j = 0; j < GP + 1; ++j) va[j] = fmul2(pack2u(ra[2 * j], ra[2 * j + 1]), lds64(rs_a + (ir * PITCH + 2 * j) * 4));
+            for (int j = 0; j < GP + 1; ++j) va[j] = pack2u(ra[2 * j], ra[2 * j + 1]);
 #pragma unroll
-            for (int j = 0; j < GP; ++j) vb[j] = fmul2(pack2u(rb[2 * j], rb[2 * j + 1]), lds64(rs_b + (ir * PITCH + 2 * j) * 4));
+            for (int j = 0; j < GP; ++j) vb[j] = pack2u(rb[2 * j], rb[2 * j + 1]);
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int orow = ir - dy;
@@ -387,8 +395,6 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(rs_empty(i & 1));
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -414,7 +420,7 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.rstd = rstd; p.w9c = w9c;
   const int NH = GATE ? 2 : 1;
-  const uint32_t smem = 1024 + p.kc * NH * PT_MB * 128 + p.kc * Cfg::XCHUNK + 2 * Cfg::STAGE + 4 * Cfg::NPX * 4 + 128;
+  const uint32_t smem = 1024 + p.kc * NH * PT_MB * 128 + p.kc * Cfg::XCHUNK + 2 * Cfg::STAGE + 256;
   KD_CHECK(smem <= 232448, "pwdw_t: shared memory budget exceeded (%u)", smem);
   static DeviceOnce once;
   bool first; int dev, g_pt_sms;

@@ -4,14 +4,23 @@
 // ConvTranspose3d (1,2,2)/s(1,2,2) = 1x1 GEMM with 4 output phases scattered by the PixelShuffle-style
 // epilogue plus the skip add at the destination.
 #include <algorithm>
+#include <type_traits>
 #include "models.cuh"
 
 namespace kd {
 
 namespace {
 
+// wx / bx: x-packed form (ConvOp::xpack_cin) of the narrow layers (16 or 32 input channels): P = 64/cin pixels per 128-byte
+// super-pixel, so TMA boxes, smem rows, MMAs (N = 64) and stores are full width instead of 1/4 - 1/2 used.  A packed output of
+// 128 columns (16 -> 32, 32 -> 64) runs as two launches over 64-column halves so the weight tiles stay resident in shared memory
 template <typename T>
-struct Conv27 { T* w; float* b; int cin, cout; };
+struct Conv27 { T* w; float* b; int cin, cout; bf16* wx; float* bx; };
+
+template <typename T>
+bool xpack_ok(int cin, int cout) {
+  return std::is_same<T, bf16>::value && (cin == 16 || cin == 32) && ((64 / cin) * cout == 64 || (64 / cin) * cout == 128);
+}
 
 template <typename T>
 struct StudentW {
@@ -29,6 +38,11 @@ void layout_student(const kdlae_student_cfg& c, Bump& b, StudentW<T>& w) {
     k.cin = cin; k.cout = cout;
     k.w = b.take<T>((size_t)cout * 27 * cin);
     k.b = b.take<float>(cout);
+    k.wx = nullptr; k.bx = nullptr;
+    if (xpack_ok<T>(cin, cout)) {
+      k.wx = b.take<bf16>((size_t)(64 / cin) * cout * xconv_tiles(3, cin) * 64);
+      k.bx = b.take<float>((64 / cin) * cout);
+    }
   };
   w.first_w = b.take<float>((size_t)27 * h0);
   w.first_b = b.take<float>(h0);
@@ -46,22 +60,58 @@ int pack27(const Conv27<T>& k, const float* wsrc, const float* bsrc, cudaStream_
   PackOp p;
   p.src = wsrc; p.n_src = k.cout; p.c_src = k.cin; p.taps = 27; p.dst = k.w; p.n_dst = k.cout; p.c_dst = k.cin;
   KD_TRY(pack_weights<T>(p, s));
+  if (k.wx) {
+    KD_TRY(pack_xconv(wsrc, nullptr, k.cout, k.cin, 3, k.wx, s));
+    for (int j = 0; j < 64 / k.cin; ++j) KD_TRY(copy_f32(bsrc, k.bx + j * k.cout, k.cout, s));
+  }
   return copy_f32(bsrc, k.b, k.cout, s);
 }
 
 template <typename T>
 int conv27(const Conv27<T>& k, const T* in, T* out, int nimg, int D, int H, int W, cudaStream_t s) {
   ConvOp g;
+  if (k.wx && W % (64 / k.cin) == 0 && W / (64 / k.cin) >= 4) {      // x-packed: rows are super-pixels of P pixels
+    const int P = 64 / k.cin, NP = P * k.cout;
+    g.a0 = in; g.c0 = 64; g.ld0 = 64; g.nimg = nimg; g.D = D; g.H = H; g.W = W / P; g.kd = g.kh = g.kw = 3;
+    g.xpack_cin = k.cin;
+    g.w_tap_ld = 64; g.w_ld = (long)xconv_tiles(3, k.cin) * 64;
+    g.epi.relu = 1; g.epi.out = out; g.epi.out_ld = NP; g.epi.N = 64; g.epi.H = H; g.epi.W = W / P;
+    for (int half = 0; half < NP / 64; ++half) {
+      g.w = k.wx + (long)half * 64 * g.w_ld;
+      g.epi.col_bias = k.bx + half * 64;
+      g.epi.out_coff = half * 64;
+      KD_TRY(conv_gemm<T>(g, s));
+    }
+    return 0;
+  }
   g.a0 = in; g.c0 = k.cin; g.ld0 = k.cin; g.nimg = nimg; g.D = D; g.H = H; g.W = W; g.kd = g.kh = g.kw = 3;
   g.w = k.w; g.w_ld = 27L * k.cin; g.w_tap_ld = k.cin;
   g.epi.col_bias = k.b; g.epi.relu = 1; g.epi.out = out; g.epi.out_ld = k.cout; g.epi.N = k.cout; g.epi.H = H; g.epi.W = W;
   return conv_gemm<T>(g, s);
 }
 
-// ConvTranspose3d kernel (1,2,2) stride (1,2,2) (:378, no overlap) + skip add (:417)
+// ConvTranspose3d kernel (1,2,2) stride (1,2,2) (:378, no overlap) + skip add (:417).
+// w: [4*cout][cin] with rows phase-major (s = 2*dy + dx), bias4 replicated per phase.  For a fixed output-row phase dy the two dx
+// phases of input pixel (y, x) are the ADJACENT output pixels (2y+dy, 2x), (2y+dy, 2x+1): 2*cout contiguous channels.  So the
+// bf16 path runs two 1x1 GEMMs (N = 2*cout) whose destination is the output seen as [nimg, H, W, 2*cout] with a row stride of
+// two output rows - plain TMA slab stores and a TMA-loaded skip tile instead of the scattered PixelShuffle epilogue.
 template <typename T>
 int upconv(const T* in, int cin, const T* w, const float* bias4, int cout, const T* skip, T* out, int nimg, int H, int W,
            cudaStream_t s) {
+  if (std::is_same<T, bf16>::value && (2 * cout) % 8 == 0 && cin % 8 == 0) {
+    for (int dy = 0; dy < 2; ++dy) {
+      ConvOp g;
+      g.a0 = in; g.c0 = cin; g.ld0 = cin; g.nimg = nimg; g.H = H; g.W = W;
+      g.w = w + (long)dy * 2 * cout * cin; g.w_ld = cin; g.w_tap_ld = cin;
+      const long row = 2L * W * cout;                       // one output row (2W pixels of cout channels)
+      g.epi.col_bias = bias4 + dy * 2 * cout;
+      g.epi.res = skip + dy * row; g.epi.res_ld = 2 * cout; g.epi.res_y_ld = 2 * row;
+      g.epi.out = out + dy * row; g.epi.out_ld = 2 * cout; g.epi.out_y_ld = 2 * row;
+      g.epi.N = 2 * cout; g.epi.H = H; g.epi.W = W;
+      KD_TRY(conv_gemm<T>(g, s));
+    }
+    return 0;
+  }
   ConvOp g;
   g.a0 = in; g.c0 = cin; g.ld0 = cin; g.nimg = nimg; g.H = H; g.W = W;
   g.w = w; g.w_ld = cin; g.w_tap_ld = cin;
