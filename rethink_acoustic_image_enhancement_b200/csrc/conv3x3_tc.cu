@@ -181,28 +181,44 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const uint32_t a_lo0 = (((a_base + s * C3_A_SLOT) & 0x3FFFF) >> 4) | lo_tag;
           // K = 16 steps that hold real channels in this chunk (a 16-channel layer needs 1 of the 4: the rest of the box is TMA
           // zero fill and would only burn tensor-pipe time - the KDLAE-S / ASDQE layers are 16..64 channels wide)
-          const int kci = ag / p.kd;
+          const int kci = p.w_resident ? 0 : ag / p.kd;      // resident modes have a single K chunk
           const int rem = kci < p.kc0 ? p.c0 - kci * 64 : p.c1 - (kci - p.kc0) * 64;
           const int ksn = rem >= 64 ? 4 : (rem + 15) >> 4;
           if (p.xpack_cin) {
             // x-packed narrow conv, weight-stationary: per kernel row ty the centre tile (4 K steps on the super-pixel itself)
             // and the two halo slots (kpc K steps each: the right neighbour's first pixel, the left neighbour's last pixel).
             // A and B descriptors advance independently, so the halo slots are packed densely in their tiles.
+            // Every offset is computed here, in warp-uniform code without divisions (single K chunk: ag is the frame tap): the
+            // first version did `h / hpt`, `ag % kd` inside the elected region and the issuing thread spent ~2500 instructions per
+            // activation tile on address arithmetic - the tensor pipe sat at 30 % waiting for it.
+            const uint32_t b_tap = (uint32_t)p.nc * 8;
+            const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | lo_tag;
+            const int kpc = p.xpack_cin >> 4;                 // K steps per pixel: 1 (16 channels) or 2 (32 channels)
+            const int hsh = (p.xpack_cin == 16) ? 1 : 0;      // (frame, row) taps per halo tile = 1 << hsh
+            const int h0 = ag * 3;
+            uint32_t a_row[3], b_c[3], b_h[3];
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty) {
+              const int h = h0 + ty;
+              a_row[ty] = a_lo0 + (uint32_t)(ty * C3_TW * 8);
+              b_c[ty] = b_lo0 + (uint32_t)h * b_tap;
+              b_h[ty] = b_lo0 + (uint32_t)(3 * p.kd + (h >> hsh)) * b_tap + (uint32_t)((h & ((1 << hsh) - 1)) * 4 * kpc);
+            }
+            const uint32_t first = (ag == 0) ? 0u : 1u;
             if (elect_one()) {
-              const uint32_t b_tap = (uint32_t)p.nc * 8;
-              const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | lo_tag;
-              const int kpc = p.xpack_cin >> 4, hpt = (64 / p.xpack_cin) >> 1;
-              const int td = ag % p.kd;
 #pragma unroll
               for (int ty = 0; ty < 3; ++ty) {
-                const int h = td * 3 + ty;
-                const uint32_t a_row = a_lo0 + (uint32_t)(ty * C3_TW * 8);
-                const uint32_t b_c = b_lo0 + (uint32_t)h * b_tap;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_bf16_lohi(d_tmem, a_row + 8 + ks * 2, b_c + ks * 2, desc_hi, idesc, (ag | ty | ks) != 0 ? 1u : 0u);
-                const uint32_t b_h = b_lo0 + (uint32_t)(3 * p.kd + h / hpt) * b_tap + (uint32_t)((h % hpt) * 2 * kpc * 2);
-                for (int ks = 0; ks < kpc; ++ks) umma_bf16_lohi(d_tmem, a_row + 16 + ks * 2, b_h + ks * 2, desc_hi, idesc, 1u);
-                for (int ks = 0; ks < kpc; ++ks) umma_bf16_lohi(d_tmem, a_row + (4 - kpc + ks) * 2, b_h + (kpc + ks) * 2, desc_hi, idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks) umma_bf16_lohi(d_tmem, a_row[ty] + 8 + ks * 2, b_c[ty] + ks * 2, desc_hi, idesc, (ty | ks) != 0 ? 1u : first);
+                if (kpc == 1) {
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 16, b_h[ty], desc_hi, idesc, 1u);            // right neighbour's first pixel
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 6, b_h[ty] + 2, desc_hi, idesc, 1u);         // left neighbour's last pixel
+                } else {
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 16, b_h[ty], desc_hi, idesc, 1u);
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 18, b_h[ty] + 2, desc_hi, idesc, 1u);
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 4, b_h[ty] + 4, desc_hi, idesc, 1u);
+                  umma_bf16_lohi(d_tmem, a_row[ty] + 6, b_h[ty] + 6, desc_hi, idesc, 1u);
+                }
               }
             }
             __syncwarp();
@@ -211,7 +227,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             if (elect_one()) {
               const uint32_t b_tap = (uint32_t)p.nc * 8;            // (nc * 128 bytes) >> 4 per tap tile
               // single K chunk: the A group index is the frame tap, whose 9 spatial tap tiles start at 9 * td
-              const uint32_t b_lo0 = (((b_base & 0x3FFFF) >> 4) | lo_tag) + (uint32_t)(ag % p.kd) * 9u * b_tap;
+              const uint32_t b_lo0 = (((b_base & 0x3FFFF) >> 4) | lo_tag) + (uint32_t)ag * 9u * b_tap;   // ag < kd here
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * C3_TW + tap % 3) * 8);

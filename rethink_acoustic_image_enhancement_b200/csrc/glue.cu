@@ -393,31 +393,31 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
     for (int td = 0; td < KD; ++td) {
       const int dd = d + td - KD / 2;
       const bool d_ok = dd >= 0 && dd < op.D;
-      const long im = (long)b * op.D + dd;
+      const long im = (long)b * op.D + min(max(dd, 0), op.D - 1);
 #pragma unroll
       for (int ty = 0; ty < 3; ++ty) {
         const int yy = y + (ty - 1) * DIL;
         const bool y_ok = d_ok && yy >= 0 && yy < Hin;
+        const long rowo = (long)min(max(yy, 0), Hin - 1) * Win;
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
           // the RW input columns of this (frame, row, channel) are loaded once and feed the three horizontal taps of all PXF
-          // pixels (the first version re-loaded every tap: 3 * PXF loads for 8 * 3 * PXF FMAs)
+          // pixels (the first version re-loaded every tap: 3 * PXF loads for 8 * 3 * PXF FMAs).  Loads are unconditional from a
+          // clamped address and zeroed by a select: with `if (in range) load` every LDG sat in its own divergent region
+          // (BSSY / BRA / BSYNC) and its latency was paid serially - 3x the FMA time of the 27-tap first layer of KDLAE-S.
           float r[RW];
+          const float* src = (c < op.cin0) ? op.in0 + im * op.in0_img + (long)c * op.in0_ch
+                                           : op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch;
+          const long px = (c < op.cin0) ? 1 : op.in1_px;
+          const float* sub = (c < op.cin0 && op.sub0) ? op.sub0 + im * op.in0_img + (long)c * op.in0_ch : nullptr;
 #pragma unroll
           for (int j = 0; j < RW; ++j) {
             const int xx = x0 - DIL + j;
-            float t = 0.f;
-            if (y_ok && xx >= 0 && xx < Win) {
-              const long sp = (long)yy * Win + xx;
-              if (c < op.cin0) {
-                const long o = im * op.in0_img + (long)c * op.in0_ch + sp;
-                t = __ldg(op.in0 + o);
-                if (op.sub0) t -= __ldg(op.sub0 + o);
-              } else {
-                t = __ldg(op.in1 + im * op.in1_img + (long)(c - op.cin0) * op.in1_ch + sp * op.in1_px);
-              }
-            }
-            r[j] = t;
+            const bool ok = y_ok && xx >= 0 && xx < Win;
+            const long sp = (rowo + min(max(xx, 0), Win - 1)) * px;
+            float t = __ldg(src + sp);
+            if (sub) t -= __ldg(sub + sp);
+            r[j] = ok ? t : 0.f;
           }
 #pragma unroll
           for (int tx = 0; tx < 3; ++tx) {
@@ -621,20 +621,17 @@ int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s
 template int maxpool2x2<float>(const float*, float*, int, int, int, int, cudaStream_t);
 template int maxpool2x2<bf16>(const bf16*, bf16*, int, int, int, int, cudaStream_t);
 
+// grid (x chunks, output row, image): 32-bit index math only (the first version decoded a 64-bit linear index with three
+// 64-bit divisions per thread and ran at 1.8 TB/s)
 template <typename T>
-__global__ void __launch_bounds__(256) k_upsample2x(const T* __restrict__ x, T* __restrict__ out, int nimg, int H, int W, int C,
-                                                    int OH, int OW) {
-  const int cg = C / 8;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)nimg * OH * OW * cg;
-  if (idx >= total) return;
-  const int c = (int)(idx % cg) * 8; idx /= cg;
-  const int ox = (int)(idx % OW); idx /= OW;
-  const int oy = (int)(idx % OH);
-  const int img = (int)(idx / OH);
+__global__ void __launch_bounds__(256) k_upsample2x(const T* __restrict__ x, T* __restrict__ out, int H, int W, int C, int OH, int OW,
+                                                    float sy, float sx) {
+  const unsigned cg = (unsigned)C / 8;
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (unsigned)OW * cg) return;
+  const int c = (int)(e % cg) * 8, ox = (int)(e / cg);
+  const int oy = blockIdx.y, img = blockIdx.z;
   // align_corners=True: src = dst * (in-1)/(out-1)   (ASDQE_model.py:54)
-  const float sy = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
-  const float sx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const float fy = sy * oy, fx = sx * ox;
   const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
@@ -652,10 +649,11 @@ __global__ void __launch_bounds__(256) k_upsample2x(const T* __restrict__ x, T* 
 }
 template <typename T>
 int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s) {
-  KD_CHECK(C % 8 == 0, "upsample: C=%d", C);
-  const long total = (long)nimg * OH * OW * (C / 8);
+  KD_CHECK(C % 8 == 0 && OH <= 65535 && nimg <= 65535, "upsample: C=%d OH=%d nimg=%d", C, OH, nimg);
   ProfScope prof(PC_POOL_RESAMPLE, s, 0.0, (double)nimg * C * sizeof(T) * ((double)H * W + (double)OH * OW));
-  k_upsample2x<T><<<cdiv(total, 256), 256, 0, s>>>(x, out, nimg, H, W, C, OH, OW);
+  const float sy = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float sx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  k_upsample2x<T><<<dim3(cdiv((long)OW * (C / 8), 256), OH, nimg), 256, 0, s>>>(x, out, H, W, C, OH, OW, sy, sx);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -130,6 +130,10 @@ template <typename T> int pack_ln_cols(const PackOp& op, const float* lnb, float
 // depthwise weights [C][1][3][3] -> [9][Cdst] fp32 (optionally with the HALVES channel map)
 // x-packed 3x3 / 3x3x3 conv weights (see ConvOp::xpack_cin): src [cout][cin][kd*9] -> dst [P*cout][xconv_tiles][64] bf16
 // (centre tiles: block-Toeplitz over the P pixels of a super-pixel; halo tiles: the neighbours' edge pixels), bias replicated P x
+// dst [ng*c][taps][ng*c]: block g (rows and columns g*c .. g*c+c) <- src[g] [c][c][taps] * nscale[g][row]; zeros elsewhere.
+// Three independent c -> c convs on the channel slices of one tensor become one dense conv (ASDQE stems, ASDQE_model.py:133-137)
+template <typename T> int pack_blockdiag(const float* const* src, const float* const* nscale, int ng, int c, int taps, T* dst,
+                                         cudaStream_t s);
 int xconv_tiles(int kd, int cin);
 int pack_xconv(const float* src, const float* nscale, int cout, int cin, int kd, bf16* dst, cudaStream_t s);
 int pack_dw(const float* src, int c_src, int h, int hp, float* dst, int c_dst, cudaStream_t s);

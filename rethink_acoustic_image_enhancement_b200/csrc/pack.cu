@@ -49,6 +49,35 @@ int pack_weights(const PackOp& op, cudaStream_t s) {
 template int pack_weights<float>(const PackOp&, cudaStream_t);
 template int pack_weights<bf16>(const PackOp&, cudaStream_t);
 
+struct BlockDiagArgs { const float* src[4]; const float* nscale[4]; };
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack_blockdiag(const BlockDiagArgs a, int ng, int c, int taps, T* __restrict__ dst) {
+  const int N = ng * c;
+  const long total = (long)N * taps * N;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % N), t = (int)((idx / N) % taps), n = (int)(idx / ((long)N * taps));
+  const int g = n / c;
+  float v = 0.f;
+  if (k / c == g) {
+    v = a.src[g][((long)(n - g * c) * c + (k - g * c)) * taps + t];
+    if (a.nscale[g]) v *= a.nscale[g][n - g * c];
+  }
+  dst[idx] = from_f<T>(v);
+}
+template <typename T>
+int pack_blockdiag(const float* const* src, const float* const* nscale, int ng, int c, int taps, T* dst, cudaStream_t s) {
+  KD_CHECK(ng >= 1 && ng <= 4, "pack_blockdiag: ng=%d", ng);
+  BlockDiagArgs a;
+  for (int g = 0; g < 4; ++g) { a.src[g] = g < ng ? src[g] : nullptr; a.nscale[g] = (g < ng && nscale) ? nscale[g] : nullptr; }
+  const long total = (long)ng * c * taps * ng * c;
+  k_pack_blockdiag<T><<<cdiv(total, 256), 256, 0, s>>>(a, ng, c, taps, dst);
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+template int pack_blockdiag<float>(const float* const*, const float* const*, int, int, int, float*, cudaStream_t);
+template int pack_blockdiag<bf16>(const float* const*, const float* const*, int, int, int, bf16*, cudaStream_t);
+
 // ---- x-packed narrow conv (ConvOp::xpack_cin, conv3x3_tc.cu) -------------------------------------------------------------
 // P = 64 / cin pixels form one 64-channel super-pixel.  Output row n = j*cout + co (pixel j of the super-pixel), K column
 // k = i*cin + ci (pixel i).  Tile h = td*3 + ty (< 3*kd) is the centre tile of that (frame, row) tap: W[co][ci][h][dx = i - j]
