@@ -88,6 +88,21 @@ __device__ __forceinline__ void tld8(uint32_t a, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
 }
 
+// tcgen05.wait::ld that names the loaded registers as in/out operands, so no consumer can be scheduled above it
+template <int N>
+__device__ __forceinline__ void tld_wait(uint32_t (&r)[N]) {
+  static_assert(N == 10 || N == 12, "row width");
+  if constexpr (N == 12) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]) :: "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9])
+                 :: "memory");
+  }
+}
+
 constexpr int PT_IH = 8, PT_OH = 6, PT_MB = 128;     // halo rows, output rows, channels per item
 template <int GATE> struct PtCfg {
   static constexpr int PITCH = GATE ? 16 : 32;       // pixels per tile row (= TMEM columns per row)
@@ -111,6 +126,8 @@ struct PtParams {
   float inv_tiles_x, inv_tiles_y;
   const float* rstd;               // [nimg*H*W]
   const float* w9c;                // depthwise weights fp32 [9][Nt]
+  int xbufs;                       // x tile buffers: 2 when shared memory allows (the next tile loads and rescales under this one)
+  int dbg;                         // bring-up probes (KDLAE_PT_DBG): 1 = skip the output stores, 2 = skip the depthwise arithmetic
 };
 
 template <int GATE>
@@ -125,16 +142,23 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // smem (1024-aligned): W1 [kc][NH] chunks | x chunks | staging[2] | barriers
+  // W1 blocks are double buffered and the x tile too where it fits: with single buffers the per-item chain "GEMM retires ->
+  // W1 TMA -> GEMM" and the per-tile chain "GEMM retires -> x TMA -> rescale -> GEMM" ran back to back and the producer side
+  // alone took 55-70 % of the kernel time (KDLAE_PT_DBG=2 probe).
+  const uint32_t w1_bytes = p.kc * NH * W1CHUNK, x_bytes = p.kc * XCHUNK;
   const uint32_t w1_base = sbase;
-  const uint32_t x_base = w1_base + p.kc * NH * W1CHUNK;
-  const uint32_t stage_base = x_base + p.kc * XCHUNK;
+  const uint32_t x_base = w1_base + 2 * w1_bytes;
+  const uint32_t stage_base = x_base + p.xbufs * x_bytes;
   const uint32_t bar_base = stage_base + 2 * STAGE;
-  const uint32_t w_full = bar_base, w_empty = bar_base + 8, x_full = bar_base + 16, x_empty = bar_base + 24;
+  auto w_full = [&](int b) { return bar_base + 8u * b; };
+  auto w_empty = [&](int b) { return bar_base + 16 + 8u * b; };
+  auto x_full = [&](int b) { return bar_base + 112 + 8u * b; };
+  auto x_empty = [&](int b) { return bar_base + 128 + 8u * b; };
   // (Handing D[b] over in two-row chunks - the GEMM of item n+2 refilling rows the depthwise warps have moved past - was measured
   // 8-35 % SLOWER: four N = 64 MMAs re-read the A operand four times and every chunk costs each warp a tcgen05 fence pair.)
   auto d_full = [&](int b) { return bar_base + 32 + 8u * b; };
   auto d_empty = [&](int b) { return bar_base + 48 + 8u * b; };
-  const uint32_t x_scaled = bar_base + 64;
+  auto x_scaled = [&](int b) { return bar_base + 64 + 8u * b; };
   const uint32_t tmem_slot = bar_base + 96;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* x_gen = smem_raw + (x_base - smem_u32(smem_raw));
@@ -148,8 +172,9 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out); prefetch_tmap(&map_out_last);
-    mbar_init(w_full, 1); mbar_init(w_empty, 1); mbar_init(x_full, 1); mbar_init(x_empty, 1);
-    mbar_init(x_scaled, 2);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(w_full(b), 1); mbar_init(w_empty(b), 1); mbar_init(x_full(b), 1); mbar_init(x_empty(b), 1); mbar_init(x_scaled(b), 2);
+    }
     for (int b = 0; b < 2; ++b) { mbar_init(d_full(b), 1); mbar_init(d_empty(b), Cfg::NDW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,25 +208,28 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
             for (int k = 0; k < p.kc; ++k) tma_prefetch_4d(&map_x, k * 64, x0 - 1, y0 - 1, img);
           __syncwarp();
         }
-        mbar_wait_lazy(x_empty, (i & 1) ^ 1);        // last GEMM of tile i-1 retired
+        const int xb = (p.xbufs == 2) ? (i & 1) : 0;
+        const uint32_t xph = (p.xbufs == 2) ? ((i >> 1) & 1) : (i & 1);
+        mbar_wait_relaxed(x_empty(xb), xph ^ 1);     // last GEMM that read this x buffer has retired
         tile_xy(i, img, y0, x0);
         if (elect_one()) {
-          mbar_expect_tx(x_full, p.kc * XCHUNK);
-          for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + k * XCHUNK, &map_x, x_full, k * 64, x0 - 1, y0 - 1, img);
+          mbar_expect_tx(x_full(xb), p.kc * XCHUNK);
+          for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + xb * x_bytes + k * XCHUNK, &map_x, x_full(xb), k * 64, x0 - 1, y0 - 1, img);
         }
         __syncwarp();
         for (int cb = 0; cb < ncb; ++cb, ++n) {
-          mbar_wait_lazy(w_empty, (n & 1) ^ 1);      // GEMM n-1 retired: the W1 buffer is free
+          const int wb = n & 1;
+          mbar_wait_relaxed(w_empty(wb), ((n >> 1) & 1) ^ 1);      // GEMM n-2 retired: this W1 buffer is free
           // W1 rows arrive per TMEM lane quarter (32 rows): a partial last block only loads its valid quarters, rotated by the
           // tile index so that the extra work lands on a different scheduler every tile (see the depthwise warps)
           const int nvalid = min(PT_MB, p.Cout - cb * PT_MB);
           const int nq = (nvalid + 31) >> 5, rot = (nq < 4) ? (i & 3) : 0;
           if (elect_one()) {
-            mbar_expect_tx(w_full, p.kc * NH * nq * 4096);
+            mbar_expect_tx(w_full(wb), p.kc * NH * nq * 4096);
             for (int k = 0; k < p.kc; ++k)
               for (int h = 0; h < NH; ++h)
                 for (int lq = 0; lq < nq; ++lq)
-                  tma_load_3d(w1_base + (k * NH + h) * W1CHUNK + ((lq + rot) & 3) * 4096, &map_w1, w_full, k * 64,
+                  tma_load_3d(w1_base + wb * w1_bytes + (k * NH + h) * W1CHUNK + ((lq + rot) & 3) * 4096, &map_w1, w_full(wb), k * 64,
                               (GATE ? h * hp : 0) + cb * PT_MB + lq * 32, 0);
           }
           __syncwarp();
@@ -219,20 +247,22 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         for (int cb = 0; cb < ncb; ++cb, ++n) {
           const int b = n & 1;
           mbar_wait_relaxed(d_empty(b), ((n >> 1) & 1) ^ 1);   // depthwise warps have drained D[b] (item n-2): on the critical path
-          mbar_wait_relaxed(w_full, n & 1);
-          if (cb == 0) mbar_wait_relaxed(x_scaled, i & 1);   // x tile landed and rescaled by rstd
+          const int wb = n & 1;
+          const int xb = (p.xbufs == 2) ? (i & 1) : 0;
+          mbar_wait_relaxed(w_full(wb), (n >> 1) & 1);
+          if (cb == 0) mbar_wait_relaxed(x_scaled(xb), (p.xbufs == 2) ? ((i >> 1) & 1) : (i & 1));   // x tile landed and rescaled by rstd
           tc_fence_after();
           if (elect_one()) {
             for (int h = 0; h < NH; ++h) {
               for (int ks = 0; ks < ksteps; ++ks) {
                 const int k = ks >> 2, kk = ks & 3;
-                const uint32_t a_lo = (((w1_base + (k * NH + h) * W1CHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
-                const uint32_t b_lo = (((x_base + k * XCHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+                const uint32_t a_lo = (((w1_base + wb * w1_bytes + (k * NH + h) * W1CHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
+                const uint32_t b_lo = (((x_base + xb * x_bytes + k * XCHUNK + kk * 32) & 0x3FFFF) >> 4) | lo_tag;
                 umma_bf16_lohi(tmem_base + b * 256 + h * NPX, a_lo, b_lo, desc_hi, idesc, ks != 0 ? 1u : 0u);
               }
             }
-            umma_commit(w_empty);                       // W1 block consumed
-            if (cb == ncb - 1) umma_commit(x_empty);    // x tile consumed
+            umma_commit(w_empty(wb));                       // W1 block consumed
+            if (cb == ncb - 1) umma_commit(x_empty(xb));    // x tile consumed
             umma_commit(d_full(b));                     // accumulators ready
           }
           __syncwarp();
@@ -256,14 +286,15 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W;
         rsv[m] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;
       }
-      mbar_wait_relaxed(x_full, i & 1);
+      const int xb = (p.xbufs == 2) ? (i & 1) : 0;
+      mbar_wait_relaxed(x_full(xb), (p.xbufs == 2) ? ((i >> 1) & 1) : (i & 1));
       for (int k = 0; k < p.kc; ++k) {
         const int vch = min(8, (p.C - k * 64 + 7) >> 3);          // 16-byte pieces of this chunk that hold channels
 #pragma unroll
         for (int m = 0; m < NPX / 8; ++m) {
           const int pix = p0 + 8 * m;
           if ((pc ^ (pix & 7)) < vch) {
-            uint4* q = reinterpret_cast<uint4*>(x_gen + k * XCHUNK + pix * 128 + pc * 16);
+            uint4* q = reinterpret_cast<uint4*>(x_gen + xb * x_bytes + k * XCHUNK + pix * 128 + pc * 16);
             uint4 v = *q;
             const u64 r2 = splat2(rsv[m]);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v);
@@ -279,7 +310,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA's operand reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(x_scaled);
+      if (lane == 0) mbar_arrive(x_scaled(xb));
     }
   } else if (warp >= 4) {
     // ===================== depthwise warps =====================
@@ -307,6 +338,14 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
           if (lane == 0) mbar_arrive(d_empty(b));
           continue;
         }
+        if (p.dbg & 2) {                                     // probe: producer / GEMM pipeline alone
+          mbar_wait_relaxed(d_full(b), (n >> 1) & 1);
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty(b));
+          continue;
+        }
         const int ch = cb * PT_MB + lq * 32 + lane;
         const bool ch_ok = ch < p.Cout;
         u64 w[NH][9];
@@ -327,31 +366,35 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         const uint32_t trow = tmem_base + b * 256 + ((uint32_t)(quarter * 32) << 16) + s0;
         uint8_t* st = stage_gen + sb * STAGE + dwp * WSTAGE + lane * 2;
         u64 acc[NH][3][GP];
+        // Every accumulator value is pulled from TMEM ONCE (columns s0 .. s0+GW+1 of a row); the odd-aligned pairs of the middle
+        // tap are formed with register moves (a second, one-column-shifted tcgen05.ld was tried first: same speed, 2.2x the TMEM
+        // reads).  The loads are software pipelined: the row for step k+1 is requested before the FFMA2s of step k and waited
+        // for after them, so the TMEM latency hides under the arithmetic instead of stalling the warp eight times per item.
+        auto issue_row = [&](int step, uint32_t (&r)[GW + 2]) {
+          const uint32_t ta = trow + (step % NH) * NPX + (step / NH) * PITCH;
+          if (GATE) {
+            tld8(ta, r);
+            if (!last_g) tld2(ta + 8, r[8], r[9]); else { r[8] = 0; r[9] = 0; }
+          } else {
+            tld8(ta, r);
+            tld4(ta + 8, r[8], r[9], r[10], r[11]);
+          }
+        };
+        uint32_t rcur[GW + 2];
+        issue_row(0, rcur);
+        tld_wait(rcur);
 #pragma unroll
         for (int ir = 0; ir < PT_IH; ++ir) {
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
-            // A: columns s0 .. s0+GW+1 (even-aligned pairs), B: columns s0+1 .. s0+GW (odd-aligned pairs)
-            uint32_t ra[GW + 2], rb[GW];
-            const uint32_t ta = trow + h * NPX + ir * PITCH;
-            if (GATE) {
-              tld8(ta, ra);
-              if (!last_g) tld2(ta + 8, ra[8], ra[9]); else { ra[8] = 0; ra[9] = 0; }
-              tld4(ta + 1, rb[0], rb[1], rb[2], rb[3]);
-              if (!last_g) tld4(ta + 5, rb[4], rb[5], rb[6], rb[7]);
-              else { tld2(ta + 5, rb[4], rb[5]); rb[6] = 0; rb[7] = 0; }
-            } else {
-              tld8(ta, ra);
-              tld4(ta + 8, ra[8], ra[9], ra[10], ra[11]);
-              tld8(ta + 1, rb);
-              tld2(ta + 9, rb[8], rb[9]);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int step = ir * NH + h;
+            uint32_t rnext[GW + 2];
+            if (step + 1 < PT_IH * NH) issue_row(step + 1, rnext);
             u64 va[GP + 1], vb[GP];
 #pragma unroll
-            for (int j = 0; j < GP + 1; ++j) va[j] = pack2u(ra[2 * j], ra[2 * j + 1]);
+            for (int j = 0; j < GP + 1; ++j) va[j] = pack2u(rcur[2 * j], rcur[2 * j + 1]);
 #pragma unroll
-            for (int j = 0; j < GP; ++j) vb[j] = pack2u(rb[2 * j], rb[2 * j + 1]);
+            for (int j = 0; j < GP; ++j) vb[j] = pack2u(rcur[2 * j + 1], rcur[2 * j + 2]);
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int orow = ir - dy;
@@ -365,6 +408,11 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
                   acc[h][a][j] = ffma2(va[j + 1], w[h][dy * 3 + 2], acc[h][a][j]);
                 }
               }
+            }
+            if (step + 1 < PT_IH * NH) {
+              tld_wait(rnext);
+#pragma unroll
+              for (int j = 0; j < GW + 2; ++j) rcur[j] = rnext[j];
             }
           }
           if (ir == PT_IH - 1) {                  // all TMEM reads of this item done: the GEMM of item n+2 may overwrite D[b]
@@ -387,7 +435,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA store
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 1)) {
           const CUtensorMap* mo = (GATE && last_g) ? &map_out_last : &map_out;
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                        ::"l"(mo), "r"(stage_base + sb * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + lq * 32), "r"(x0 + s0), "r"(y0), "r"(img)
@@ -419,8 +467,11 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   KD_CHECK(p.ntiles_all < (1L << 24), "pwdw_t: too many tiles");
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.rstd = rstd; p.w9c = w9c;
+  { const char* e = getenv("KDLAE_PT_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int NH = GATE ? 2 : 1;
-  const uint32_t smem = 1024 + p.kc * NH * PT_MB * 128 + p.kc * Cfg::XCHUNK + 2 * Cfg::STAGE + 256;
+  const uint32_t fixed = 1024 + 2 * p.kc * NH * PT_MB * 128 + 2 * Cfg::STAGE + 256;
+  p.xbufs = (fixed + 2 * p.kc * Cfg::XCHUNK <= 232448) ? 2 : 1;
+  const uint32_t smem = fixed + p.xbufs * p.kc * Cfg::XCHUNK;
   KD_CHECK(smem <= 232448, "pwdw_t: shared memory budget exceeded (%u)", smem);
   static DeviceOnce once;
   bool first; int dev, g_pt_sms;

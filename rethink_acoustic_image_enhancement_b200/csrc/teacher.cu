@@ -225,7 +225,9 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   trace_point("blk.rstd2", sc.rstd, 1, rows * 4, rows * 4, s);
-  if (f2ok && fuse_t_ffn(fmode)) {
+  // default schedule (7): the GDFN pair goes through pwdw_f2 at C <= 64 and through the transposed kernel above that
+  // (scripts/pw_bench.py, 8 x 512^2: 96 -> 2x256: 1126-1146 us transposed vs 1260 us pwdw_f2; 48 -> 2x128: 720 vs 630 us)
+  if (f2ok && (fuse_t_ffn(fmode) || (fmode == 7 && C > 64))) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else if (f2ok && fuse_f2_ffn(fmode)) {
