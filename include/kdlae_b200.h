@@ -177,6 +177,26 @@ size_t kdlae_l1_sr_scratch_bytes(void);
 int kdlae_l1_sr_loss(const float* hq, const float* hq_gt, long n_hq, const float* sr, const float* sr_gt, long n_sr,
                      float loss_weight, float* loss, float* grad_hq, float* grad_sr, double* terms, void* scratch, void* stream);
 
+/* ---- training-step slice, fp32 reference-grade path -----------------------------------------------------
+ * GDFN half of a TransformerBlock (KDLAE_model.py:50-52,101-106,163): out = x + project_out(gelu(u[:h]) * u[h:]),
+ * u = dwconv3x3(project_in(BiasFree_LayerNorm(x))).  x, out, dout, dx: NHWC fp32 [nimg,H,W,C].  Weights in the packed layouts
+ * of the forward path: gamma [C]; w_in [2hp][C] (chunk(2) halves each padded from h to hp rows); w_dw [9][2hp]; w_out [C][hp].
+ * forward_train saves its intermediates in `ws` (kdlae_gdfn_train_ws_floats floats), backward consumes them and writes the
+ * gradients in the same layouts.  Replaces autograd through FeedForward + LayerNorm (image_restoration_model.py:198-216). */
+size_t kdlae_gdfn_train_ws_floats(int nimg, int H, int W, int C, int hp);
+int kdlae_gdfn_forward_train(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, float* out,
+                             int nimg, int H, int W, int C, int hp, float* ws, void* stream);
+int kdlae_gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
+                        float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp,
+                        float* ws, void* stream);
+/* Fused torch.nn.utils.clip_grad_norm_(params, max_norm) + AdamW step (image_restoration_model.py:218-220) over flat fp32
+ * buffers.  kdlae_grad_norm_sq: *norm_sq (device double) = sum g^2, scratch = 1024 device doubles.  kdlae_adamw_step: decoupled
+ * weight decay, bias-corrected moments; the clip coefficient min(1, max_norm / (sqrt(*norm_sq) + 1e-6)) is applied on the fly
+ * (norm_sq NULL or max_norm <= 0: no clipping).  step counts from 1. */
+int kdlae_grad_norm_sq(const float* grad, long n, double* norm_sq, double* scratch, void* stream);
+int kdlae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, float max_norm, const double* norm_sq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -401,6 +401,34 @@ int kdlae_l1_sr_loss(const float* hq, const float* hq_gt, long n_hq, const float
   return 0;
 }
 
+size_t kdlae_gdfn_train_ws_floats(int nimg, int H, int W, int C, int hp) {
+  return (nimg > 0 && H > 0 && W > 0 && C > 0 && hp > 0) ? kd::gdfn_train_ws_floats(nimg, H, W, C, hp) : 0;
+}
+int kdlae_gdfn_forward_train(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, float* out,
+                             int nimg, int H, int W, int C, int hp, float* ws, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && gamma && w_in && w_dw && w_out && out && ws, "kdlae_gdfn_forward_train: NULL argument");
+  return kd::gdfn_forward_train(x, gamma, w_in, w_dw, w_out, out, nimg, H, W, C, hp, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+int kdlae_gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
+                        float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp,
+                        float* ws, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && gamma && w_in && w_dw && w_out && dout && dx && dgamma && dw_in && dw_dw && dw_out && ws, "kdlae_gdfn_backward: NULL argument");
+  return kd::gdfn_backward(x, gamma, w_in, w_dw, w_out, dout, dx, dgamma, dw_in, dw_dw, dw_out, nimg, H, W, C, hp, ws,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+int kdlae_grad_norm_sq(const float* grad, long n, double* norm_sq, double* scratch, void* stream) {
+  API_BEGIN();
+  return kd::grad_norm_sq(grad, n, norm_sq, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+int kdlae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, float max_norm, const double* norm_sq, void* stream) {
+  API_BEGIN();
+  return kd::adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, max_norm, norm_sq,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
 int kdlae_debug_trace_begin(void) {
   API_BEGIN();
   if (!kd::g_trace_dev) KD_CUDA(cudaMalloc(&kd::g_trace_dev, sizeof(unsigned long long) * 2 * kd::TRACE_MAX));

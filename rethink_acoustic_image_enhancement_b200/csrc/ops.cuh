@@ -101,6 +101,18 @@ size_t l1_sr_scratch_bytes();
 int l1_shadow_term(const float* pred, const float* tgt, long n, float w_l1, float w_sh, int accumulate, float* loss, float* grad,
                    double* terms, void* scratch, cudaStream_t s);
 
+// training-step slice (train.cu): GDFN half of a TransformerBlock with saves + backward (fp32), fused
+// clip-norm + AdamW over flat buffers
+size_t gdfn_train_ws_floats(int nimg, int H, int W, int C, int hp);
+int gdfn_forward_train(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, float* out, int nimg,
+                       int H, int W, int C, int hp, float* ws, cudaStream_t s);
+int gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
+                  float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp, float* ws,
+                  cudaStream_t s);
+int grad_norm_sq(const float* g, long n, double* out, double* scratch, cudaStream_t s);
+int adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd, int step,
+               float max_norm, const double* norm_sq, cudaStream_t s);
+
 // pooling / resampling / misc glue
 template <typename T> int maxpool2x2(const T* x, T* out, int nimg, int H, int W, int C, cudaStream_t s);
 template <typename T> int upsample_bilinear2x(const T* x, T* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t s);

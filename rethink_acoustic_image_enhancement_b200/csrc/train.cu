@@ -1,0 +1,346 @@
+// First slice of the training step: forward-with-saves and backward of the GDFN half of a TransformerBlock,
+//     out = x + project_out( gelu(u[:h]) * u[h:] ),   u = dwconv3x3(project_in(LayerNorm(x)))          (KDLAE_model.py:50-52,101-106,163)
+// in the fp32 reference-grade path: NHWC fp32 activations, CUDA-core kernels, every sum in a fixed order (deterministic).
+// The 1x1 convs (forward and dgrad) reuse conv_gemm_simt, the depthwise conv and its dgrad reuse dwconv3x3 (dgrad = the same conv
+// with the taps reversed); new here: wgrad of the 1x1 convs (a pixel-reduction GEMM), wgrad of the depthwise conv, the GELU-gate
+// backward and the BiasFree LayerNorm backward with the residual add and the gamma gradient.  Weight layouts are the packed ones of
+// the forward path (project_in [2hp][C] with the two chunk(2) halves padded to hp, depthwise [9][2hp], project_out [C][hp]); the
+// Python wrapper (training.py) maps them from / to the reference's parameter shapes.
+// The end of the file holds the fused clip-norm + AdamW step over flat buffers.  tcgen05 dgrad / wgrad for the bf16 path and the
+// MDTA half of the block are the next steps of this row.
+#include <algorithm>
+#include "ops.cuh"
+
+namespace kd {
+
+namespace {
+
+constexpr int WG_T = 64, WG_P = 32;      // wgrad tile: 64 x 64 outputs, 32 pixels per step
+
+// part[split][n][k] = sum_{p in split} A[p][n] * B[p][k]     (A: [P][lda], B: [P][ldb])
+__global__ void __launch_bounds__(256) k_wgrad_part(const float* __restrict__ A, long lda, int N, const float* __restrict__ B, long ldb,
+                                                    int K, long P, int per, float* __restrict__ part) {
+  __shared__ float As[WG_P][WG_T + 4];
+  __shared__ float Bs[WG_P][WG_T + 4];
+  const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T, split = blockIdx.z;
+  const long p_begin = (long)split * per, p_end = min(P, p_begin + per);
+  const int tid = threadIdx.x, tn = (tid >> 4) * 4, tk = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long p0 = p_begin; p0 < p_end; p0 += WG_P) {
+    for (int e = tid; e < WG_P * WG_T; e += 256) {
+      const int pp = e / WG_T, c = e % WG_T;
+      const long p = p0 + pp;
+      As[pp][c] = (p < p_end && n0 + c < N) ? A[p * lda + n0 + c] : 0.f;
+      Bs[pp][c] = (p < p_end && k0 + c < K) ? B[p * ldb + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pp = 0; pp < WG_P; ++pp) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[pp][tn]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[pp][tk]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + tn + i < N && k0 + tk + j < K) part[((long)split * N + n0 + tn + i) * K + k0 + tk + j] = acc[i][j];
+}
+// out[e] = sum_split part[split][e]  (fixed order)
+__global__ void k_sum_parts(const float* __restrict__ part, int splits, long n, float* __restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(long)sp * n + e];
+  out[e] = s;
+}
+
+// depthwise wgrad: part[split][tap][c] = sum_{p in split} du[p][c] * t[p shifted by tap][c]   (zero padding)
+__global__ void __launch_bounds__(128) k_dw_wgrad_part(const float* __restrict__ du, const float* __restrict__ t, int nimg, int H, int W,
+                                                       int C, int per, float* __restrict__ part) {
+  const int c = blockIdx.x * 128 + threadIdx.x, split = blockIdx.y;
+  if (c >= C) return;
+  const long P = (long)nimg * H * W, p_begin = (long)split * per, p_end = min(P, p_begin + per);
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (long p = p_begin; p < p_end; ++p) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const float g = du[p * C + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc[k] = fmaf(g, t[(p + (long)(k / 3 - 1) * W + (k % 3 - 1)) * C + c], acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) part[((long)split * 9 + k) * C + c] = acc[k];
+}
+
+// y = x * rstd * gamma (BiasFree LayerNorm, x not centred)
+__global__ void k_ln_apply(const float* __restrict__ x, const float* __restrict__ rstd, const float* __restrict__ gamma, int C, long n,
+                           float* __restrict__ y) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  y[e] = x[e] * rstd[e / C] * gamma[e % C];
+}
+// g = gelu(u1) * u2
+__global__ void k_gate_fwd(const float* __restrict__ u, int hp, long P, float* __restrict__ g) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * hp) return;
+  const long p = e / hp; const int j = (int)(e % hp);
+  g[e] = gelu_erf(u[p * 2 * hp + j]) * u[p * 2 * hp + hp + j];
+}
+// du1 = dg * u2 * gelu'(u1), du2 = dg * gelu(u1);  gelu'(x) = Phi(x) + x * phi(x)
+__global__ void k_gate_bwd(const float* __restrict__ u, const float* __restrict__ dg, int hp, long P, float* __restrict__ du) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * hp) return;
+  const long p = e / hp; const int j = (int)(e % hp);
+  const float u1 = u[p * 2 * hp + j], u2 = u[p * 2 * hp + hp + j], d = dg[e];
+  const float Phi = 0.5f * (1.0f + erff(u1 * 0.70710678118654752440f));
+  const float phi = 0.39894228040143267794f * expf(-0.5f * u1 * u1);
+  du[p * 2 * hp + j] = d * u2 * (Phi + u1 * phi);
+  du[p * 2 * hp + hp + j] = d * (u1 * Phi);
+}
+// dx = dout + LN_backward(dy);  part_gamma[block][c] = sum over the block's pixels of dy_c * x_c * rstd
+// one warp per pixel; C <= 1024
+__global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ x, const float* __restrict__ rstd, const float* __restrict__ mu,
+                                                const float* __restrict__ gamma, const float* __restrict__ dy,
+                                                const float* __restrict__ dout, int C, long P, int pix_per_block,
+                                                float* __restrict__ dx, float* __restrict__ part_gamma) {
+  extern __shared__ float sg[];           // [8 warps][C] gamma-gradient partials
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = lane; c < C; c += 32) sg[warp * C + c] = 0.f;
+  const long p_begin = (long)blockIdx.x * pix_per_block, p_end = min(P, p_begin + pix_per_block);
+  for (long p = p_begin + warp; p < p_end; p += 8) {
+    const float r = rstd[p], m = mu[p];
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(dy[p * C + c] * gamma[c], x[p * C + c], s);
+    s = warp_sum(s);
+    const float k = -r * r * r * s / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xv = x[p * C + c], d = dy[p * C + c];
+      dx[p * C + c] = dout[p * C + c] + r * gamma[c] * d + k * (xv - m);
+      sg[warp * C + c] = fmaf(d * xv, r, sg[warp * C + c]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sg[w * C + c];
+    part_gamma[(long)blockIdx.x * C + c] = t;
+  }
+}
+__global__ void k_transpose(const float* __restrict__ a, int R, int Cc, float* __restrict__ out) {   // out[c][r] = a[r][c]
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)R * Cc) return;
+  const int r = (int)(e / Cc), c = (int)(e % Cc);
+  out[(long)c * R + r] = a[e];
+}
+__global__ void k_flip9(const float* __restrict__ w9c, int C, float* __restrict__ out) {              // out[t][c] = w9c[8 - t][c]
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * C) return;
+  out[e] = w9c[(8 - e / C) * C + e % C];
+}
+
+int wgrad_1x1(const float* A, long lda, int N, const float* B, long ldb, int K, long P, float* out, float* part, int splits,
+              cudaStream_t s) {
+  const int per = (int)((P + splits - 1) / splits);
+  ProfScope prof(PC_GEMM_SIMT, s, 2.0 * P * N * K, 4.0 * (double)P * (N + K));
+  k_wgrad_part<<<dim3(cdiv(N, WG_T), cdiv(K, WG_T), splits), 256, 0, s>>>(A, lda, N, B, ldb, K, P, per, part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sum_parts<<<cdiv((long)N * K, 256), 256, 0, s>>>(part, splits, (long)N * K, out);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv1x1_f32(const float* a, int C, const float* w, int N, const float* res, float* out, int nimg, int H, int W, cudaStream_t s) {
+  ConvOp g;
+  g.a0 = a; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.w = w; g.w_ld = C; g.w_tap_ld = C;
+  g.epi.res = res; g.epi.res_ld = N; g.epi.out = out; g.epi.out_ld = N; g.epi.N = N; g.epi.H = H; g.epi.W = W;
+  return conv_gemm_simt<float>(g, s);
+}
+
+struct GdfnWs {
+  float *rstd, *mu, *y, *t, *u, *g;                 // saved by the forward
+  float *dg, *du, *dt, *dy, *wt, *w9f, *part;       // backward scratch
+  size_t total;
+};
+constexpr int GD_SPLITS = 32, GD_LN_PIX = 256;
+
+GdfnWs gdfn_layout(float* base, int nimg, int H, int W, int C, int hp) {
+  const size_t P = (size_t)nimg * H * W;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
+  GdfnWs L;
+  L.rstd = take(P); L.mu = take(P); L.y = take(P * C); L.t = take(P * 2 * hp); L.u = take(P * 2 * hp); L.g = take(P * hp);
+  L.dg = take(P * hp); L.du = take(P * 2 * hp); L.dt = take(P * 2 * hp); L.dy = take(P * C);
+  L.wt = take((size_t)2 * hp * C); L.w9f = take((size_t)9 * 2 * hp);
+  const size_t ln_blocks = (P + GD_LN_PIX - 1) / GD_LN_PIX;
+  L.part = take(std::max<size_t>((size_t)GD_SPLITS * 2 * hp * std::max(C, 9), ln_blocks * C));
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+size_t gdfn_train_ws_floats(int nimg, int H, int W, int C, int hp) { return gdfn_layout(nullptr, nimg, H, W, C, hp).total; }
+
+int gdfn_forward_train(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, float* out, int nimg,
+                       int H, int W, int C, int hp, float* ws, cudaStream_t s) {
+  KD_CHECK(C % 8 == 0 && hp % 8 == 0 && C <= 1024, "gdfn_forward_train: C=%d hp=%d", C, hp);
+  const GdfnWs L = gdfn_layout(ws, nimg, H, W, C, hp);
+  const long P = (long)nimg * H * W;
+  KD_TRY(ln_stats<float>(x, C, C, P, L.rstd, L.mu, s));
+  k_ln_apply<<<cdiv(P * C, 256), 256, 0, s>>>(x, L.rstd, gamma, C, P * C, L.y);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(conv1x1_f32(L.y, C, w_in, 2 * hp, nullptr, L.t, nimg, H, W, s));
+  KD_TRY(dwconv3x3<float>(L.t, 2 * hp, L.u, 2 * hp, w_dw, nullptr, nimg, H, W, 2 * hp, 0, s));
+  k_gate_fwd<<<cdiv(P * hp, 256), 256, 0, s>>>(L.u, hp, P, L.g);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return conv1x1_f32(L.g, hp, w_out, C, x, out, nimg, H, W, s);
+}
+
+// dout [P][C] -> dx [P][C], dgamma [C], dw_in [2hp][C], dw_dw [9][2hp], dw_out [C][hp]; ws as left by gdfn_forward_train
+int gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
+                  float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp, float* ws,
+                  cudaStream_t s) {
+  const GdfnWs L = gdfn_layout(ws, nimg, H, W, C, hp);
+  const long P = (long)nimg * H * W;
+  const int splits = (int)std::min<long>(GD_SPLITS, std::max<long>(1, P / 256));
+  // project_out: wgrad and dgrad
+  KD_TRY(wgrad_1x1(dout, C, C, L.g, hp, hp, P, dw_out, L.part, splits, s));
+  k_transpose<<<cdiv((long)C * hp, 256), 256, 0, s>>>(w_out, C, hp, L.wt);                 // [hp][C]
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(conv1x1_f32(dout, C, L.wt, hp, nullptr, L.dg, nimg, H, W, s));
+  // gate
+  k_gate_bwd<<<cdiv(P * hp, 256), 256, 0, s>>>(L.u, L.dg, hp, P, L.du);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  // depthwise conv: wgrad, dgrad (= the conv with reversed taps)
+  {
+    const int per = (int)((P + splits - 1) / splits);
+    k_dw_wgrad_part<<<dim3(cdiv(2 * hp, 128), splits), 128, 0, s>>>(L.du, L.t, nimg, H, W, 2 * hp, per, L.part);
+    count_launch();
+    KD_LAUNCH_CHECK();
+    k_sum_parts<<<cdiv(9L * 2 * hp, 256), 256, 0, s>>>(L.part, splits, 9L * 2 * hp, dw_dw);
+    count_launch();
+    KD_LAUNCH_CHECK();
+  }
+  k_flip9<<<cdiv(9 * 2 * hp, 256), 256, 0, s>>>(w_dw, 2 * hp, L.w9f);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(dwconv3x3<float>(L.du, 2 * hp, L.dt, 2 * hp, L.w9f, nullptr, nimg, H, W, 2 * hp, 0, s));
+  // project_in: wgrad and dgrad
+  KD_TRY(wgrad_1x1(L.dt, 2 * hp, 2 * hp, L.y, C, C, P, dw_in, L.part, splits, s));
+  k_transpose<<<cdiv((long)2 * hp * C, 256), 256, 0, s>>>(w_in, 2 * hp, C, L.wt);           // [C][2hp]
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(conv1x1_f32(L.dt, 2 * hp, L.wt, C, nullptr, L.dy, nimg, H, W, s));
+  // LayerNorm backward + residual + gamma gradient
+  const int ln_blocks = (int)cdiv(P, GD_LN_PIX);
+  k_ln_bwd<<<ln_blocks, 256, sizeof(float) * 8 * C, s>>>(x, L.rstd, L.mu, gamma, L.dy, dout, C, P, GD_LN_PIX, dx, L.part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sum_parts<<<cdiv(C, 256), 256, 0, s>>>(L.part, ln_blocks, C, dgamma);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace kd
+
+// ---- fused gradient clipping + AdamW over flat fp32 buffers (image_restoration_model.py:218-220: clip_grad_norm_(params, 0.01),
+// then the AdamW step of KDLAET.yml) ----------------------------------------------------------------------------------------------
+// Parameters, gradients and both moments live in flat buffers (the same flat gradient buffer the bucketed NCCL all-reduce
+// works on), so the step is two passes: a deterministic sum of squares and one fused update that applies the clip
+// coefficient min(1, max_norm / (||g|| + 1e-6)) on the fly - the clipped gradient is never written back.
+namespace kd {
+namespace {
+__global__ void __launch_bounds__(256) k_sumsq_part(const float* __restrict__ g, long n, double* __restrict__ part) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  for (long i0 = (long)blockIdx.x * 2048; i0 < n; i0 += (long)gridDim.x * 2048) {
+    float t = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long i = i0 + u * 256 + threadIdx.x;
+      if (i < n) { const float v = g[i]; t = fmaf(v, v, t); }
+    }
+    s += (double)t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void k_sumsq_final(const double* __restrict__ part, int nblk, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int i = 0; i < nblk; ++i) t += part[i];
+  *out = t;
+}
+__global__ void __launch_bounds__(256) k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                               float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                                               float bc1, float bc2_sqrt, float max_norm, const double* __restrict__ norm_sq) {
+  float coef = 1.0f;
+  if (norm_sq != nullptr && max_norm > 0.f) {
+    const float total = (float)sqrt(*norm_sq);
+    coef = fminf(1.0f, max_norm / (total + 1e-6f));
+  }
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * coef;
+  float pi = p[i] * (1.0f - lr * wd);                      // decoupled weight decay
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+}  // namespace
+
+int grad_norm_sq(const float* g, long n, double* out, double* scratch /* 1024 doubles */, cudaStream_t s) {
+  KD_CHECK(g && out && scratch && n > 0, "grad_norm_sq: bad argument");
+  const int nblk = (int)std::min<long>(1024, (n + 2047) / 2048);
+  ProfScope prof(PC_POOL_RESAMPLE, s, 2.0 * n, 4.0 * n);
+  k_sumsq_part<<<nblk, 256, 0, s>>>(g, n, scratch);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sumsq_final<<<1, 32, 0, s>>>(scratch, nblk, out);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd, int step,
+               float max_norm, const double* norm_sq, cudaStream_t s) {
+  KD_CHECK(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad argument");
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  ProfScope prof(PC_POOL_RESAMPLE, s, 12.0 * n, 28.0 * n);
+  k_adamw<<<cdiv(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), max_norm, norm_sq);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace kd

@@ -1,0 +1,238 @@
+"""First slice of the KDLAE-T training step on the device, behind the C ABI.
+
+Mirrors, at the call boundary, what ``ImageCleanModel.optimize_parameters`` does around the network
+(Train/basicsr/models/image_restoration_model.py:198-224) and what DDP does for it (base_model.py:76-82):
+
+  * ``gdfn_block_train``    - the GDFN half of a TransformerBlock (``x + ffn(norm2(x))``, KDLAE_model.py:50-52,101-106,163) as an
+                              autograd function whose forward AND backward are CUDA kernels (kdlae_gdfn_forward_train / _backward);
+  * ``L1LossSr``            - in ``metrics.py`` (fused loss value + gradient);
+  * ``FlatAdamW``           - parameters, gradients and moments in flat fp32 buffers; ``clip_grad_norm_(params, 0.01)`` + AdamW as
+                              one reduction + one fused update (kdlae_grad_norm_sq / kdlae_adamw_step);
+  * ``BucketedAllReducer``  - the DDP gradient all-reduce: the flat gradient buffer is cut into buckets that are all-reduced
+                              (NCCL over NVLink on the GPU box, gloo in the CPU tests) on a side stream as soon as every
+                              gradient of a bucket has been produced, so communication overlaps the rest of the backward.
+PyTorch supplies tensors, streams, autograd bookkeeping and torch.distributed; the arithmetic is in libkdlae_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ceil8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GDFN half of a TransformerBlock with a CUDA backward
+# ------------------------------------------------------------------------------------------------------------------
+class _GdfnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, w_in, w_dw, w_out):
+        if not x.is_cuda:
+            raise RuntimeError("gdfn_block_train: expected CUDA tensors (there is no CPU path)")
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        h = w_out.shape[1]
+        hp = _ceil8(h)
+        dev = x.device
+        with torch.cuda.device(dev):
+            # layout plumbing (no arithmetic): NCHW -> NHWC, reference parameter shapes -> packed layouts of the forward path
+            xh = x.detach().float().permute(0, 2, 3, 1).contiguous()
+            g = gamma.detach().float().contiguous()
+            w2 = w_in.detach().float().view(2 * h, C)
+            win = torch.zeros(2 * hp, C, device=dev)
+            win[:h] = w2[:h]
+            win[hp:hp + h] = w2[h:]
+            d2 = w_dw.detach().float().view(2 * h, 9)
+            wdw = torch.zeros(9, 2 * hp, device=dev)
+            wdw[:, :h] = d2[:h].t()
+            wdw[:, hp:hp + h] = d2[h:].t()
+            wout = torch.zeros(C, hp, device=dev)
+            wout[:, :h] = w_out.detach().float().view(C, h)
+            out = torch.empty_like(xh)
+            ws = torch.empty(lib.kdlae_gdfn_train_ws_floats(B, H, W, C, hp), dtype=torch.float32, device=dev)
+            _lib.check(lib.kdlae_gdfn_forward_train(xh.data_ptr(), g.data_ptr(), win.data_ptr(), wdw.data_ptr(), wout.data_ptr(),
+                                                    out.data_ptr(), B, H, W, C, hp, ws.data_ptr(), _stream()), "kdlae_gdfn_forward_train")
+        ctx.save_for_backward(xh, g, win, wdw, wout, ws)
+        ctx.dims = (B, C, H, W, h, hp)
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xh, g, win, wdw, wout, ws = ctx.saved_tensors
+        B, C, H, W, h, hp = ctx.dims
+        lib = _lib.load()
+        dev = xh.device
+        with torch.cuda.device(dev):
+            dout = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()
+            dx = torch.empty_like(xh)
+            dg = torch.empty(C, device=dev)
+            dwin, dwdw, dwout = torch.empty_like(win), torch.empty_like(wdw), torch.empty_like(wout)
+            _lib.check(lib.kdlae_gdfn_backward(xh.data_ptr(), g.data_ptr(), win.data_ptr(), wdw.data_ptr(), wout.data_ptr(), dout.data_ptr(),
+                                               dx.data_ptr(), dg.data_ptr(), dwin.data_ptr(), dwdw.data_ptr(), dwout.data_ptr(),
+                                               B, H, W, C, hp, ws.data_ptr(), _stream()), "kdlae_gdfn_backward")
+        d_w_in = torch.cat([dwin[:h], dwin[hp:hp + h]]).view(2 * h, C, 1, 1)
+        d_w_dw = torch.cat([dwdw[:, :h].t(), dwdw[:, hp:hp + h].t()]).reshape(2 * h, 1, 3, 3)
+        d_w_out = dwout[:, :h].reshape(C, h, 1, 1)
+        return dx.permute(0, 3, 1, 2).contiguous(), dg, d_w_in, d_w_dw, d_w_out
+
+
+def gdfn_block_train(x: torch.Tensor, norm_weight: torch.Tensor, project_in_weight: torch.Tensor, dwconv_weight: torch.Tensor,
+                     project_out_weight: torch.Tensor) -> torch.Tensor:
+    """``x + FeedForward(BiasFree_LayerNorm(x))`` (KDLAE_model.py:163) with forward and backward in CUDA (fp32 path).
+    x [B,C,H,W]; parameters in the reference's shapes: norm2.body.weight [C], ffn.project_in.weight [2h,C,1,1],
+    ffn.dwconv.weight [2h,1,3,3], ffn.project_out.weight [C,h,1,1]."""
+    return _GdfnFn.apply(x, norm_weight, project_in_weight, dwconv_weight, project_out_weight)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# flat parameters + fused clip-norm / AdamW
+# ------------------------------------------------------------------------------------------------------------------
+class FlatAdamW:
+    """AdamW over ONE flat fp32 buffer (parameters are re-pointed to views of it, gradients accumulate into views of a flat
+    gradient buffer), with ``torch.nn.utils.clip_grad_norm_(params, max_norm)`` fused into the update.
+    Defaults follow Train/Denoising/Options/paper202508/KDLAET.yml (AdamW, lr 3e-4, betas (0.9, 0.999), weight_decay 1e-4) and
+    image_restoration_model.py:218-219 (clip at 0.01)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 3e-4, betas: Sequence[float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-4, max_norm: float = 0.01):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdamW: no trainable parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            self.offsets.append(off)
+            off += k
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, tuple(betas), eps, weight_decay, max_norm
+        self.steps = 0
+        if dev.type == "cuda":
+            self._norm_sq = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._scratch = torch.empty(1024, dtype=torch.float64, device=dev)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def grad_norm(self) -> torch.Tensor:
+        """Total gradient norm (device scalar) as clip_grad_norm_ computes it."""
+        self._require_cuda()
+        _lib.check(_lib.load().kdlae_grad_norm_sq(self.grad.data_ptr(), self.grad.numel(), self._norm_sq.data_ptr(),
+                                                  self._scratch.data_ptr(), _stream()), "kdlae_grad_norm_sq")
+        return self._norm_sq.sqrt()
+
+    def step(self) -> None:
+        self._require_cuda()
+        lib = _lib.load()
+        self.steps += 1
+        with torch.cuda.device(self.flat.device):
+            clip = self.max_norm is not None and self.max_norm > 0
+            if clip:
+                _lib.check(lib.kdlae_grad_norm_sq(self.grad.data_ptr(), self.grad.numel(), self._norm_sq.data_ptr(),
+                                                  self._scratch.data_ptr(), _stream()), "kdlae_grad_norm_sq")
+            _lib.check(lib.kdlae_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1],
+                                            self.eps, self.weight_decay, self.steps, float(self.max_norm or 0.0),
+                                            self._norm_sq.data_ptr() if clip else None, _stream()), "kdlae_adamw_step")
+
+    def _require_cuda(self) -> None:
+        if self.flat.device.type != "cuda":
+            raise RuntimeError("FlatAdamW: the fused update runs in CUDA only (there is no CPU path)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DDP gradient all-reduce over the flat gradient buffer
+# ------------------------------------------------------------------------------------------------------------------
+class BucketedAllReducer:
+    """Average a flat gradient buffer over the ranks in buckets (base_model.py:76-82 wraps the net in DDP; this is the same
+    collective, issued by hand over the flat buffer).  Buckets are filled from the END of the parameter list - the order in
+    which backward produces gradients - and each bucket's all-reduce is launched on a communication stream as soon as its last
+    gradient has been accumulated (``attach``), or all at once (``all_reduce``)."""
+
+    def __init__(self, flat_grad: torch.Tensor, bucket_bytes: int = 25 << 20, group: Optional[dist.ProcessGroup] = None):
+        self.flat, self.group = flat_grad, group
+        n, per = flat_grad.numel(), max(1, bucket_bytes // flat_grad.element_size())
+        self.bounds: List[tuple] = []
+        hi = n
+        while hi > 0:                       # bucket 0 = the tail of the buffer (first gradients to be ready)
+            lo = max(0, hi - per)
+            self.bounds.append((lo, hi))
+            hi = lo
+        self.comm_stream = torch.cuda.Stream(flat_grad.device) if flat_grad.is_cuda else None
+        self._pending: List = []
+        self._ready = [0] * len(self.bounds)
+        self._need = [0] * len(self.bounds)
+        self._hooks: List = []
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _launch(self, b: int) -> None:
+        lo, hi = self.bounds[b]
+        chunk = self.flat[lo:hi]
+        if self.world == 1:
+            return
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(self.comm_stream):
+                self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:                               # gloo (CPU tests): no AVG reduction
+            w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((w, chunk))
+
+    def all_reduce(self) -> None:
+        for b in range(len(self.bounds)):
+            self._launch(b)
+        self.wait()
+
+    def attach(self, params: Sequence[torch.nn.Parameter], offsets: Sequence[int]) -> None:
+        """Launch each bucket from autograd as soon as all gradients that end inside it have been accumulated."""
+        self._need = [0] * len(self.bounds)
+        owners = []
+        for p, off in zip(params, offsets):
+            end = off + p.numel()
+            bs = [i for i, (lo, hi) in enumerate(self.bounds) if lo < end and off < hi]     # every bucket the gradient overlaps
+            owners.append(bs)
+            for b in bs:
+                self._need[b] += 1
+        for p, bs in zip(params, owners):
+            def hook(_p, bs=bs):
+                for b in bs:
+                    self._ready[b] += 1
+                    if self._ready[b] == self._need[b]:
+                        self._launch(b)
+            self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+
+    def wait(self) -> None:
+        for w in self._pending:
+            if isinstance(w, tuple):
+                w[0].wait()
+                w[1].div_(self.world)
+            else:
+                w.wait()
+        self._pending.clear()
+        self._ready = [0] * len(self.bounds)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+
+
+__all__ = ["gdfn_block_train", "FlatAdamW", "BucketedAllReducer"]
