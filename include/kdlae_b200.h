@@ -189,6 +189,15 @@ int kdlae_gdfn_forward_train(const float* x, const float* gamma, const float* w_
 int kdlae_gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
                         float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp,
                         float* ws, void* stream);
+/* MDTA half of a TransformerBlock (KDLAE_model.py:124-145,162): out = x + project_out(softmax(q^ k^T * temperature) v), BiasFree
+ * LayerNorm in front.  gamma [C]; w_qkv [3C][C]; w_dw [9][3C]; w_proj [C][C]; temp [heads]; channels per head: multiple of 8, <= 96.
+ * Same workspace contract as the GDFN pair; gradients come back in the same layouts (dtemp [heads]). */
+size_t kdlae_mdta_train_ws_floats(int nimg, int H, int W, int C, int heads);
+int kdlae_mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj,
+                             const float* temp, float* out, int nimg, int H, int W, int C, int heads, float* ws, void* stream);
+int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                        const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg,
+                        int H, int W, int C, int heads, float* ws, void* stream);
 /* Fused torch.nn.utils.clip_grad_norm_(params, max_norm) + AdamW step (image_restoration_model.py:218-220) over flat fp32
  * buffers.  kdlae_grad_norm_sq: *norm_sq (device double) = sum g^2, scratch = 1024 device doubles.  kdlae_adamw_step: decoupled
  * weight decay, bias-corrected moments; the clip coefficient min(1, max_norm / (sqrt(*norm_sq) + 1e-6)) is applied on the fly

@@ -83,6 +83,9 @@ SIGNATURES = {
     "kdlae_gdfn_train_ws_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "kdlae_gdfn_forward_train": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "kdlae_gdfn_backward": (C.c_int, [C.c_void_p] * 11 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "kdlae_mdta_train_ws_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kdlae_mdta_forward_train": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "kdlae_mdta_backward": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "kdlae_grad_norm_sq": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdlae_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

@@ -418,6 +418,24 @@ int kdlae_gdfn_backward(const float* x, const float* gamma, const float* w_in, c
   return kd::gdfn_backward(x, gamma, w_in, w_dw, w_out, dout, dx, dgamma, dw_in, dw_dw, dw_out, nimg, H, W, C, hp, ws,
                            reinterpret_cast<cudaStream_t>(stream));
 }
+size_t kdlae_mdta_train_ws_floats(int nimg, int H, int W, int C, int heads) {
+  return (nimg > 0 && H > 0 && W > 0 && C > 0 && heads > 0 && C % heads == 0) ? kd::mdta_train_ws_floats(nimg, H, W, C, heads) : 0;
+}
+int kdlae_mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj,
+                             const float* temp, float* out, int nimg, int H, int W, int C, int heads, float* ws, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && gamma && w_qkv && w_dw && w_proj && temp && out && ws, "kdlae_mdta_forward_train: NULL argument");
+  return kd::mdta_forward_train(x, gamma, w_qkv, w_dw, w_proj, temp, out, nimg, H, W, C, heads, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                        const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg,
+                        int H, int W, int C, int heads, float* ws, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && gamma && w_qkv && w_dw && w_proj && temp && dout && dx && dgamma && dw_qkv && dw_dw && dw_proj && dtemp && ws,
+           "kdlae_mdta_backward: NULL argument");
+  return kd::mdta_backward(x, gamma, w_qkv, w_dw, w_proj, temp, dout, dx, dgamma, dw_qkv, dw_dw, dw_proj, dtemp, nimg, H, W, C, heads, ws,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
 int kdlae_grad_norm_sq(const float* grad, long n, double* norm_sq, double* scratch, void* stream) {
   API_BEGIN();
   return kd::grad_norm_sq(grad, n, norm_sq, scratch, reinterpret_cast<cudaStream_t>(stream));

@@ -109,6 +109,12 @@ int gdfn_forward_train(const float* x, const float* gamma, const float* w_in, co
 int gdfn_backward(const float* x, const float* gamma, const float* w_in, const float* w_dw, const float* w_out, const float* dout,
                   float* dx, float* dgamma, float* dw_in, float* dw_dw, float* dw_out, int nimg, int H, int W, int C, int hp, float* ws,
                   cudaStream_t s);
+size_t mdta_train_ws_floats(int nimg, int H, int W, int C, int heads);
+int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                       float* out, int nimg, int H, int W, int C, int heads, float* ws, cudaStream_t s);
+int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                  const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg, int H,
+                  int W, int C, int heads, float* ws, cudaStream_t s);
 int grad_norm_sq(const float* g, long n, double* out, double* scratch, cudaStream_t s);
 int adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd, int step,
                float max_norm, const double* norm_sq, cudaStream_t s);

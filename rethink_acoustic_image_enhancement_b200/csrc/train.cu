@@ -344,3 +344,270 @@ int adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, f
   return 0;
 }
 }  // namespace kd
+
+// ---- MDTA half of a TransformerBlock (KDLAE_model.py:124-145,162): out = x + project_out(softmax(q^ k^T * temp) v) ----------------
+//   q, k, v = chunk(dwconv3x3(qkv(LayerNorm(x))));  q^ = q / max(|q|, 1e-12) over the pixels of each (image, head, channel)
+// Forward keeps what the backward needs (y, t, u, o, the summed Gram / squared norms and the softmax).  The backward never forms a
+// per-pixel normalised q^, k^: with G^ = q^ k^T and dG^ = temp * dS,
+//   dq_i = sum_j dG^_ij / (|q_i| |k_j|) k_j - (sum_j dG^_ij G^_ij) / |q_i|^2 q_i        (and symmetrically for k),
+// so d(q, k) is ONE per-image 2C x 2C pixel-wise linear map of (q, k) - a grouped 1x1 GEMM - whose matrix a small kernel builds
+// from the ch x ch quantities.  dA = do v^T is the same pixel reduction as the forward Gram (mdta_gram on [do | v]).
+namespace kd {
+namespace {
+
+__global__ void k_sum_groups(const float* __restrict__ part, int splits, long psz, long total, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long g = i / psz, e = i % psz;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(g * splits + sp) * psz + e];
+  out[i] = s;
+}
+// grid (heads, nimg), one warp per softmax row: A = softmax(temp * G / (nq nk)); Ab / AbT = blockdiag(A) / its transpose [nimg][C][C]
+__global__ void __launch_bounds__(256) k_attn_softmax_train(const float* __restrict__ gs, int C, int heads, const float* __restrict__ temp,
+                                                            float* __restrict__ A, float* __restrict__ Ab, float* __restrict__ AbT) {
+  const int ch = C / heads, head = blockIdx.x, img = blockIdx.y;
+  const long psz = (long)ch * ch + 2 * ch;
+  const float* g = gs + ((long)img * heads + head) * psz;
+  float* a = A + ((long)img * heads + head) * ch * ch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float tp = temp[head];
+  for (int i = warp; i < ch; i += 8) {
+    const float nq = fmaxf(sqrtf(g[ch * ch + i]), 1e-12f);
+    float mx = -INFINITY;
+    for (int j = lane; j < ch; j += 32) {
+      const float l = g[i * ch + j] / (nq * fmaxf(sqrtf(g[ch * ch + ch + j]), 1e-12f)) * tp;
+      a[i * ch + j] = l;
+      mx = fmaxf(mx, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < ch; j += 32) { const float e = expf(a[i * ch + j] - mx); a[i * ch + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    const int n = head * ch + i;
+    __syncwarp();                    // the loop below reads a[] entries written by other lanes
+    for (int c = lane; c < C; c += 32) {
+      const int j = c - head * ch;
+      float v = 0.f;
+      if (j >= 0 && j < ch) { v = a[i * ch + j] * inv; a[i * ch + j] = v; }
+      Ab[((long)img * C + n) * C + c] = v;
+      AbT[((long)img * C + c) * C + n] = v;
+    }
+  }
+  // AbT rows outside this head's columns are written by the other heads' blocks (each block writes column range n of all rows c)
+}
+__global__ void k_copy_cols(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, int C, long P) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * C) return;
+  dst[(e / C) * ldd + e % C] = src[(e / C) * lds + e % C];
+}
+// grid (heads, nimg): softmax / temperature / normalisation backward on the ch x ch quantities; builds the per-image [2C][2C] matrix of
+// the d(q, k) map and the per-(image, head) temperature gradient.  dynamic smem: ch*ch floats (dG^) + 2*ch.
+__global__ void __launch_bounds__(256) k_attn_bwd_small(const float* __restrict__ gs, const float* __restrict__ A,
+                                                        const float* __restrict__ dAs, int C, int heads, const float* __restrict__ temp,
+                                                        float* __restrict__ Wqk, float* __restrict__ dtemp_part) {
+  extern __shared__ float sm[];
+  const int ch = C / heads, head = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const long psz = (long)ch * ch + 2 * ch;
+  const float* g = gs + ((long)img * heads + head) * psz;
+  const float* a = A + ((long)img * heads + head) * ch * ch;
+  const float* da = dAs + ((long)img * heads + head) * psz;      // first ch*ch entries: dA = do v^T
+  float* dG = sm;                 // [ch][ch]  temp * dS
+  float* sq = sm + ch * ch;       // [ch] s_i
+  float* rk = sq + ch;            // [ch] r_j
+  __shared__ float red[8];
+  const float tp = temp[head];
+  const int warp = tid >> 5, lane = tid & 31;
+  float dt_acc = 0.f;
+  for (int i = warp; i < ch; i += 8) {
+    float rd = 0.f;
+    for (int j = lane; j < ch; j += 32) rd = fmaf(a[i * ch + j], da[i * ch + j], rd);
+    rd = warp_sum(rd);
+    const float nq = fmaxf(sqrtf(g[ch * ch + i]), 1e-12f);
+    float si = 0.f;
+    for (int j = lane; j < ch; j += 32) {
+      const float nk = fmaxf(sqrtf(g[ch * ch + ch + j]), 1e-12f);
+      const float dS = a[i * ch + j] * (da[i * ch + j] - rd);
+      const float gh = g[i * ch + j] / (nq * nk);
+      dt_acc = fmaf(dS, gh, dt_acc);
+      const float dg = tp * dS;
+      dG[i * ch + j] = dg;
+      si = fmaf(dg, gh, si);
+    }
+    si = warp_sum(si);
+    if (lane == 0) sq[i] = si;
+  }
+  dt_acc = warp_sum(dt_acc);
+  if (lane == 0) red[warp] = dt_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dtemp_part[(long)img * heads + head] = t;
+  }
+  for (int j = tid; j < ch; j += 256) {
+    const float nk = fmaxf(sqrtf(g[ch * ch + ch + j]), 1e-12f);
+    float r = 0.f;
+    for (int i = 0; i < ch; ++i) r = fmaf(dG[i * ch + j], g[i * ch + j] / (fmaxf(sqrtf(g[ch * ch + i]), 1e-12f) * nk), r);
+    rk[j] = r;
+  }
+  __syncthreads();
+  // rows/cols of this head inside the [2C][2C] matrix (the buffer is zeroed beforehand)
+  float* Wm = Wqk + (long)img * 4 * C * C;
+  const int C2 = 2 * C, q0 = head * ch, k0 = C + head * ch;
+  for (int e = tid; e < ch * ch; e += 256) {
+    const int i = e / ch, j = e % ch;
+    const float nq = fmaxf(sqrtf(g[ch * ch + i]), 1e-12f), nk = fmaxf(sqrtf(g[ch * ch + ch + j]), 1e-12f);
+    const float m = dG[e] / (nq * nk);
+    Wm[(long)(q0 + i) * C2 + k0 + j] = m;     // dq_i += m * k_j
+    Wm[(long)(k0 + j) * C2 + q0 + i] = m;     // dk_j += m * q_i
+  }
+  for (int i = tid; i < ch; i += 256) {
+    const float nq2 = fmaxf(g[ch * ch + i], 1e-24f), nk2 = fmaxf(g[ch * ch + ch + i], 1e-24f);
+    Wm[(long)(q0 + i) * C2 + q0 + i] = -sq[i] / nq2;
+    Wm[(long)(k0 + i) * C2 + k0 + i] = -rk[i] / nk2;
+  }
+}
+__global__ void k_sum_dtemp(const float* __restrict__ part, int nimg, int heads, float* __restrict__ out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= heads) return;
+  float s = 0.f;
+  for (int i = 0; i < nimg; ++i) s += part[(long)i * heads + h];
+  out[h] = s;
+}
+__global__ void k_zero(float* __restrict__ p, long n) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) p[e] = 0.f;
+}
+
+struct MdtaWs {
+  float *rstd, *mu, *y, *t, *u, *o, *gs, *A, *Ab, *AbT;          // saved by the forward
+  float *dov, *dAs, *Wqk, *du, *dt, *dy, *wt, *w9f, *dtp, *part;  // backward scratch
+  size_t total;
+};
+MdtaWs mdta_layout(float* base, int nimg, int H, int W, int C, int heads) {
+  const size_t P = (size_t)nimg * H * W, ch = C / heads, psz = ch * ch + 2 * ch;
+  const int splits = mdta_gram_splits(H * W, nimg * heads);
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
+  MdtaWs L;
+  L.rstd = take(P); L.mu = take(P); L.y = take(P * C); L.t = take(P * 3 * C); L.u = take(P * 3 * C); L.o = take(P * C);
+  L.gs = take((size_t)nimg * heads * psz); L.A = take((size_t)nimg * heads * ch * ch);
+  L.Ab = take((size_t)nimg * C * C); L.AbT = take((size_t)nimg * C * C);
+  L.dov = take(P * 2 * C); L.dAs = take((size_t)nimg * heads * psz); L.Wqk = take((size_t)nimg * 4 * C * C);
+  L.du = take(P * 3 * C); L.dt = take(P * 3 * C); L.dy = take(P * C);
+  L.wt = take((size_t)3 * C * C); L.w9f = take((size_t)9 * 3 * C); L.dtp = take((size_t)nimg * heads);
+  const size_t ln_blocks = (P + GD_LN_PIX - 1) / GD_LN_PIX;
+  L.part = take(std::max<size_t>({(size_t)GD_SPLITS * 3 * C * std::max(C, 9), ln_blocks * C, (size_t)nimg * heads * splits * psz}));
+  L.total = off;
+  return L;
+}
+int grouped_1x1_f32(const float* a, int Cin, long lda, const float* w, int N, long w_group_stride, float* out, long ldo, int coff,
+                    int nimg, int H, int W, cudaStream_t s) {
+  ConvOp g;
+  g.a0 = a; g.c0 = Cin; g.ld0 = lda; g.nimg = nimg; g.H = H; g.W = W; g.w = w; g.w_ld = Cin; g.w_tap_ld = Cin;
+  g.groups = nimg; g.w_group_stride = w_group_stride;
+  g.epi.out = out; g.epi.out_ld = ldo; g.epi.out_coff = coff; g.epi.N = N; g.epi.H = H; g.epi.W = W;
+  return conv_gemm_simt<float>(g, s);
+}
+}  // namespace
+
+size_t mdta_train_ws_floats(int nimg, int H, int W, int C, int heads) { return mdta_layout(nullptr, nimg, H, W, C, heads).total; }
+
+int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                       float* out, int nimg, int H, int W, int C, int heads, float* ws, cudaStream_t s) {
+  const int ch = heads > 0 ? C / heads : 0;
+  KD_CHECK(heads > 0 && C % heads == 0 && ch % 8 == 0 && ch <= 96 && C <= 1024, "mdta_forward_train: C=%d heads=%d (channels per head <= 96)", C, heads);
+  const MdtaWs L = mdta_layout(ws, nimg, H, W, C, heads);
+  const long P = (long)nimg * H * W;
+  const int HW = H * W, splits = mdta_gram_splits(HW, nimg * heads);
+  const long psz = (long)ch * ch + 2 * ch;
+  KD_TRY(ln_stats<float>(x, C, C, P, L.rstd, L.mu, s));
+  k_ln_apply<<<cdiv(P * C, 256), 256, 0, s>>>(x, L.rstd, gamma, C, P * C, L.y);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(conv1x1_f32(L.y, C, w_qkv, 3 * C, nullptr, L.t, nimg, H, W, s));
+  KD_TRY(dwconv3x3<float>(L.t, 3 * C, L.u, 3 * C, w_dw, nullptr, nimg, H, W, 3 * C, 0, s));
+  KD_TRY(mdta_gram<float>(L.u, 3 * C, nimg, HW, C, heads, splits, L.part, s));
+  k_sum_groups<<<cdiv((long)nimg * heads * psz, 256), 256, 0, s>>>(L.part, splits, psz, (long)nimg * heads * psz, L.gs);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_attn_softmax_train<<<dim3(heads, nimg), 256, 0, s>>>(L.gs, C, heads, temp, L.A, L.Ab, L.AbT);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(grouped_1x1_f32(L.u + 2 * C, C, 3 * C, L.Ab, C, (long)C * C, L.o, C, 0, nimg, H, W, s));        // o = attn @ v
+  return conv1x1_f32(L.o, C, w_proj, C, x, out, nimg, H, W, s);                                          // + residual
+}
+
+int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
+                  const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg, int H,
+                  int W, int C, int heads, float* ws, cudaStream_t s) {
+  const int ch = C / heads;
+  const MdtaWs L = mdta_layout(ws, nimg, H, W, C, heads);
+  const long P = (long)nimg * H * W;
+  const int HW = H * W, gsplits = mdta_gram_splits(HW, nimg * heads);
+  const int splits = (int)std::min<long>(GD_SPLITS, std::max<long>(1, P / 256));
+  const long psz = (long)ch * ch + 2 * ch;
+  // project_out: wgrad, dgrad (do -> columns [0, C) of dov)
+  KD_TRY(wgrad_1x1(dout, C, C, L.o, C, C, P, dw_proj, L.part, splits, s));
+  k_transpose<<<cdiv((long)C * C, 256), 256, 0, s>>>(w_proj, C, C, L.wt);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  {
+    ConvOp g;
+    g.a0 = dout; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.w = L.wt; g.w_ld = C; g.w_tap_ld = C;
+    g.epi.out = L.dov; g.epi.out_ld = 2 * C; g.epi.N = C; g.epi.H = H; g.epi.W = W;
+    KD_TRY(conv_gemm_simt<float>(g, s));
+  }
+  k_copy_cols<<<cdiv(P * C, 256), 256, 0, s>>>(L.u + 2 * C, 3 * C, L.dov + C, 2 * C, C, P);              // v -> columns [C, 2C)
+  count_launch();
+  KD_LAUNCH_CHECK();
+  // dA = do v^T (pixel reduction), dv = A^T do
+  KD_TRY(mdta_gram<float>(L.dov, 2 * C, nimg, HW, C, heads, gsplits, L.part, s));
+  k_sum_groups<<<cdiv((long)nimg * heads * psz, 256), 256, 0, s>>>(L.part, gsplits, psz, (long)nimg * heads * psz, L.dAs);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(grouped_1x1_f32(L.dov, C, 2 * C, L.AbT, C, (long)C * C, L.du, 3 * C, 2 * C, nimg, H, W, s));
+  // softmax / temperature / normalisation backward -> per-image d(q, k) matrix, then one grouped GEMM on (q, k)
+  k_zero<<<cdiv((long)nimg * 4 * C * C, 256), 256, 0, s>>>(L.Wqk, (long)nimg * 4 * C * C);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_attn_bwd_small<<<dim3(heads, nimg), 256, sizeof(float) * (ch * ch + 2 * ch), s>>>(L.gs, L.A, L.dAs, C, heads, temp, L.Wqk, L.dtp);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sum_dtemp<<<cdiv(heads, 32), 32, 0, s>>>(L.dtp, nimg, heads, dtemp);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(grouped_1x1_f32(L.u, 2 * C, 3 * C, L.Wqk, 2 * C, 4L * C * C, L.du, 3 * C, 0, nimg, H, W, s));
+  // depthwise conv: wgrad, dgrad
+  {
+    const int per = (int)((P + splits - 1) / splits);
+    k_dw_wgrad_part<<<dim3(cdiv(3 * C, 128), splits), 128, 0, s>>>(L.du, L.t, nimg, H, W, 3 * C, per, L.part);
+    count_launch();
+    KD_LAUNCH_CHECK();
+    k_sum_parts<<<cdiv(27L * C, 256), 256, 0, s>>>(L.part, splits, 27L * C, dw_dw);
+    count_launch();
+    KD_LAUNCH_CHECK();
+  }
+  k_flip9<<<cdiv(27 * C, 256), 256, 0, s>>>(w_dw, 3 * C, L.w9f);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(dwconv3x3<float>(L.du, 3 * C, L.dt, 3 * C, L.w9f, nullptr, nimg, H, W, 3 * C, 0, s));
+  // qkv 1x1: wgrad, dgrad
+  KD_TRY(wgrad_1x1(L.dt, 3 * C, 3 * C, L.y, C, C, P, dw_qkv, L.part, splits, s));
+  k_transpose<<<cdiv(3L * C * C, 256), 256, 0, s>>>(w_qkv, 3 * C, C, L.wt);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  KD_TRY(conv1x1_f32(L.dt, 3 * C, L.wt, C, nullptr, L.dy, nimg, H, W, s));
+  const int ln_blocks = (int)cdiv(P, GD_LN_PIX);
+  k_ln_bwd<<<ln_blocks, 256, sizeof(float) * 8 * C, s>>>(x, L.rstd, L.mu, gamma, L.dy, dout, C, P, GD_LN_PIX, dx, L.part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sum_parts<<<cdiv(C, 256), 256, 0, s>>>(L.part, ln_blocks, C, dgamma);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace kd

@@ -3,6 +3,8 @@
 Mirrors, at the call boundary, what ``ImageCleanModel.optimize_parameters`` does around the network
 (Train/basicsr/models/image_restoration_model.py:198-224) and what DDP does for it (base_model.py:76-82):
 
+  * ``transformer_block_train`` = ``mdta_block_train`` + ``gdfn_block_train`` - a whole BiasFree TransformerBlock
+                              (KDLAE_model.py:159-163) whose forward AND backward are CUDA kernels;
   * ``gdfn_block_train``    - the GDFN half of a TransformerBlock (``x + ffn(norm2(x))``, KDLAE_model.py:50-52,101-106,163) as an
                               autograd function whose forward AND backward are CUDA kernels (kdlae_gdfn_forward_train / _backward);
   * ``L1LossSr``            - in ``metrics.py`` (fused loss value + gradient);
@@ -92,6 +94,64 @@ def gdfn_block_train(x: torch.Tensor, norm_weight: torch.Tensor, project_in_weig
     x [B,C,H,W]; parameters in the reference's shapes: norm2.body.weight [C], ffn.project_in.weight [2h,C,1,1],
     ffn.dwconv.weight [2h,1,3,3], ffn.project_out.weight [C,h,1,1]."""
     return _GdfnFn.apply(x, norm_weight, project_in_weight, dwconv_weight, project_out_weight)
+
+
+class _MdtaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, temperature, w_qkv, w_dw, w_proj):
+        if not x.is_cuda:
+            raise RuntimeError("mdta_block_train: expected CUDA tensors (there is no CPU path)")
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        heads = temperature.numel()
+        dev = x.device
+        with torch.cuda.device(dev):
+            xh = x.detach().float().permute(0, 2, 3, 1).contiguous()
+            g = gamma.detach().float().contiguous()
+            tp = temperature.detach().float().reshape(heads).contiguous()
+            wq = w_qkv.detach().float().view(3 * C, C).contiguous()
+            wd = w_dw.detach().float().view(3 * C, 9).t().contiguous()          # [9][3C]
+            wp = w_proj.detach().float().view(C, C).contiguous()
+            out = torch.empty_like(xh)
+            ws = torch.empty(lib.kdlae_mdta_train_ws_floats(B, H, W, C, heads), dtype=torch.float32, device=dev)
+            _lib.check(lib.kdlae_mdta_forward_train(xh.data_ptr(), g.data_ptr(), wq.data_ptr(), wd.data_ptr(), wp.data_ptr(), tp.data_ptr(),
+                                                    out.data_ptr(), B, H, W, C, heads, ws.data_ptr(), _stream()), "kdlae_mdta_forward_train")
+        ctx.save_for_backward(xh, g, tp, wq, wd, wp, ws)
+        ctx.dims = (B, C, H, W, heads, tuple(temperature.shape))
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xh, g, tp, wq, wd, wp, ws = ctx.saved_tensors
+        B, C, H, W, heads, tshape = ctx.dims
+        lib = _lib.load()
+        dev = xh.device
+        with torch.cuda.device(dev):
+            dout = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()
+            dx = torch.empty_like(xh)
+            dg, dtp = torch.empty(C, device=dev), torch.empty(heads, device=dev)
+            dwq, dwd, dwp = torch.empty_like(wq), torch.empty_like(wd), torch.empty_like(wp)
+            _lib.check(lib.kdlae_mdta_backward(xh.data_ptr(), g.data_ptr(), wq.data_ptr(), wd.data_ptr(), wp.data_ptr(), tp.data_ptr(),
+                                               dout.data_ptr(), dx.data_ptr(), dg.data_ptr(), dwq.data_ptr(), dwd.data_ptr(), dwp.data_ptr(),
+                                               dtp.data_ptr(), B, H, W, C, heads, ws.data_ptr(), _stream()), "kdlae_mdta_backward")
+        return (dx.permute(0, 3, 1, 2).contiguous(), dg, dtp.view(tshape), dwq.view(3 * C, C, 1, 1),
+                dwd.t().reshape(3 * C, 1, 3, 3), dwp.view(C, C, 1, 1))
+
+
+def mdta_block_train(x: torch.Tensor, norm_weight: torch.Tensor, temperature: torch.Tensor, qkv_weight: torch.Tensor,
+                     qkv_dwconv_weight: torch.Tensor, project_out_weight: torch.Tensor) -> torch.Tensor:
+    """``x + Attention(BiasFree_LayerNorm(x))`` (KDLAE_model.py:162) with forward and backward in CUDA (fp32 path).
+    Parameters in the reference's shapes: norm1.body.weight [C], attn.temperature [heads,1,1], attn.qkv.weight [3C,C,1,1],
+    attn.qkv_dwconv.weight [3C,1,3,3], attn.project_out.weight [C,C,1,1]."""
+    return _MdtaFn.apply(x, norm_weight, temperature, qkv_weight, qkv_dwconv_weight, project_out_weight)
+
+
+def transformer_block_train(x: torch.Tensor, p: dict, prefix: str) -> torch.Tensor:
+    """One BiasFree TransformerBlock (KDLAE_model.py:159-163) in training mode from a dict of the reference's parameters."""
+    x = mdta_block_train(x, p[prefix + ".norm1.body.weight"], p[prefix + ".attn.temperature"], p[prefix + ".attn.qkv.weight"],
+                         p[prefix + ".attn.qkv_dwconv.weight"], p[prefix + ".attn.project_out.weight"])
+    return gdfn_block_train(x, p[prefix + ".norm2.body.weight"], p[prefix + ".ffn.project_in.weight"], p[prefix + ".ffn.dwconv.weight"],
+                            p[prefix + ".ffn.project_out.weight"])
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -235,4 +295,4 @@ class BucketedAllReducer:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
 
 
-__all__ = ["gdfn_block_train", "FlatAdamW", "BucketedAllReducer"]
+__all__ = ["gdfn_block_train", "mdta_block_train", "transformer_block_train", "FlatAdamW", "BucketedAllReducer"]

@@ -101,6 +101,39 @@ def test_gdfn_backward_matches_oracle_autograd(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,heads", [((2, 48, 64, 64), 1), ((1, 96, 24, 40), 2), ((1, 96, 32, 32), 1)])
+def test_transformer_block_backward_matches_oracle_autograd(shape, heads):
+    """A whole BiasFree TransformerBlock (KDLAE_model.py:159-163): every gradient (input, LayerNorm weights, temperature, qkv,
+    depthwise, project_out, GDFN weights) from the CUDA backward vs autograd through oracle.functional in float64."""
+    from oracle import functional as ofn, synth
+    from rethink_acoustic_image_enhancement_b200.training import transformer_block_train
+    B, C, H, W = shape
+    sd = {}
+    synth._block(sd, "blk", C, 2.66, False, False, seed=5, temp_scale=4.0, heads=heads)
+    x = synth.seeded_tensor("train.xb", shape, 5, "normal")
+    dout = synth.seeded_tensor("train.doutb", shape, 6, "normal")
+    ref_p = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    p1 = {("stage.0" + k[3:]): v for k, v in ref_p.items()}
+    out_ref = ofn._blocks(xr, p1, "stage", 1, heads)
+    out_ref.backward(dout.double())
+    cu_p = {k: v.to(DEV).requires_grad_(True) for k, v in sd.items()}
+    xc = x.to(DEV).requires_grad_(True)
+    out = transformer_block_train(xc, cu_p, "blk")
+    out.backward(dout.to(DEV))
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    errs = {"out": rel(out.detach(), out_ref.detach()), "dx": rel(xc.grad, xr.grad)}
+    for k in sd:
+        assert cu_p[k].grad is not None and cu_p[k].grad.shape == sd[k].shape, k
+        errs[k] = rel(cu_p[k].grad, ref_p[k].grad)
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 1e-5, errs
+
+
+@pytest.mark.gpu
 def test_fused_clip_adamw_matches_torch():
     from rethink_acoustic_image_enhancement_b200.training import FlatAdamW
     torch.manual_seed(1)
