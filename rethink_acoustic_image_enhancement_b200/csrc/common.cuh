@@ -195,10 +195,11 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, long prow, in
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int n = n0 + i;
-    float t = v[i] * rs;
+    // explicit operation order (no compiler-chosen contraction): the fused pwdw_f2 conversion warps repeat it bit for bit
+    float t = __fmul_rn(v[i], rs);
     if (n < e.N) {
-      if (e.row_mu) t -= rmu * e.col_s1[n];
-      if (e.col_bias) t += e.col_bias[n];
+      if (e.row_mu) t = fmaf(-rmu, e.col_s1[n], t);
+      if (e.col_bias) t = __fadd_rn(t, e.col_bias[n]);
     }
     v[i] = t;
   }

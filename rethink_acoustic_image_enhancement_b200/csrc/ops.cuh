@@ -46,8 +46,10 @@ bool pwdw_t_eligible(int C, int Nt, int gate);   // transposed schedule (pwdw_t.
 int pwdw_t(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
            int H, int W, int C, int gate, cudaStream_t s);
 bool pwdw_f2_eligible(int C, int Nt, int gate);
+// mu / s1 / s2 (optional, together): WithBias LayerNorm fold, t = rstd * acc - rstd * mu[p] * s1[n] + s2[n] (pack_ln_cols)
 int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
-            int H, int W, int C, int gate, cudaStream_t s);
+            int H, int W, int C, int gate, cudaStream_t s, const float* mu = nullptr, const float* s1 = nullptr,
+            const float* s2 = nullptr);
 
 // MDTA reductions: partial Gram q k^T and squared norms per (image, head, split)
 // qk: [nimg*HW, ld] with q at channel 0 and k at channel C.  part: [nimg][heads][splits][ch*ch + 2*ch] fp32

@@ -45,6 +45,8 @@ struct PfParams {
   long ntiles_all;                 // spatial tiles (images x tiles_y x tiles_x)
   float inv_tiles_x, inv_tiles_y;
   const float* rstd;               // [nimg*H*W]
+  const float* mu;                 // WithBias LayerNorm (:67-70): per-pixel mean, and the two per-column fold vectors
+  const float* s1; const float* s2;   //   t = rstd * acc - rstd * mu * s1[n] + s2[n]   (pack_ln_cols)
   const float* w9c;                // depthwise weights fp32 [9][Nt]
   bf16* out; long ldo;
 };
@@ -101,7 +103,7 @@ __device__ __forceinline__ u64 gelu_gate2(u64 a, u64 b) {
   return fmul2(fmul2(a, pack2f(r0, r1)), b);
 }
 
-template <int GATE>
+template <int GATE, int WB>
 __global__ void __launch_bounds__(PfCfg<GATE>::THREADS, 1)
 k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1, const PfParams p) {
   constexpr int NH = GATE ? 2 : 1;
@@ -211,13 +213,15 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     for (int i = 0; i < ntiles; ++i) {
       int img, y0, x0;
       tile_xy(i, img, y0, x0);
-      float rs[2];
+      float rs[2], rmu[2], inside[2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int pix = mt * 128 + r;           // pixel of the 8 x 32 halo tile
         const int y = y0 - 1 + pix / PF_TW, x = x0 - 1 + pix % PF_TW;
         const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W;
         rs[mt] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;   // 0 outside: conv zero padding of t
+        rmu[mt] = (WB && inimg) ? __ldg(p.mu + ((long)img * p.H + y) * p.W + x) * rs[mt] : 0.f;
+        inside[mt] = inimg ? 1.f : 0.f;
       }
       for (int cb = 0; cb < ncb; ++cb, ++n) {
       const int b = n & 1;
@@ -252,10 +256,21 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
               const int o = (c4 & 1) * 8;
               uint4 w4;       // packed multiply by rstd (FMUL2), then one cvt.rn.bf16x2 per pair
               const u64 rs2 = splat2(rs[mt]);
-              const float2 f0 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1])), rs2));
-              const float2 f1 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), rs2));
-              const float2 f2 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])), rs2));
-              const float2 f3 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), rs2));
+              float2 f0 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1])), rs2));
+              float2 f1 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), rs2));
+              float2 f2 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])), rs2));
+              float2 f3 = as_float2(fmul2(pack2f(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), rs2));
+              if (WB) {       // WithBias LayerNorm fold, same operation order as the GEMM epilogue: (v*rs - rmu*s1[n]) + s2[n]
+                const int nb = (GATE ? h * hp : 0) + cb * PF_CB + half * 32 + c4 * 8;
+                float* ff[4] = {&f0.x, &f1.x, &f2.x, &f3.x};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float& t = ff[e >> 1][e & 1];
+                  const bool nok = nb + e < p.Nt;
+                  const float a1 = nok ? __ldg(p.s1 + nb + e) : 0.f, a2 = nok ? __ldg(p.s2 + nb + e) : 0.f;
+                  t = __fadd_rn(fmaf(-rmu[mt], a1, t), a2 * inside[mt]);
+                }
+              }
               w4.x = pack_bf16x2(f0.x, f0.y); w4.y = pack_bf16x2(f1.x, f1.y);
               w4.z = pack_bf16x2(f2.x, f2.y); w4.w = pack_bf16x2(f3.x, f3.y);
               const int chunk = half * 4 + c4;
@@ -356,6 +371,18 @@ k_pwdw_f2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   }
 }
 
+template <int GATE, int WB>
+int launch_pf(const CUtensorMap& map_x, const CUtensorMap& map_w1, const PfParams& p, int grid, uint32_t smem, cudaStream_t s) {
+  static DeviceOnce once;
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
+    KD_CUDA(cudaFuncSetAttribute(k_pwdw_f2<GATE, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    device_mark(once, dev);
+  }
+  k_pwdw_f2<GATE, WB><<<grid, PfCfg<GATE>::THREADS, smem, s>>>(map_x, map_w1, p);
+  return 0;
+}
 }  // namespace
 
 bool pwdw_f2_eligible(int C, int Nt, int gate) {
@@ -365,7 +392,8 @@ bool pwdw_f2_eligible(int C, int Nt, int gate) {
 // x [nimg,H,W,C] (row stride ldx) --1x1 (w1: [Nt][C] bf16, LayerNorm gamma folded), * rstd--> t --dw3x3 (w9c fp32 [9][Nt])
 // --> [gate] --> out (row stride ldo)
 int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, const float* w9c, bf16* out, long ldo, int nimg,
-            int H, int W, int C, int gate, cudaStream_t s) {
+            int H, int W, int C, int gate, cudaStream_t s, const float* mu, const float* s1, const float* s2) {
+  KD_CHECK((mu == nullptr) == (s1 == nullptr) && (mu == nullptr) == (s2 == nullptr), "pwdw_f2: mu, s1 and s2 go together");
   KD_CHECK(pwdw_f2_eligible(C, Nt, gate), "pwdw_f2: shape not eligible (C=%d Nt=%d)", C, Nt);
   KD_CHECK(!(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(out) & 3) && !(reinterpret_cast<uintptr_t>(w1) & 15) &&
                ldx % 8 == 0 && ldo % 2 == 0 && ldo < (1L << 28),
@@ -377,17 +405,10 @@ int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   p.ntiles_all = (long)nimg * p.tiles_x * p.tiles_y;
   KD_CHECK(p.ntiles_all < (1L << 24), "pwdw_f2: too many tiles");
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
-  p.rstd = rstd; p.w9c = w9c; p.out = out; p.ldo = ldo;
+  p.rstd = rstd; p.mu = mu; p.s1 = s1; p.s2 = s2; p.w9c = w9c; p.out = out; p.ldo = ldo;
   const int NH = gate ? 2 : 1;
   const uint32_t smem = 1024 + p.kc * NH * 8192 + p.kc * PF_XCHUNK + 2 * NH * PF_XCHUNK + 1024;
-  static DeviceOnce once;
-  bool first; int dev, g_pf_sms;
-  KD_TRY(device_first_use(once, &first, &dev));
-  if (first) {
-    KD_CUDA(cudaFuncSetAttribute(k_pwdw_f2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    KD_CUDA(cudaFuncSetAttribute(k_pwdw_f2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    device_mark(once, dev);
-  }
+  int g_pf_sms;
   KD_TRY(device_sms(&g_pf_sms));
   KD_CHECK(smem <= 232448, "pwdw_f2: shared memory budget exceeded (%u)", smem);
   CUtensorMap map_x, map_w1;
@@ -407,8 +428,10 @@ int pwdw_f2(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt, 
   const double pix = (double)nimg * H * W;
   ProfScope prof(PC_PWDW, s, 2.0 * pix * Nt * C + 18.0 * pix * Nt, pix * (C + p.Cout) * 2.0 + 4.0 * pix + 2.0 * Nt * C);
   const int grid = (int)std::min<long>(p.ntiles_all, (long)g_pf_sms);
-  if (gate) k_pwdw_f2<1><<<grid, PfCfg<1>::THREADS, smem, s>>>(map_x, map_w1, p);
-  else k_pwdw_f2<0><<<grid, PfCfg<0>::THREADS, smem, s>>>(map_x, map_w1, p);
+  int lr;
+  if (mu) lr = gate ? (launch_pf<1, 1>(map_x, map_w1, p, grid, smem, s)) : (launch_pf<0, 1>(map_x, map_w1, p, grid, smem, s));
+  else lr = gate ? (launch_pf<1, 0>(map_x, map_w1, p, grid, smem, s)) : (launch_pf<0, 0>(map_x, map_w1, p, grid, smem, s));
+  KD_TRY(lr);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -193,14 +193,16 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   trace_point("blk.rstd1", sc.rstd, 1, rows * 4, rows * 4, s);
   // bf16 + BiasFree LayerNorm: the 1x1 conv is fused into the tensor-core depthwise kernel (t never reaches HBM)
   const int fmode = fuse_pwdw_mode();
-  const bool f2ok = std::is_same<T, bf16>::value && !lnb && pwdw_f2_eligible(C, 3 * C, 0) && pwdw_f2_eligible(C, 2 * w.hp, 1);
+  // WithBias LayerNorm (the constructor default): only pwdw_f2 carries the mean / bias fold, so every fused mode maps to it
+  const bool f2ok = std::is_same<T, bf16>::value && pwdw_f2_eligible(C, 3 * C, 0) && pwdw_f2_eligible(C, 2 * w.hp, 1);
+  const bool wb_f2 = lnb && fmode != 0;
   ConvOp g;
-  if (f2ok && fuse_t_qkv(fmode)) {
+  if (f2ok && !lnb && fuse_t_qkv(fmode)) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
-  } else if (f2ok && fuse_f2_qkv(fmode)) {
+  } else if (f2ok && (fuse_f2_qkv(fmode) || wb_f2)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.wqkv), 3 * C, w.wdw_qkv,
-                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s));
+                   reinterpret_cast<bf16*>(sc.bufB), 3 * C, nimg, H, W, C, 0, s, lnb ? sc.mu : nullptr, w.qkv_s1, w.qkv_s2));
   } else {
     g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;
     g.w = w.wqkv; g.w_ld = C; g.w_tap_ld = C;
@@ -227,12 +229,12 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   trace_point("blk.rstd2", sc.rstd, 1, rows * 4, rows * 4, s);
   // default schedule (7): the GDFN pair goes through pwdw_f2 at C <= 64 and through the transposed kernel above that
   // (scripts/pw_bench.py, 8 x 512^2: 96 -> 2x256: 1126-1146 us transposed vs 1260 us pwdw_f2; 48 -> 2x128: 720 vs 630 us)
-  if (f2ok && (fuse_t_ffn(fmode) || (fmode == 7 && C > 64))) {
+  if (f2ok && !lnb && (fuse_t_ffn(fmode) || (fmode == 7 && C > 64))) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
-  } else if (f2ok && fuse_f2_ffn(fmode)) {
+  } else if (f2ok && (fuse_f2_ffn(fmode) || wb_f2)) {
     KD_TRY(pwdw_f2(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
-                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
+                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s, lnb ? sc.mu : nullptr, w.in_s1, w.in_s2));
   } else {
     g = ConvOp();
     g.a0 = x; g.c0 = C; g.ld0 = ldx; g.nimg = nimg; g.H = H; g.W = W;

@@ -221,6 +221,26 @@ def test_teacher_fused_conv1x1_dwconv_schedule_matches_reference(mode, manifest,
             assert torch.equal(out[key], base[key])
 
 
+def test_teacher_withbias_fused_matches_unfused(manifest, monkeypatch):
+    """WithBias LayerNorm (the constructor default) through the fused pwdw_f2 kernels (mean / bias fold in the conversion warps):
+    bit-identical to the unfused schedule and within the parity gate of the reference fixture."""
+    name = "teacher_c3_withbias_32x48"
+    case, g = manifest[name], load_golden(name)
+    m = _teacher(case["kwargs"], case["seed"], case["temp_scale"], "bf16")
+    b, h, w = case["shape"]
+    x = {"img": g["img"].to(DEV), "denoise_rate": g["rate"].view(b, 1, 1, 1).to(DEV)}
+    with torch.no_grad():
+        monkeypatch.setenv("KDLAE_FUSE_PWDW", "7")
+        fused = m(x)
+        monkeypatch.setenv("KDLAE_FUSE_PWDW", "0")
+        base = m(x)
+    for key in ("hq", "sr"):
+        p = synth.psnr(fused[key].cpu(), g[key])
+        print(f"WithBias fused {key}: psnr={p:.2f} dB, max|fused-unfused|={(fused[key] - base[key]).abs().max().item():.2e}")
+        assert p >= BF16_PSNR
+        assert torch.equal(fused[key], base[key])
+
+
 def test_teacher_repack_after_weight_update():
     kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no")
     m = _teacher(kw, 3, 1.0, "bf16")
