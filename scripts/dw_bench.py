@@ -1,5 +1,4 @@
-"""Depthwise 3x3 kernel variants on KDLAE-T shapes (batch 8): algorithmic GB/s.  KDLAE_DW=f2|tma picks the CUDA-core kernel
-behind kdlae_dwconv3x3; the tensor-core kernel is timed through kdlae_dwconv3x3_tc in the same process."""
+"""Stand-alone depthwise 3x3 kernel (dwconv_f2.cu, packed FFMA2) on KDLAE-T shapes (batch 8): algorithmic GB/s."""
 import os, sys, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rethink_acoustic_image_enhancement_b200 import _lib
@@ -14,22 +13,13 @@ for (n, H, W, C, gate) in SHAPES:
     w9c = (torch.randn(9, C, device="cuda") / 3).contiguous()
     Co = C // 2 if gate else C
     out = torch.empty(n, H, W, Co, dtype=torch.bfloat16, device="cuda")
-    out2 = torch.empty_like(out)
-    scratch = torch.empty(lib.kdlae_dwconv_tc_weight_bytes(C, gate), dtype=torch.uint8, device="cuda")
     nbytes = n * H * W * (C + Co) * 2
-    def run_cc():
-        _lib.check(lib.kdlae_dwconv3x3(x.data_ptr(), out.data_ptr(), w9c.data_ptr(), n, H, W, C, gate, 1, st), "dw")
-    def run_tc():
-        _lib.check(lib.kdlae_dwconv3x3_tc(x.data_ptr(), out2.data_ptr(), w9c.data_ptr(), scratch.data_ptr(), n, H, W, C, gate, st), "dwtc")
-    row = {}
-    for name, f in (("cuda_core", run_cc), ("tensor_core", run_tc)):
-        for _ in range(3): f()
-        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-        torch.cuda.synchronize(); a.record()
-        for _ in range(10): f()
-        b.record(); torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / 10
-        row[name] = dict(us=round(ms * 1e3, 1), GBs=round(nbytes / ms / 1e6, 0))
-    row["max_diff"] = (out.float() - out2.float()).abs().max().item()
-    res[str((n, H, W, C, gate))] = row
-print(json.dumps({"KDLAE_DW": os.environ.get("KDLAE_DW", "tma"), "shapes": res}, indent=1))
+    f = lambda: _lib.check(lib.kdlae_dwconv3x3(x.data_ptr(), out.data_ptr(), w9c.data_ptr(), n, H, W, C, gate, 1, st), "dw")
+    for _ in range(3): f()
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(10): f()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    res[str((n, H, W, C, gate))] = dict(us=round(ms * 1e3, 1), GBs=round(nbytes / ms / 1e6, 0))
+print(json.dumps(res, indent=1))
