@@ -281,6 +281,36 @@ def test_student_matches_reference_fixture(name, precision, manifest):
         assert p >= BF16_PSNR
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_student_and_asdqe_multi_tile_against_oracle(precision):
+    """Sizes that span several tiles of the x-packed convs: KDLAE-S at 3 x 36 x 256 (64 super-pixels of 4 pixels -> three 30-wide
+    tiles with a ragged last one, 32 super-pixels of 2 at the next level, ConvTranspose row phases over 2 tile rows) and ASDQE at
+    40 x 136 (padded to 48 x 144; the merged block-diagonal stem conv and the GAP-commuted head over several tiles)."""
+    ss = synth.student_state_dict(seed=8)
+    s = pk.KDLAE_student(residual=True)
+    s.load_state_dict(ss)
+    s = s.to(DEV).eval().set_precision(precision)
+    x = synth.seeded_tensor("multi.s", (2, 3, 36, 256), 8, "sonar")
+    with torch.no_grad():
+        ref = oracle.student_forward(ss, x, residual=True)
+        got = s(x.to(DEV)).cpu()
+    err, p = (got - ref).abs().max().item(), synth.psnr(got, ref)
+    print(f"student 2x3x36x256 {precision}: max|d|={err:.3e} psnr={p:.2f}")
+    assert (err <= FP32_TOL) if precision == "fp32" else (p >= BF16_PSNR)
+    sa = synth.asdqe_state_dict(seed=9)
+    a = pk.DenoiseRatePredictor()
+    a.load_state_dict(sa, strict=False)
+    a = a.to(DEV).eval().set_precision(precision)
+    lq = synth.seeded_tensor("multi.lq", (2, 3, 40, 136), 9)
+    gt = synth.seeded_tensor("multi.gt", (2, 3, 40, 136), 10)
+    with torch.no_grad():
+        ref_s = oracle.asdqe_forward(sa, lq, gt)
+        got_s = a(lq.to(DEV), gt.to(DEV)).cpu()
+    es = (got_s - ref_s).abs().max().item()
+    print(f"asdqe 2x3x40x136 {precision}: score max|d|={es:.3e}")
+    assert es <= 1e-3
+
+
 def test_student_rejects_bad_sizes():
     m = pk.KDLAE_student(residual=True).to(DEV).eval()
     with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 4"):
