@@ -17,7 +17,7 @@
 // the image edge), so the depthwise warps never synchronise with each other: with CTA-wide barriers per item they ran in
 // lockstep, all in their FFMA2 bursts at once (ncu: math-pipe throttle on top) and all idle together in the store phase.
 //   GATE = 0: tile = 8 x 32 pixels (6 x 30 outputs), item = (tile, 128 channels), D = 256 TMEM columns, double buffered.
-//   GATE = 1: tile = 8 x 16 pixels (6 x 14 outputs), item = (tile, 128 gated channels): x1 rows -> columns [0,128),
+//   GATE = 1: tile = 7 x 18 pixels (5 x 16 outputs), item = (tile, 128 gated channels): x1 rows -> columns [0,128),
 //             x2 rows -> columns [128,256), double buffered.
 // Warps: 0 TMA producer, 1 MMA issuer, 2-3 x-tile rescale, 4.. depthwise (TMEM lane quarter = warp % 4).
 #include <algorithm>
@@ -103,19 +103,26 @@ __device__ __forceinline__ void tld_wait(uint32_t (&r)[N]) {
   }
 }
 
-constexpr int PT_IH = 8, PT_OH = 6, PT_MB = 128;     // halo rows, output rows, channels per item
+constexpr int PT_MB = 128;                           // channels per item
 template <int GATE> struct PtCfg {
-  static constexpr int PITCH = GATE ? 16 : 32;       // pixels per tile row (= TMEM columns per row)
+  // The gate tile is 7 x 18 pixels (5 x 16 outputs): its 126 pixels fit the 128 TMEM columns a half may use, and the 16 output
+  // columns split into two groups of four pixel pairs with nothing left over (the earlier 8 x 16 tile gave 14 columns = 8 + 6,
+  // and the second group ran a fourth, discarded pair: 1/8 of the gate kernel's arithmetic).
+  static constexpr int IH = GATE ? 7 : 8;            // halo rows
+  static constexpr int OH = IH - 2;                  // output rows
+  static constexpr int PITCH = GATE ? 18 : 32;       // pixels per tile row (= TMEM columns per row)
   static constexpr int OW = PITCH - 2;               // output columns per tile
-  static constexpr int NPX = PITCH * PT_IH;          // pixels per tile = GEMM N
+  static constexpr int NPX_REAL = PITCH * IH;        // pixels per tile
+  static constexpr int NPX = (NPX_REAL + 15) / 16 * 16;   // GEMM N (gate: 126 -> 128, the two extra columns are never read)
   static constexpr int NG = GATE ? 2 : 3;            // column groups of depthwise warps
-  static constexpr int GP = GATE ? 4 : 5;            // output pixel pairs per group per row (gate: 8 + 6 columns; 16 warps of
-                                                     // 4 + 4 + 4 + 2 columns were measured 5 % slower)
+  static constexpr int GP = GATE ? 4 : 5;            // output pixel pairs per group per row
   static constexpr int NDW = NG * 4;                 // depthwise warps
   static constexpr int THREADS = (4 + NDW) * 32;
   static constexpr uint32_t XCHUNK = NPX * 128;      // one 64-channel K chunk of the x tile
-  static constexpr uint32_t WSTAGE = 2 * GP * PT_OH * 64;   // per-warp staging block [row][column][32 ch] bf16
+  static constexpr uint32_t XLOAD = NPX_REAL * 128;  // bytes TMA delivers into it
+  static constexpr uint32_t WSTAGE = 2 * GP * OH * 64;   // per-warp staging block [row][column][32 ch] bf16
   static constexpr uint32_t STAGE = NDW * WSTAGE;
+  static_assert(NG * 2 * GP == OW, "column groups must tile the output columns");
 };
 
 struct PtParams {
@@ -133,10 +140,11 @@ struct PtParams {
 template <int GATE>
 __global__ void __launch_bounds__(PtCfg<GATE>::THREADS, 1)
 k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-         const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out_last, const PtParams p) {
+         const __grid_constant__ CUtensorMap map_out, const PtParams p) {
   typedef PtCfg<GATE> Cfg;
   constexpr int NH = GATE ? 2 : 1;
   constexpr int PITCH = Cfg::PITCH, OW = Cfg::OW, NPX = Cfg::NPX, NG = Cfg::NG, GP = Cfg::GP, GW = 2 * GP;
+  constexpr int PT_IH = Cfg::IH, PT_OH = Cfg::OH;
   constexpr uint32_t XCHUNK = Cfg::XCHUNK, STAGE = Cfg::STAGE, WSTAGE = Cfg::WSTAGE;
   constexpr uint32_t W1CHUNK = PT_MB * 128;          // 128 rows x 64 channels of one chunk(2) half
   extern __shared__ uint8_t smem_raw[];
@@ -171,7 +179,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
   const int ncb = p.ncb;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out); prefetch_tmap(&map_out_last);
+    prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_out);
     for (int b = 0; b < 2; ++b) {
       mbar_init(w_full(b), 1); mbar_init(w_empty(b), 1); mbar_init(x_full(b), 1); mbar_init(x_empty(b), 1); mbar_init(x_scaled(b), 2);
     }
@@ -213,7 +221,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
         mbar_wait_relaxed(x_empty(xb), xph ^ 1);     // last GEMM that read this x buffer has retired
         tile_xy(i, img, y0, x0);
         if (elect_one()) {
-          mbar_expect_tx(x_full(xb), p.kc * XCHUNK);
+          mbar_expect_tx(x_full(xb), p.kc * Cfg::XLOAD);
           for (int k = 0; k < p.kc; ++k) tma_load_4d(x_base + xb * x_bytes + k * XCHUNK, &map_x, x_full(xb), k * 64, x0 - 1, y0 - 1, img);
         }
         __syncwarp();
@@ -283,7 +291,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
       for (int m = 0; m < NPX / 8; ++m) {
         const int pix = p0 + 8 * m;
         const int y = y0 - 1 + pix / PITCH, x = x0 - 1 + pix % PITCH;
-        const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W;
+        const bool inimg = y >= 0 && y < p.H && x >= 0 && x < p.W && pix < Cfg::NPX_REAL;
         rsv[m] = inimg ? __ldg(p.rstd + ((long)img * p.H + y) * p.W + x) : 0.f;
       }
       const int xb = (p.xbufs == 2) ? (i & 1) : 0;
@@ -318,8 +326,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
     const int quarter = warp & 3;                 // TMEM lane quarter (== dwp & 3)
     const int g = dwp >> 2;                       // column group
     const int s0 = g * GW;                        // first input column (tile coordinates) of this group
-    const bool last_g = (g == NG - 1);
-    const int gw = (GATE && last_g) ? OW - s0 : GW;     // output columns of this group (gate: 8, 6; otherwise 10 each)
+    constexpr int gw = GW;                        // output columns of every group
     uint32_t n = 0;
     uint32_t nstored = 0;                         // items this warp has stored: picks its staging block (see below)
     for (int i = 0; i < ntiles; ++i) {
@@ -374,7 +381,7 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
           const uint32_t ta = trow + (step % NH) * NPX + (step / NH) * PITCH;
           if (GATE) {
             tld8(ta, r);
-            if (!last_g) tld2(ta + 8, r[8], r[9]); else { r[8] = 0; r[9] = 0; }
+            tld2(ta + 8, r[8], r[9]);
           } else {
             tld8(ta, r);
             tld4(ta + 8, r[8], r[9], r[10], r[11]);
@@ -425,18 +432,16 @@ k_pwdw_t(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUte
 #pragma unroll
             for (int j = 0; j < GP; ++j) {
               const float2 f = as_float2(GATE ? gelu_gate2(acc[0][a][j], acc[NH - 1][a][j]) : acc[0][a][j]);
-              // output columns 2j, 2j+1 of this group; the last group of the gate tile is 6 columns wide
-              if (2 * j < gw) {
-                *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j) * 64) = __float2bfloat16_rn(f.x);
-                *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j + 1) * 64) = __float2bfloat16_rn(f.y);
-              }
+              // output columns 2j, 2j+1 of this group
+              *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j) * 64) = __float2bfloat16_rn(f.x);
+              *reinterpret_cast<__nv_bfloat16*>(st + (orow * gw + 2 * j + 1) * 64) = __float2bfloat16_rn(f.y);
             }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0 && !(p.dbg & 1)) {
-          const CUtensorMap* mo = (GATE && last_g) ? &map_out_last : &map_out;
+          const CUtensorMap* mo = &map_out;
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                        ::"l"(mo), "r"(stage_base + sb * STAGE + dwp * WSTAGE), "r"(cb * PT_MB + lq * 32), "r"(x0 + s0), "r"(y0), "r"(img)
                        : "memory");
@@ -462,7 +467,7 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   PtParams p;
   p.H = H; p.W = W; p.C = C; p.Nt = Nt; p.Cout = GATE ? Nt / 2 : Nt; p.nimg = nimg;
   p.kc = (C + 63) / 64;
-  p.tiles_x = cdiv(W, Cfg::OW); p.tiles_y = cdiv(H, PT_OH); p.ncb = cdiv(p.Cout, PT_MB);
+  p.tiles_x = cdiv(W, Cfg::OW); p.tiles_y = cdiv(H, Cfg::OH); p.ncb = cdiv(p.Cout, PT_MB);
   p.ntiles_all = (long)nimg * p.tiles_x * p.tiles_y;
   KD_CHECK(p.ntiles_all < (1L << 24), "pwdw_t: too many tiles");
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
@@ -481,11 +486,11 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
     device_mark(once, dev);
   }
   KD_TRY(device_sms(&g_pt_sms));
-  CUtensorMap map_x, map_w1, map_out, map_out_last;
+  CUtensorMap map_x, map_w1, map_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
     const cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H};
-    const cuuint32_t box[4] = {64, (cuuint32_t)Cfg::PITCH, PT_IH, 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)Cfg::PITCH, (cuuint32_t)Cfg::IH, 1};
     KD_TRY(make_map(&map_x, x, 4, dims, str, box));
   }
   {
@@ -497,15 +502,13 @@ int launch_pt(const bf16* x, long ldx, const float* rstd, const bf16* w1, int Nt
   {
     const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
     const cuuint64_t str[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)ldo * 2 * W, (cuuint64_t)ldo * 2 * W * H};
-    const cuuint32_t box[4] = {32, (cuuint32_t)(2 * Cfg::GP), PT_OH, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)(2 * Cfg::GP), (cuuint32_t)Cfg::OH, 1};
     KD_TRY(make_map(&map_out, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
-    const cuuint32_t box_last[4] = {32, (cuuint32_t)(Cfg::OW - (Cfg::NG - 1) * 2 * Cfg::GP), PT_OH, 1};
-    KD_TRY(make_map(&map_out_last, out, 4, dims, str, box_last, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
   const double pix = (double)nimg * H * W;
   ProfScope prof(PC_PWDW, s, 2.0 * pix * Nt * C + 18.0 * pix * Nt, pix * (C + p.Cout) * 2.0 + 4.0 * pix + 2.0 * Nt * C);
   const int grid = (int)std::min<long>(p.ntiles_all, (long)g_pt_sms);
-  k_pwdw_t<GATE><<<grid, Cfg::THREADS, smem, s>>>(map_x, map_w1, map_out, map_out_last, p);
+  k_pwdw_t<GATE><<<grid, Cfg::THREADS, smem, s>>>(map_x, map_w1, map_out, p);
   count_launch();
   KD_LAUNCH_CHECK();
   return 0;

@@ -164,12 +164,12 @@ struct Scratch {
 //   0  unfused (conv_gemm + dwconv3x3);
 //   3  both pairs through pwdw_f2.cu (tcgen05 1x1, packed-FFMA2 depthwise; bit-identical to unfused; stages with
 //      C > 128 or a WithBias LayerNorm stay unfused), 4 only qkv, 5 only ffn;
-//   6  both pairs through pwdw_t.cu (transposed GEMM, depthwise inputs read from TMEM in fp32), 7 (default) qkv via pwdw_t +
-//      ffn via pwdw_f2 (the fastest pairing measured: 94.6 vs 92.3 images/s for mode 3), 8 the other way round, 9 qkv via
-//      pwdw_t with the ffn pair unfused.
+//   6  (default) both pairs through pwdw_t.cu (transposed GEMM, depthwise inputs read from TMEM in fp32; with the 7 x 18 gate
+//      tile it is the faster kernel for every pair: scripts/pw_bench.py), 7 qkv via pwdw_t + ffn via pwdw_f2, 8 the other way
+//      round, 9 qkv via pwdw_t with the ffn pair unfused.
 inline int fuse_pwdw_mode() {
   const char* e = getenv("KDLAE_FUSE_PWDW");
-  return e ? atoi(e) : 7;
+  return e ? atoi(e) : 6;
 }
 inline bool fuse_f2_qkv(int m) { return m == 3 || m == 4 || m == 8; }
 inline bool fuse_f2_ffn(int m) { return m == 3 || m == 5 || m == 7; }
@@ -227,9 +227,8 @@ int run_block(const BlockW<T>& w, bool lnb, T* x, long ldx, T* xout, long ldo, i
   // ---- x = x + ffn(norm2(x)) ----
   if (!fused_stats) KD_TRY(ln_stats<T>(x, ldx, C, rows, sc.rstd, lnb ? sc.mu : nullptr, s));
   trace_point("blk.rstd2", sc.rstd, 1, rows * 4, rows * 4, s);
-  // default schedule (7): the GDFN pair goes through pwdw_f2 at C <= 64 and through the transposed kernel above that
-  // (scripts/pw_bench.py, 8 x 512^2: 96 -> 2x256: 1126-1146 us transposed vs 1260 us pwdw_f2; 48 -> 2x128: 720 vs 630 us)
-  if (f2ok && !lnb && (fuse_t_ffn(fmode) || (fmode == 7 && C > 64))) {
+  // (scripts/pw_bench.py, 8 x 512^2: 96 -> 2x256: 1008 us transposed vs 1270 us pwdw_f2; 48 -> 2x128: 590 vs 630 us)
+  if (f2ok && !lnb && fuse_t_ffn(fmode)) {
     KD_TRY(pwdw_t(reinterpret_cast<const bf16*>(x), ldx, sc.rstd, reinterpret_cast<const bf16*>(w.win), 2 * w.hp, w.wdw_ffn,
                   reinterpret_cast<bf16*>(sc.bufB), w.hp, nimg, H, W, C, 1, s));
   } else if (f2ok && (fuse_f2_ffn(fmode) || wb_f2)) {
