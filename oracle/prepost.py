@@ -2,7 +2,10 @@
 (KDLAE/KDLAE_T.ipynb cell 5; the cell is notebook code, not an importable function, so this restatement uses the same
 ATen / numpy operations in the same order: astype(float32)/255, permute, F.pad(..., 'reflect'), torch.ones * rate,
 torch.clamp, crop, skimage.img_as_ubyte == rint(x*255) for floats in [0,1], zero mask, np.repeat for the sr mask).
-Parity for this row is pinned by construction only (no reference fixture exists for it): "parity unpinned"."""
+Pinned: oracle/make_golden_prepost.py EXECUTES the cell's own source (read from the notebook at run time) on synthetic PNG
+files and froze its inputs / outputs in tests/golden/prepost.npz; this restatement reproduces them bit for bit
+(tests/test_prepost.py).  One caveat: scikit-image (requirements.txt:9, unpinned) is not installed in the build image, so the
+cell ran with a restatement of `img_as_ubyte`'s published float -> uint8 conversion (skimage/util/dtype.py `_convert`)."""
 import numpy as np
 import torch
 import torch.nn.functional as F

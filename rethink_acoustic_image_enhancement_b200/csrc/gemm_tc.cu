@@ -19,6 +19,7 @@
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 //   allocator, warps 2..9 epilogue, warp 10 residual-slab producer, warp 11 slab store issuer.
 //   mbarrier pipelines: smem ring full/empty, TMEM full/empty, slab full/empty (+ named barriers per slab).
+#include <algorithm>
 #include "sm100.cuh"
 
 namespace kd {
@@ -28,7 +29,8 @@ namespace {
 constexpr int TC_BM = 128;         // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;          // K elements per stage (one 128B swizzle atom of bf16)
 constexpr int TC_NC_MAX = 256;     // max N per accumulator (UMMA N)
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;        // ring depth with a full-width (256-column) weight tile per stage
+constexpr int TC_MAX_STAGES = 8;    // narrower weight tiles shrink the stage and deepen the ring inside the same bytes
 constexpr int TC_NSLAB = 4;        // output slabs of 128 rows x 64 columns
 constexpr int TC_TW = 16, TC_TH = 8;   // spatial tile of the 3x3 path
 constexpr int TC_EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column quarters of a 64-column slab
@@ -38,7 +40,8 @@ constexpr uint32_t TC_B_BYTES = TC_NC_MAX * TC_BK * 2;
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_SLAB_BYTES = TC_BM * 64 * 2;
 constexpr uint32_t TC_STAT_BYTES = TC_NSLAB * 4 * TC_BM * 2 * 4;   // [slab buffer][column quarter][row]{sum, sum of squares}
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_NSLAB * TC_SLAB_BYTES + TC_STAT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;
+constexpr uint32_t TC_SMEM_BYTES = TC_RING_BYTES + TC_NSLAB * TC_SLAB_BYTES + TC_STAT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_STORE_BAR_THREADS = TC_EPI_WARPS * 32 + 32;
 
 struct TcParams {
@@ -50,6 +53,9 @@ struct TcParams {
   int c0;               // weight column offset of source 1
   long w_tap_ld;
   int n_chunks, nc;     // N split
+  int stages;           // ring depth: TC_RING_BYTES / (A tile + nc weight rows), at most TC_MAX_STAGES.  The write- and
+                        // read-heavy 1x1 GEMMs are HBM bound and three 16 KB A tiles in flight per SM do not cover the latency
+  uint32_t stage_bytes;
   long items;           // tiles_m * n_chunks
   // linear mode
   long rows_per_group;
@@ -111,16 +117,16 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_res, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t slab_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t slab_base = smem_base + TC_RING_BYTES;
   const uint32_t stat_base = slab_base + TC_NSLAB * TC_SLAB_BYTES;
   const uint32_t bar_base = stat_base + TC_STAT_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + b); };
-  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + TC_NSLAB + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 2 * TC_NSLAB);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_MAX_STAGES + 4 + b); };
+  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_MAX_STAGES + 4 + TC_NSLAB + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4 + 2 * TC_NSLAB);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* slab_gen = smem_raw + (slab_base - smem_u32(smem_raw));
@@ -133,7 +139,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (p.kc1 > 0) prefetch_tmap(&map_a1);
     prefetch_tmap(&map_w);
     if (FAST) { prefetch_tmap(&map_out); if (p.has_res) prefetch_tmap(&map_res); }
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
     for (int b = 0; b < TC_NSLAB; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +161,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer (A and W tiles): warp-uniform loop, elected issuer (see elect_one()) =====================
     {
-      uint32_t kidx = 0;
+      int s = 0; uint32_t ph = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const TileCoord t = tile_coord(p, item);
         int fb = 0, fd = 0;                       // 3-D: batch element and frame of this tile's image index
@@ -163,11 +169,9 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dx = (tap % p.kw - p.kw / 2) * p.dil, dy = ((tap / p.kw) % 3 - p.kw / 2) * p.dil;
           const int dd = (p.kd == 3) ? tap / 9 - 1 : 0;
-          for (int kc = 0; kc < kchunks; ++kc, ++kidx) {
-            const int s = kidx % TC_STAGES;
-            const uint32_t ph = (kidx / TC_STAGES) & 1;
+          for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait_relaxed(empty_bar(s), ph ^ 1);
-            const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
+            const uint32_t a_dst = smem_base + s * p.stage_bytes;
             const uint32_t b_dst = a_dst + TC_A_BYTES;
             const bool src1 = kc >= p.kc0;
             const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
@@ -181,6 +185,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               tma_load_3d(b_dst, &map_w, full_bar(s), wk, t.nchunk * p.nc, t.g);
             }
             __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -189,18 +194,17 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
     {
       const uint32_t idesc = make_idesc(p.nc);
-      uint32_t kidx = 0, it = 0;
+      uint32_t it = 0;
+      int s = 0; uint32_t ph = 0;
       for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1, aph = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_NC_MAX;
-        for (int kb = 0; kb < kblocks; ++kb, ++kidx) {
-          const int s = kidx % TC_STAGES;
-          const uint32_t ph = (kidx / TC_STAGES) & 1;
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + s * TC_STAGE_BYTES;
+          const uint32_t a_addr = smem_base + s * p.stage_bytes;
           const uint32_t b_addr = a_addr + TC_A_BYTES;
           if (elect_one()) {
 #pragma unroll
@@ -212,6 +216,7 @@ k_conv_gemm_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             umma_commit(empty_bar(s));      // frees the smem stage when these MMAs retire
           }
           __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(tfull_bar(acc));      // accumulator complete
         __syncwarp();
@@ -489,6 +494,9 @@ int conv_gemm_tc(const ConvOp& op, cudaStream_t s) {
   p.c0 = op.c0;
   p.w_tap_ld = op.w_tap_ld;
   p.nc = pick_nc(op.epi.N, &p.n_chunks);
+  p.stage_bytes = TC_A_BYTES + (uint32_t)p.nc * TC_BK * 2;       // nc % 16 == 0: the weight tile keeps the 1024-byte alignment
+  p.stages = (int)std::min<uint32_t>(TC_RING_BYTES / p.stage_bytes, TC_MAX_STAGES);
+  { const char* e = getenv("KDLAE_TC_STAGES"); if (e && atoi(e) >= 2) p.stages = std::min(p.stages, atoi(e)); }   // A/B probe
   p.H = op.H; p.W = op.W;
   p.epi = op.epi;
   const Epilogue& e = op.epi;

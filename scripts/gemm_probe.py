@@ -8,7 +8,8 @@ st = torch.cuda.current_stream().cuda_stream
 res = {}
 for name, S, C, N, has_res in [("L1 qkv 48->144", 512, 48, 144, 0), ("L1 project_in 48->256", 512, 48, 256, 0),
                                ("L1 project_out 128->48 +res", 512, 128, 48, 1), ("L2 qkv 96->288", 256, 96, 288, 0),
-                               ("L2 project_out 256->96 +res", 256, 256, 96, 1)]:
+                               ("L2 project_out 256->96 +res", 256, 256, 96, 1), ("L1 attn apply 96->96 +res", 512, 96, 96, 1),
+                               ("L1 project_out 256->96 +res", 512, 256, 96, 1)]:
     n = 8
     x = torch.randn(n, S, S, C, device="cuda").bfloat16()
     w = (torch.randn(N, C, device="cuda") / C ** 0.5).bfloat16()
@@ -25,4 +26,4 @@ for name, S, C, N, has_res in [("L1 qkv 48->144", 512, 48, 144, 0), ("L1 project
     ms = a.elapsed_time(b) / 10
     nbytes = n * S * S * (C + N * (2 if has_res else 1)) * 2
     res[name] = dict(us=round(ms * 1e3, 1), GBs=round(nbytes / ms / 1e6))
-print(json.dumps({"sm_limit": os.environ.get("KDLAE_SM_LIMIT", "all"), **res}))
+print(json.dumps({"sm_limit": os.environ.get("KDLAE_SM_LIMIT", "all"), "tc_stages": os.environ.get("KDLAE_TC_STAGES", "auto"), **res}))

@@ -1,4 +1,7 @@
-"""uint8 pre / post-processing: oracle restatement on CPU, CUDA passes bit-exact against it on the GPU."""
+"""uint8 pre / post-processing: oracle restatement on CPU against the outputs of the reference's own notebook
+cell (tests/golden/prepost.npz, frozen by oracle/make_golden_prepost.py), CUDA passes bit-exact against both on the GPU."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +10,43 @@ import torch.nn.functional as F
 from oracle import prepost as op
 
 DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepost.npz")
+
+
+def _golden_cases():
+    z = np.load(GOLDEN)
+    for ci in range(int(z["n_cases"])):
+        yield ci, {k[len(f"c{ci}_"):]: z[k] for k in z.files if k.startswith(f"c{ci}_")}
+
+
+def test_oracle_prepost_reproduces_the_reference_cell():
+    """oracle/prepost.py against what KDLAE_T.ipynb cell 5 itself produced (padded input, rate map shape, uint8 hq / sr)."""
+    n = 0
+    for ci, c in _golden_cases():
+        img, rate = c["img"], float(c["rate"])
+        x, alpha = op.preprocess_u8(img[None], rate)
+        assert np.array_equal(x.numpy(), c["x"]), f"case {ci}: padded input"
+        assert tuple(alpha.shape) == tuple(c["alpha_shape"]) and torch.all(alpha == np.float32(rate))
+        assert np.array_equal(op.postprocess_u8(torch.from_numpy(c["pred_hq"]), img[None], 1)[0], c["hq_u8"]), f"case {ci}: hq"
+        assert np.array_equal(op.postprocess_u8(torch.from_numpy(c["pred_sr"]), img[None], 2)[0], c["sr_u8"]), f"case {ci}: sr"
+        n += 1
+    assert n == 4
+
+
+@pytest.mark.gpu
+def test_prepost_kernels_reproduce_the_reference_cell():
+    """The CUDA passes against the reference cell's frozen outputs, bit for bit."""
+    import rethink_acoustic_image_enhancement_b200 as pk
+    for ci, c in _golden_cases():
+        img, rate = c["img"], float(c["rate"])
+        img_d = torch.from_numpy(img[None].copy()).to(DEV)
+        x, a = pk.preprocess_u8(img_d, torch.tensor([rate]), rate_map=True)
+        assert np.array_equal(x.cpu().numpy(), c["x"]), f"case {ci}: padded input"
+        assert tuple(a.shape) == tuple(c["alpha_shape"]) and torch.all(a == np.float32(rate))
+        hq = pk.postprocess_u8(torch.from_numpy(c["pred_hq"]).to(DEV), img_d, 1)
+        sr = pk.postprocess_u8(torch.from_numpy(c["pred_sr"]).to(DEV), img_d, 2)
+        assert np.array_equal(hq.cpu().numpy()[0], c["hq_u8"]), f"case {ci}: hq"
+        assert np.array_equal(sr.cpu().numpy()[0], c["sr_u8"]), f"case {ci}: sr"
 
 
 def _sonar_u8(B, h, w, c, seed):
