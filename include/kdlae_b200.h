@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KDLAE_ABI_VERSION 2
+#define KDLAE_ABI_VERSION 3
 #define KDLAE_PREC_FP32 0
 #define KDLAE_PREC_BF16 1
 
@@ -198,6 +198,15 @@ int kdlae_mdta_forward_train(const float* x, const float* gamma, const float* w_
 int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
                         const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg,
                         int H, int W, int C, int heads, float* ws, void* stream);
+/* The dense convolutions of KDLAE-T outside its TransformerBlocks in training mode (OverlapPatchEmbed KDLAE_model.py:169-178, the
+ * Downsample / Upsample bodies :182-200, reduce_chan_level*, output, output_param (dilation 2), output2, cen, upen, outputen
+ * :239-268): 1x1 or 3x3, stride 1, zero padding dilation * (ksize / 2), no bias; fp32 NHWC, w [Cout][ksize*ksize][Cin].
+ * backward: dx (nullable: the first layer needs none) [nimg,H,W,Cin], dw like w; ws: kdlae_conv_train_ws_floats() floats. */
+size_t kdlae_conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ksize);
+int kdlae_conv_train_forward(const float* x, const float* w, float* out, int nimg, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                             void* stream);
+int kdlae_conv_train_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, int nimg, int H, int W, int Cin,
+                              int Cout, int ksize, int dilation, float* ws, void* stream);
 /* Fused torch.nn.utils.clip_grad_norm_(params, max_norm) + AdamW step (image_restoration_model.py:218-220) over flat fp32
  * buffers.  kdlae_grad_norm_sq: *norm_sq (device double) = sum g^2, scratch = 1024 device doubles.  kdlae_adamw_step: decoupled
  * weight decay, bias-corrected moments; the clip coefficient min(1, max_norm / (sqrt(*norm_sq) + 1e-6)) is applied on the fly

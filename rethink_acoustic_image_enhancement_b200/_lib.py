@@ -86,6 +86,9 @@ SIGNATURES = {
     "kdlae_mdta_train_ws_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "kdlae_mdta_forward_train": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "kdlae_mdta_backward": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "kdlae_conv_train_ws_floats": (C.c_size_t, [C.c_int] * 6),
+    "kdlae_conv_train_forward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]),
+    "kdlae_conv_train_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "kdlae_grad_norm_sq": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdlae_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
@@ -116,7 +119,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.kdlae_abi_version() != 2:
+    if lib.kdlae_abi_version() != 3:
         raise RuntimeError("libkdlae_b200.so ABI version mismatch")
     _lib = lib
     return lib

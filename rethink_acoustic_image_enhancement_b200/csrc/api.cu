@@ -436,6 +436,22 @@ int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, 
   return kd::mdta_backward(x, gamma, w_qkv, w_dw, w_proj, temp, dout, dx, dgamma, dw_qkv, dw_dw, dw_proj, dtemp, nimg, H, W, C, heads, ws,
                            reinterpret_cast<cudaStream_t>(stream));
 }
+size_t kdlae_conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ksize) {
+  return (nimg > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ksize == 1 || ksize == 3)) ? kd::conv_train_ws_floats(nimg, H, W, Cin, Cout, ksize)
+                                                                                         : 0;
+}
+int kdlae_conv_train_forward(const float* x, const float* w, float* out, int nimg, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                             void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && w && out, "kdlae_conv_train_forward: NULL argument");
+  return kd::conv_train_forward(x, w, out, nimg, H, W, Cin, Cout, ksize, dilation, reinterpret_cast<cudaStream_t>(stream));
+}
+int kdlae_conv_train_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, int nimg, int H, int W, int Cin,
+                              int Cout, int ksize, int dilation, float* ws, void* stream) {
+  API_BEGIN();
+  KD_CHECK(x && w && dout && dw && ws, "kdlae_conv_train_backward: NULL argument");
+  return kd::conv_train_backward(x, w, dout, dx, dw, nimg, H, W, Cin, Cout, ksize, dilation, ws, reinterpret_cast<cudaStream_t>(stream));
+}
 int kdlae_grad_norm_sq(const float* grad, long n, double* norm_sq, double* scratch, void* stream) {
   API_BEGIN();
   return kd::grad_norm_sq(grad, n, norm_sq, scratch, reinterpret_cast<cudaStream_t>(stream));

@@ -117,6 +117,12 @@ int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, c
 int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
                   const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg, int H,
                   int W, int C, int heads, float* ws, cudaStream_t s);
+// dense 1x1 / 3x3 conv (dilation, zero padding, no bias) with backward, fp32 NHWC, weights [Cout][k*k][Cin]
+size_t conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ks);
+int conv_train_forward(const float* x, const float* w, float* out, int nimg, int H, int W, int Cin, int Cout, int ks, int dil,
+                       cudaStream_t s);
+int conv_train_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, int nimg, int H, int W, int Cin, int Cout,
+                        int ks, int dil, float* ws, cudaStream_t s);
 int grad_norm_sq(const float* g, long n, double* out, double* scratch, cudaStream_t s);
 int adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd, int step,
                float max_norm, const double* norm_sq, cudaStream_t s);

@@ -115,7 +115,10 @@ template <int GATE> struct PtCfg {
   static constexpr int NPX_REAL = PITCH * IH;        // pixels per tile
   static constexpr int NPX = (NPX_REAL + 15) / 16 * 16;   // GEMM N (gate: 126 -> 128, the two extra columns are never read)
   static constexpr int NG = GATE ? 2 : 3;            // column groups of depthwise warps
-  static constexpr int GP = GATE ? 4 : 5;            // output pixel pairs per group per row
+  static constexpr int GP = GATE ? 4 : 5;            // output pixel pairs per group per row.  (Gate with 16 warps of two pairs,
+                                                     // 93 registers: 96 -> 2x256 6 % slower, 48 -> 2x128 2.6 % faster: the narrower
+                                                     // groups load 6 columns per 4 outputs.  Gate without its four MUFU per pair:
+                                                     // 5 % faster - the kernel is bound by the FMA pipe / issue mix, not by MUFU.)
   static constexpr int NDW = NG * 4;                 // depthwise warps
   static constexpr int THREADS = (4 + NDW) * 32;
   static constexpr uint32_t XCHUNK = NPX * 128;      // one 64-channel K chunk of the x tile

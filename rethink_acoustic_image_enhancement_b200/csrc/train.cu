@@ -611,3 +611,130 @@ int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const 
   return 0;
 }
 }  // namespace kd
+
+
+// ==========================================================================================================================
+// Dense conv (1x1 / 3x3, dilation d, zero padding d * (k / 2), no bias) in training mode, fp32 NHWC: the layers of KDLAE-T
+// outside the TransformerBlocks (OverlapPatchEmbed :169-178, Downsample / Upsample bodies :182-200, reduce_chan, output,
+// output_param (dilation 2), output2, cen, upen, outputen :239-268).  Weights [Cout][k*k][Cin].
+//   forward : out = conv(x, w)                                   (the fp32 implicit-GEMM kernel of the inference path)
+//   backward: dx = conv(dout, w^T with the taps mirrored)        (same kernel)
+//             dw[n][tap][k] = sum_p dout[p][n] * x[p + off(tap)][k]   (pixel-split partial sums, fixed-order reduction)
+// ==========================================================================================================================
+namespace kd {
+namespace {
+
+// part[split][n][tap][k] = sum_{p in split} dY[p][n] * X[shift_tap(p)][k];  blockIdx.z = split * taps + tap
+__global__ void __launch_bounds__(256) k_wgrad_conv_part(const float* __restrict__ dY, int N, const float* __restrict__ X, int K, int H, int W,
+                                                         long P, int ks, int dil, int per, float* __restrict__ part) {
+  __shared__ float As[WG_P][WG_T + 4];
+  __shared__ float Bs[WG_P][WG_T + 4];
+  __shared__ long src[WG_P];
+  const int taps = ks * ks;
+  const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T, split = blockIdx.z / taps, tap = blockIdx.z % taps;
+  const int dx = (tap % ks - ks / 2) * dil, dy = (tap / ks - ks / 2) * dil;
+  const long p_begin = (long)split * per, p_end = min(P, p_begin + per);
+  const int tid = threadIdx.x, tn = (tid >> 4) * 4, tk = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long p0 = p_begin; p0 < p_end; p0 += WG_P) {
+    if (tid < WG_P) {                       // source pixel of the tap (or -1: zero padding / past the split)
+      const long p = p0 + tid;
+      long sp = -1;
+      if (p < p_end) {
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        if (x + dx >= 0 && x + dx < W && y + dy >= 0 && y + dy < H) sp = p + (long)dy * W + dx;
+      }
+      src[tid] = sp;
+    }
+    __syncthreads();
+    for (int e = tid; e < WG_P * WG_T; e += 256) {
+      const int pp = e / WG_T, c = e % WG_T;
+      const long p = p0 + pp, sp = src[pp];
+      As[pp][c] = (p < p_end && n0 + c < N) ? dY[p * N + n0 + c] : 0.f;
+      Bs[pp][c] = (sp >= 0 && k0 + c < K) ? X[sp * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pp = 0; pp < WG_P; ++pp) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[pp][tn]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[pp][tk]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + tn + i < N && k0 + tk + j < K) part[(((long)split * N + n0 + tn + i) * taps + tap) * K + k0 + tk + j] = acc[i][j];
+}
+
+// wt[k][taps - 1 - tap][n] = w[n][tap][k]
+__global__ void k_conv_wt(const float* __restrict__ w, int N, int taps, int K, float* __restrict__ wt) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)N * taps * K) return;
+  const int k = (int)(e % K), tap = (int)((e / K) % taps), n = (int)(e / ((long)K * taps));
+  wt[((long)k * taps + (taps - 1 - tap)) * N + n] = w[e];
+}
+
+int conv_splits(long P) { return (int)std::max<long>(1, std::min<long>(32, P / 256)); }
+
+int conv_f32(const float* a, int Cin, const float* w, int Cout, float* out, int nimg, int H, int W, int ks, int dil, cudaStream_t s) {
+  ConvOp g;
+  g.a0 = a; g.c0 = Cin; g.ld0 = Cin; g.nimg = nimg; g.H = H; g.W = W; g.kh = ks; g.kw = ks; g.dil = dil;
+  g.w = w; g.w_ld = (long)ks * ks * Cin; g.w_tap_ld = Cin;
+  g.epi.out = out; g.epi.out_ld = Cout; g.epi.N = Cout; g.epi.H = H; g.epi.W = W;
+  return conv_gemm_simt<float>(g, s);
+}
+
+}  // namespace
+
+size_t conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ks) {
+  const long P = (long)nimg * H * W;
+  const size_t wsz = (size_t)Cin * ks * ks * Cout;
+  return (wsz + 63) / 64 * 64 + (size_t)conv_splits(P) * wsz;
+}
+
+int conv_train_forward(const float* x, const float* w, float* out, int nimg, int H, int W, int Cin, int Cout, int ks, int dil,
+                       cudaStream_t s) {
+  KD_CHECK((ks == 1 || ks == 3) && dil >= 1 && Cin > 0 && Cout > 0, "conv_train_forward: ks=%d dil=%d", ks, dil);
+  return conv_f32(x, Cin, w, Cout, out, nimg, H, W, ks, dil, s);
+}
+
+int conv_train_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, int nimg, int H, int W, int Cin, int Cout,
+                        int ks, int dil, float* ws, cudaStream_t s) {
+  KD_CHECK((ks == 1 || ks == 3) && dil >= 1 && Cin > 0 && Cout > 0, "conv_train_backward: ks=%d dil=%d", ks, dil);
+  const long P = (long)nimg * H * W;
+  const int taps = ks * ks, splits = conv_splits(P);
+  const size_t wsz = (size_t)Cin * taps * Cout;
+  float* wt = ws;
+  float* part = ws + (wsz + 63) / 64 * 64;
+  if (dx) {
+    k_conv_wt<<<cdiv((long)wsz, 256), 256, 0, s>>>(w, Cout, taps, Cin, wt);
+    count_launch();
+    KD_LAUNCH_CHECK();
+    KD_TRY(conv_f32(dout, Cout, wt, Cin, dx, nimg, H, W, ks, dil, s));
+  }
+  const int per = (int)((P + splits - 1) / splits);
+  KD_CHECK((long)splits * taps <= 65535, "conv_train_backward: grid too large");
+  {
+    ProfScope prof(PC_GEMM_SIMT, s, 2.0 * P * Cout * Cin * taps, 4.0 * (double)P * (Cout + Cin) * taps);
+    k_wgrad_conv_part<<<dim3(cdiv(Cout, WG_T), cdiv(Cin, WG_T), splits * taps), 256, 0, s>>>(dout, Cout, x, Cin, H, W, P, ks, dil, per, part);
+    count_launch();
+    KD_LAUNCH_CHECK();
+  }
+  k_sum_parts<<<cdiv((long)wsz, 256), 256, 0, s>>>(part, splits, (long)wsz, dw);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace kd

@@ -131,15 +131,17 @@ class _FusedModule(nn.Module):
         self._engine.invalidate()
         return super()._apply(fn, *args, **kwargs)
 
+    def _wants_autograd(self, *inputs: Optional[torch.Tensor]) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        wants_param_grad = self.training and any(p.requires_grad for p in self.parameters())
+        return wants_param_grad or any(t is not None and t.requires_grad for t in inputs)
+
     def _no_autograd(self, name: str, *inputs: Optional[torch.Tensor]) -> None:
         """The fused forward records no autograd graph.  Refuse loudly wherever the reference would have propagated a
         gradient: training mode with trainable parameters, or (in any mode, e.g. a frozen teacher used as a loss term on a
         student's output) an input that requires grad - silently returning a constant would zero that gradient."""
-        if not torch.is_grad_enabled():
-            return
-        wants_param_grad = self.training and any(p.requires_grad for p in self.parameters())
-        wants_input_grad = any(t is not None and t.requires_grad for t in inputs)
-        if wants_param_grad or wants_input_grad:
+        if self._wants_autograd(*inputs):
             raise NotImplementedError(
                 f"{name}: the fused CUDA forward has no backward yet (training step = SURVEY.md section 8f N1); "
                 "call it under torch.no_grad() (and model.eval()) for inference and validation, and detach inputs that "
@@ -215,17 +217,31 @@ class KDLAE_teacher(_FusedModule):
         self._cfg = cfg
         self._io = (inp_channels, out_channels)
 
+    def _forward_train(self, inp_img: torch.Tensor, denoise_rate: torch.Tensor) -> Dict[str, Optional[torch.Tensor]]:
+        """Training mode (or an input that requires grad): the fp32 CUDA forward-with-saves + CUDA backward of training.py
+        (image_restoration_model.py:198-224 calls the net exactly like this).  BiasFree LayerNorm only - the
+        shipped KDLAET.yml setting."""
+        from . import training
+        if self._cfg.ln_with_bias:
+            raise NotImplementedError("KDLAE_teacher: the CUDA backward is built for LayerNorm_type='BiasFree' (the shipped training "
+                                      "configuration); WithBias models run inference only")
+        with torch.cuda.device(inp_img.device):
+            hq, sr = training.teacher_train_forward(dict(self.named_parameters()), inp_img, denoise_rate,
+                                                    static=self.static, mode=self.params)
+        return {"hq": hq, "sr": sr}
+
     def forward(self, input: Dict[str, torch.Tensor]) -> Dict[str, Optional[torch.Tensor]]:
         inp_img = input["img"]
         denoise_rate = input["denoise_rate"]
         eng = self._engine
         eng.require_cuda(inp_img, "KDLAE_teacher")
-        self._no_autograd("KDLAE_teacher", inp_img, denoise_rate)
         if inp_img.dim() != 4 or inp_img.shape[1] != self._io[0]:
             raise RuntimeError(f"KDLAE_teacher: expected img [B,{self._io[0]},H,W], got {tuple(inp_img.shape)}")
         B, _, H, W = inp_img.shape
         if H % 8 or W % 8:
             raise RuntimeError(f"KDLAE_teacher: H and W must be multiples of 8 (pixel_unshuffle), got {H}x{W}")
+        if self._wants_autograd(inp_img, denoise_rate):
+            return self._forward_train(inp_img, denoise_rate)
         lib, cfg, dev = _lib.load(), self._cfg, inp_img.device
         prec = _lib.PRECISIONS[self.precision]
         with torch.cuda.device(dev):

@@ -37,18 +37,20 @@ def _ceil8(v: int) -> int:
 # GDFN half of a TransformerBlock with a CUDA backward
 # ------------------------------------------------------------------------------------------------------------------
 class _GdfnFn(torch.autograd.Function):
+    """x is NHWC ([B,H,W,C] fp32); parameters in the reference's shapes."""
+
     @staticmethod
     def forward(ctx, x, gamma, w_in, w_dw, w_out):
         if not x.is_cuda:
             raise RuntimeError("gdfn_block_train: expected CUDA tensors (there is no CPU path)")
         lib = _lib.load()
-        B, C, H, W = x.shape
+        B, H, W, C = x.shape
         h = w_out.shape[1]
         hp = _ceil8(h)
         dev = x.device
         with torch.cuda.device(dev):
-            # layout plumbing (no arithmetic): NCHW -> NHWC, reference parameter shapes -> packed layouts of the forward path
-            xh = x.detach().float().permute(0, 2, 3, 1).contiguous()
+            # layout plumbing (no arithmetic): reference parameter shapes -> packed layouts of the forward path
+            xh = x.detach().float().contiguous()
             g = gamma.detach().float().contiguous()
             w2 = w_in.detach().float().view(2 * h, C)
             win = torch.zeros(2 * hp, C, device=dev)
@@ -66,7 +68,7 @@ class _GdfnFn(torch.autograd.Function):
                                                     out.data_ptr(), B, H, W, C, hp, ws.data_ptr(), _stream()), "kdlae_gdfn_forward_train")
         ctx.save_for_backward(xh, g, win, wdw, wout, ws)
         ctx.dims = (B, C, H, W, h, hp)
-        return out.permute(0, 3, 1, 2).contiguous()
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -75,7 +77,7 @@ class _GdfnFn(torch.autograd.Function):
         lib = _lib.load()
         dev = xh.device
         with torch.cuda.device(dev):
-            dout = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()
+            dout = grad_out.detach().float().contiguous()
             dx = torch.empty_like(xh)
             dg = torch.empty(C, device=dev)
             dwin, dwdw, dwout = torch.empty_like(win), torch.empty_like(wdw), torch.empty_like(wout)
@@ -85,7 +87,7 @@ class _GdfnFn(torch.autograd.Function):
         d_w_in = torch.cat([dwin[:h], dwin[hp:hp + h]]).view(2 * h, C, 1, 1)
         d_w_dw = torch.cat([dwdw[:, :h].t(), dwdw[:, hp:hp + h].t()]).reshape(2 * h, 1, 3, 3)
         d_w_out = dwout[:, :h].reshape(C, h, 1, 1)
-        return dx.permute(0, 3, 1, 2).contiguous(), dg, d_w_in, d_w_dw, d_w_out
+        return dx, dg, d_w_in, d_w_dw, d_w_out
 
 
 def gdfn_block_train(x: torch.Tensor, norm_weight: torch.Tensor, project_in_weight: torch.Tensor, dwconv_weight: torch.Tensor,
@@ -93,20 +95,22 @@ def gdfn_block_train(x: torch.Tensor, norm_weight: torch.Tensor, project_in_weig
     """``x + FeedForward(BiasFree_LayerNorm(x))`` (KDLAE_model.py:163) with forward and backward in CUDA (fp32 path).
     x [B,C,H,W]; parameters in the reference's shapes: norm2.body.weight [C], ffn.project_in.weight [2h,C,1,1],
     ffn.dwconv.weight [2h,1,3,3], ffn.project_out.weight [C,h,1,1]."""
-    return _GdfnFn.apply(x, norm_weight, project_in_weight, dwconv_weight, project_out_weight)
+    return _nchw(_GdfnFn.apply(_nhwc(x), norm_weight, project_in_weight, dwconv_weight, project_out_weight))
 
 
 class _MdtaFn(torch.autograd.Function):
+    """x is NHWC ([B,H,W,C] fp32); parameters in the reference's shapes."""
+
     @staticmethod
     def forward(ctx, x, gamma, temperature, w_qkv, w_dw, w_proj):
         if not x.is_cuda:
             raise RuntimeError("mdta_block_train: expected CUDA tensors (there is no CPU path)")
         lib = _lib.load()
-        B, C, H, W = x.shape
+        B, H, W, C = x.shape
         heads = temperature.numel()
         dev = x.device
         with torch.cuda.device(dev):
-            xh = x.detach().float().permute(0, 2, 3, 1).contiguous()
+            xh = x.detach().float().contiguous()
             g = gamma.detach().float().contiguous()
             tp = temperature.detach().float().reshape(heads).contiguous()
             wq = w_qkv.detach().float().view(3 * C, C).contiguous()
@@ -118,7 +122,7 @@ class _MdtaFn(torch.autograd.Function):
                                                     out.data_ptr(), B, H, W, C, heads, ws.data_ptr(), _stream()), "kdlae_mdta_forward_train")
         ctx.save_for_backward(xh, g, tp, wq, wd, wp, ws)
         ctx.dims = (B, C, H, W, heads, tuple(temperature.shape))
-        return out.permute(0, 3, 1, 2).contiguous()
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -127,14 +131,14 @@ class _MdtaFn(torch.autograd.Function):
         lib = _lib.load()
         dev = xh.device
         with torch.cuda.device(dev):
-            dout = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()
+            dout = grad_out.detach().float().contiguous()
             dx = torch.empty_like(xh)
             dg, dtp = torch.empty(C, device=dev), torch.empty(heads, device=dev)
             dwq, dwd, dwp = torch.empty_like(wq), torch.empty_like(wd), torch.empty_like(wp)
             _lib.check(lib.kdlae_mdta_backward(xh.data_ptr(), g.data_ptr(), wq.data_ptr(), wd.data_ptr(), wp.data_ptr(), tp.data_ptr(),
                                                dout.data_ptr(), dx.data_ptr(), dg.data_ptr(), dwq.data_ptr(), dwd.data_ptr(), dwp.data_ptr(),
                                                dtp.data_ptr(), B, H, W, C, heads, ws.data_ptr(), _stream()), "kdlae_mdta_backward")
-        return (dx.permute(0, 3, 1, 2).contiguous(), dg, dtp.view(tshape), dwq.view(3 * C, C, 1, 1),
+        return (dx, dg, dtp.view(tshape), dwq.view(3 * C, C, 1, 1),
                 dwd.t().reshape(3 * C, 1, 3, 3), dwp.view(C, C, 1, 1))
 
 
@@ -143,15 +147,130 @@ def mdta_block_train(x: torch.Tensor, norm_weight: torch.Tensor, temperature: to
     """``x + Attention(BiasFree_LayerNorm(x))`` (KDLAE_model.py:162) with forward and backward in CUDA (fp32 path).
     Parameters in the reference's shapes: norm1.body.weight [C], attn.temperature [heads,1,1], attn.qkv.weight [3C,C,1,1],
     attn.qkv_dwconv.weight [3C,1,3,3], attn.project_out.weight [C,C,1,1]."""
-    return _MdtaFn.apply(x, norm_weight, temperature, qkv_weight, qkv_dwconv_weight, project_out_weight)
+    return _nchw(_MdtaFn.apply(_nhwc(x), norm_weight, temperature, qkv_weight, qkv_dwconv_weight, project_out_weight))
+
+
+def _block_nhwc(x: torch.Tensor, p: dict, prefix: str) -> torch.Tensor:
+    x = _MdtaFn.apply(x, p[prefix + ".norm1.body.weight"], p[prefix + ".attn.temperature"], p[prefix + ".attn.qkv.weight"],
+                      p[prefix + ".attn.qkv_dwconv.weight"], p[prefix + ".attn.project_out.weight"])
+    return _GdfnFn.apply(x, p[prefix + ".norm2.body.weight"], p[prefix + ".ffn.project_in.weight"], p[prefix + ".ffn.dwconv.weight"],
+                         p[prefix + ".ffn.project_out.weight"])
 
 
 def transformer_block_train(x: torch.Tensor, p: dict, prefix: str) -> torch.Tensor:
-    """One BiasFree TransformerBlock (KDLAE_model.py:159-163) in training mode from a dict of the reference's parameters."""
-    x = mdta_block_train(x, p[prefix + ".norm1.body.weight"], p[prefix + ".attn.temperature"], p[prefix + ".attn.qkv.weight"],
-                         p[prefix + ".attn.qkv_dwconv.weight"], p[prefix + ".attn.project_out.weight"])
-    return gdfn_block_train(x, p[prefix + ".norm2.body.weight"], p[prefix + ".ffn.project_in.weight"], p[prefix + ".ffn.dwconv.weight"],
-                            p[prefix + ".ffn.project_out.weight"])
+    """One BiasFree TransformerBlock (KDLAE_model.py:159-163) in training mode from a dict of the reference's parameters
+    (x and the result are NCHW)."""
+    return _nchw(_block_nhwc(_nhwc(x), p, prefix))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# dense convolutions outside the blocks, and the whole KDLAE-T training forward
+# ------------------------------------------------------------------------------------------------------------------
+class _ConvFn(torch.autograd.Function):
+    """Conv2d(Cin, Cout, k, stride 1, padding dilation * (k // 2), bias=False) on NHWC fp32 with a CUDA backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, dilation):
+        if not x.is_cuda:
+            raise RuntimeError("conv_train: expected CUDA tensors (there is no CPU path)")
+        lib = _lib.load()
+        B, H, W, Cin = x.shape
+        Cout, _, k, _ = weight.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            xh = x.detach().float().contiguous()
+            w = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous()      # [Cout][tap][Cin]
+            out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
+            _lib.check(lib.kdlae_conv_train_forward(xh.data_ptr(), w.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, k, int(dilation),
+                                                    _stream()), "kdlae_conv_train_forward")
+        ctx.save_for_backward(xh, w)
+        ctx.dims = (B, H, W, Cin, Cout, k, int(dilation))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xh, w = ctx.saved_tensors
+        B, H, W, Cin, Cout, k, dil = ctx.dims
+        lib = _lib.load()
+        dev = xh.device
+        with torch.cuda.device(dev):
+            dout = grad_out.detach().float().contiguous()
+            dx = torch.empty_like(xh) if ctx.needs_input_grad[0] else None
+            dw = torch.empty_like(w)
+            ws = torch.empty(lib.kdlae_conv_train_ws_floats(B, H, W, Cin, Cout, k), dtype=torch.float32, device=dev)
+            _lib.check(lib.kdlae_conv_train_backward(xh.data_ptr(), w.data_ptr(), dout.data_ptr(), None if dx is None else dx.data_ptr(),
+                                                     dw.data_ptr(), B, H, W, Cin, Cout, k, dil, ws.data_ptr(), _stream()),
+                       "kdlae_conv_train_backward")
+        return dx, dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), None
+
+
+def conv_train(x: torch.Tensor, weight: torch.Tensor, dilation: int = 1) -> torch.Tensor:
+    """``F.conv2d(x, weight, None, padding=dilation * (k // 2), dilation=dilation)`` for NCHW x with forward and backward in CUDA."""
+    return _nchw(_ConvFn.apply(_nhwc(x), weight, dilation))
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 2, 3, 1)
+
+
+def _nchw(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _unshuffle2(x: torch.Tensor) -> torch.Tensor:
+    """nn.PixelUnshuffle(2) on NHWC (pure data movement): out[.., c*4 + 2*dy + dx] = in[2y+dy, 2x+dx, c]."""
+    B, H, W, C = x.shape
+    return x.reshape(B, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, C * 4)
+
+
+def _shuffle2(x: torch.Tensor) -> torch.Tensor:
+    """nn.PixelShuffle(2) on NHWC."""
+    B, H, W, C4 = x.shape
+    C = C4 // 4
+    return x.reshape(B, H, W, C, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(B, 2 * H, 2 * W, C)
+
+
+def teacher_train_forward(params: dict, img: torch.Tensor, denoise_rate: torch.Tensor, static: str = "train", mode: str = "cat"):
+    """KDLAE_teacher.forward (KDLAE_model.py:270-336, BiasFree LayerNorm, bias=False) in training mode: every convolution and
+    every TransformerBlock runs a CUDA forward that saves what its CUDA backward needs; PixelShuffle / PixelUnshuffle, the
+    channel concats and the two adds are torch data movement that autograd differentiates.  ``params``: name -> parameter in the
+    reference's state_dict naming (``dict(model.named_parameters())``).  Returns (hq, sr) like the reference's dict entries."""
+    def nb(prefix):
+        n = 0
+        while f"{prefix}.{n}.norm1.body.weight" in params:
+            n += 1
+        return n
+
+    def blocks(x, prefix):
+        for i in range(nb(prefix)):
+            x = _block_nhwc(x, params, f"{prefix}.{i}")
+        return x
+
+    conv = lambda t, key, dil=1: _ConvFn.apply(t, params[key + ".weight"], dil)
+    x0 = _nhwc(img.float()).contiguous()
+    e1 = blocks(conv(x0, "patch_embed.proj"), "encoder_level1")
+    e2 = blocks(_unshuffle2(conv(e1, "down1_2.body.0")), "encoder_level2")
+    e3 = blocks(_unshuffle2(conv(e2, "down2_3.body.0")), "encoder_level3")
+    lat = blocks(_unshuffle2(conv(e3, "down3_4.body.0")), "latent")
+    d3 = conv(torch.cat([_shuffle2(conv(lat, "up4_3.body.0")), e3], dim=-1), "reduce_chan_level3")
+    d3 = blocks(d3, "decoder_level3")
+    d2 = conv(torch.cat([_shuffle2(conv(d3, "up3_2.body.0")), e2], dim=-1), "reduce_chan_level2")
+    d2 = blocks(d2, "decoder_level2")
+    d1 = blocks(torch.cat([_shuffle2(conv(d2, "up2_1.body.0")), e1], dim=-1), "decoder_level1")
+    d1 = blocks(d1, "refinement")
+    out = conv(d1, "output")
+    if mode == "cat":
+        rate = denoise_rate.float()
+        if rate.dim() == 4 and rate.shape[-2:] != img.shape[-2:]:
+            rate = rate.expand(img.shape[0], 1, img.shape[2], img.shape[3])
+        out = conv(torch.cat([out, _nhwc(rate)], dim=-1), "output_param", 2)
+        out = conv(blocks(out, "refinement_out"), "output2")
+    hq = out + x0
+    sr = None
+    if static == "train":
+        s = _shuffle2(conv(conv(hq, "cen"), "upen.body.0"))
+        sr = _nchw(conv(blocks(s, "enhance"), "outputen"))
+    return _nchw(hq), sr
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -295,4 +414,5 @@ class BucketedAllReducer:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
 
 
-__all__ = ["gdfn_block_train", "mdta_block_train", "transformer_block_train", "FlatAdamW", "BucketedAllReducer"]
+__all__ = ["gdfn_block_train", "mdta_block_train", "transformer_block_train", "conv_train", "teacher_train_forward", "FlatAdamW",
+           "BucketedAllReducer"]

@@ -189,10 +189,12 @@ def test_two_devices_in_one_process():
     assert torch.equal(a["hq"].cpu(), b["hq"].cpu()) and torch.equal(a["sr"].cpu(), b["sr"].cpu())
 
 
-def test_grad_requiring_input_is_refused_in_eval_mode():
-    m = _teacher(dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no"), 0, 1.0, "bf16")
+def test_withbias_teacher_refuses_autograd_and_eval_follows_input_dtype():
+    """The CUDA backward exists for BiasFree models (tests/test_training.py); a WithBias model must refuse instead of returning a
+    constant, and inference on a detached half input returns the input's dtype."""
+    m = _teacher(dict(inp_channels=1, out_channels=1, LayerNorm_type="WithBias", static="no"), 0, 1.0, "bf16")
     x = torch.rand(1, 1, 16, 16, device=DEV, requires_grad=True)
-    with pytest.raises(NotImplementedError, match="no backward"):
+    with pytest.raises(NotImplementedError, match="BiasFree"):
         m({"img": x, "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)})
     out = m({"img": x.detach().half(), "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)})   # eval + no grad needed: fine
     assert out["hq"].dtype == torch.float16 and out["sr"] is None                                    # output follows the input dtype

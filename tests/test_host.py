@@ -19,7 +19,7 @@ def test_header_symbols_are_all_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libkdlae_b200.so"
-    assert lib.kdlae_abi_version() == 2
+    assert lib.kdlae_abi_version() == 3
 
 
 def test_teacher_state_dict_layout_matches_reference_layout():

@@ -134,6 +134,100 @@ def test_transformer_block_backward_matches_oracle_autograd(shape, heads):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [(2, 5, 12, 20, 17, 3, 1), (1, 2, 16, 16, 32, 3, 2), (2, 64, 8, 24, 16, 1, 1), (1, 48, 9, 7, 96, 3, 1)])
+def test_conv_train_matches_torch_autograd(case):
+    """Dense conv forward / dgrad / wgrad of the layers outside the blocks (any channel counts, dilation 2 of output_param)."""
+    import torch.nn.functional as F
+    from rethink_acoustic_image_enhancement_b200.training import conv_train
+    B, Cin, H, W, Cout, k, dil = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    dout = torch.randn(B, Cout, H, W, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, padding=dil * (k // 2), dilation=dil)
+    ref.backward(dout.double())
+    xc, wc = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    out = conv_train(xc, wc, dil)
+    out.backward(dout.to(DEV))
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max())
+    errs = {"out": rel(out.detach(), ref.detach()), "dx": rel(xc.grad, xr.grad), "dw": rel(wc.grad, wr.grad)}
+    print(case, errs)
+    assert max(errs.values()) < 1e-5, errs
+
+
+def _small_teacher(static, seed):
+    import rethink_acoustic_image_enhancement_b200 as pk
+    from oracle import synth
+    kw = dict(inp_channels=1, out_channels=1, dim=16, num_blocks=[1, 1, 1, 2], num_refinement_blocks=1, heads=[1, 2, 4, 8],
+              LayerNorm_type="BiasFree", static=static)
+    sd = synth.teacher_state_dict(seed=seed, temp_scale=4.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV), sd, kw
+
+
+@pytest.mark.gpu
+def test_teacher_training_step_gradients_match_oracle_autograd():
+    """The whole KDLAE-T training forward + L1LossSr + backward through the MODULE (model.train(); image_restoration_model.py
+    :198-224 makes exactly these calls): every one of the parameter gradients against autograd through oracle.functional in
+    float64 with the oracle's loss (a reduced-width model: dim 16, blocks 1/1/1/2, all layer kinds present)."""
+    from oracle import functional as ofn, metrics as om, synth
+    from rethink_acoustic_image_enhancement_b200.metrics import L1LossSr
+    m, sd, kw = _small_teacher("train", 12)
+    m.train()
+    B, H, W = 2, 32, 48
+    img = synth.seeded_tensor("tstep.img", (B, 1, H, W), 1, "sonar")
+    rate = torch.tensor([0.3, 0.9]).view(B, 1, 1, 1).expand(B, 1, H, W).contiguous()
+    gt_hq = synth.seeded_tensor("tstep.hq", (B, 1, H, W), 2, "sonar")
+    gt_sr = synth.seeded_tensor("tstep.sr", (B, 1, 2 * H, 2 * W), 3, "sonar")
+    # oracle: float64 autograd
+    ref_p = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    hq_r, sr_r = ofn.teacher_forward(ref_p, img.double(), rate.double(), heads=kw["heads"], static="train", params="cat")
+    loss_r = om.l1_loss_sr({"hq": hq_r, "sr": sr_r}, {"hq": gt_hq.double(), "sr": gt_sr.double()}, 1.0)
+    loss_r.backward()
+    # product: module in training mode, CUDA loss
+    out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+    loss = L1LossSr(loss_weight=1.0)(out, {"hq": gt_hq.to(DEV), "sr": gt_sr.to(DEV)})
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(out["hq"].detach(), hq_r.detach()) < 1e-5 and rel(out["sr"].detach(), sr_r.detach()) < 1e-5
+    assert abs(float(loss.detach()) - float(loss_r.detach())) < 1e-5 * abs(float(loss_r.detach()))
+    errs, named = {}, dict(m.named_parameters())
+    assert set(named) == set(sd)
+    for k, p in named.items():
+        assert p.grad is not None and p.grad.shape == sd[k].shape, k
+        errs[k] = rel(p.grad, ref_p[k].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print(f"{len(errs)} parameter gradients, worst: {[(k, f'{v:.2e}') for k, v in worst]}")
+    assert max(errs.values()) < 1e-4, worst          # fp32 kernels vs float64 autograd through ~20 layers
+
+
+@pytest.mark.gpu
+def test_frozen_teacher_propagates_input_gradients():
+    """eval() teacher as a loss term on another network's output (the KD setting): d loss / d input from the CUDA backward."""
+    from oracle import functional as ofn, synth
+    m, sd, kw = _small_teacher("no", 13)
+    m.eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    x = synth.seeded_tensor("frozen.img", (1, 1, 24, 24), 4, "sonar")
+    rate = torch.full((1, 1, 24, 24), 0.5)
+    xr = x.double().requires_grad_(True)
+    hq_r, _ = ofn.teacher_forward({k: v.double() for k, v in sd.items()}, xr, rate.double(), heads=kw["heads"], static="no", params="cat")
+    hq_r.square().sum().backward()
+    xc = x.to(DEV).requires_grad_(True)
+    out = m({"img": xc, "denoise_rate": rate.to(DEV)})
+    assert out["sr"] is None
+    out["hq"].square().sum().backward()
+    err = float((xc.grad.double().cpu() - xr.grad).abs().max() / xr.grad.abs().max())
+    print(f"d loss / d input rel err {err:.2e}")
+    assert err < 1e-4
+
+
+@pytest.mark.gpu
 def test_fused_clip_adamw_matches_torch():
     from rethink_acoustic_image_enhancement_b200.training import FlatAdamW
     torch.manual_seed(1)
