@@ -3,6 +3,7 @@
 // gemm_tc.cu so both paths share the host orchestration.
 //
 // Tile: 128 pixels x 64 output channels x 16 K per step, 256 threads, 4x8 outputs per thread.
+#include <type_traits>
 #include "ops.cuh"
 
 namespace kd {
@@ -109,6 +110,101 @@ __global__ void __launch_bounds__(NT) k_conv_gemm_simt(const SimtParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// fp32 1x1 conv = plain SGEMM  out[P][N] = A[P][K] . W[N][K]^T : the dominant kernel of the fp32 training step (every qkv /
+// project / GDFN 1x1, forward and dgrad) and of the fp32 inference path.  8 x 8 outputs per thread, K in steps of 8 with the
+// next step's global float4 loads in flight under the FMAs (register prefetch + two shared-memory buffers), 16-byte loads on both
+// operands.  CG = column groups: 16 -> tile 128 x 128, 8 -> tile 256 x 64 (narrow N such as the 48-channel project_out).
+// Same ConvOp / Epilogue contract as the generic kernel (row scale, bias, residual, ragged N, per-image weight groups).
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(256, 2) k_sgemm_1x1(const SimtParams p) {
+  constexpr int RG = 256 / CG, SBM = RG * 8, SBN = CG * 8, SBK = 8;
+  constexpr int NA = SBM / 128;                 // float4 loads of A per thread and step
+  __shared__ __align__(16) float As[2][SBK][SBM + 4];
+  __shared__ __align__(16) float Bs[2][SBK][SBN + 4];
+  const ConvOp& op = p.op;
+  const int tid = threadIdx.x, g = blockIdx.z;
+  const long row0 = (long)g * p.rows_per_group + (long)blockIdx.x * SBM;
+  const long row_end = (long)(g + 1) * p.rows_per_group;
+  const int n0 = blockIdx.y * SBN, K = op.c0;
+  const float* __restrict__ a = reinterpret_cast<const float*>(op.a0);
+  const float* __restrict__ w = reinterpret_cast<const float*>(op.w) + (long)g * op.w_group_stride;
+  // loaders: float4 f of a tile covers row f / 2, k offset (f & 1) * 4
+  const int lk = (tid & 1) * 4;
+  const float* ap[NA];
+  bool a_ok[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const long r = row0 + (tid >> 1) + i * 128;
+    a_ok[i] = r < row_end;
+    ap[i] = a + (a_ok[i] ? r : row0) * op.ld0 + lk;
+  }
+  const int brow = tid >> 1;
+  const bool b_act = brow < SBN, b_ok = b_act && (n0 + brow) < op.epi.N;
+  const float* bp = w + (long)(b_ok ? n0 + brow : 0) * op.w_ld + lk;
+  float4 ra[NA], rb;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto gload = [&](int k0) {
+    const bool k_ok = k0 + lk < K;              // K % 4 == 0: a float4 is entirely inside or outside
+#pragma unroll
+    for (int i = 0; i < NA; ++i) ra[i] = (a_ok[i] && k_ok) ? __ldg(reinterpret_cast<const float4*>(ap[i] + k0)) : zero4;
+    rb = (b_ok && k_ok) ? __ldg(reinterpret_cast<const float4*>(bp + k0)) : zero4;
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int r = (tid >> 1) + i * 128;
+      As[buf][lk + 0][r] = ra[i].x; As[buf][lk + 1][r] = ra[i].y; As[buf][lk + 2][r] = ra[i].z; As[buf][lk + 3][r] = ra[i].w;
+    }
+    if (b_act) { Bs[buf][lk + 0][brow] = rb.x; Bs[buf][lk + 1][brow] = rb.y; Bs[buf][lk + 2][brow] = rb.z; Bs[buf][lk + 3][brow] = rb.w; }
+  };
+  const int ty = tid / CG, tx = tid % CG;       // rows ty * 4 + {0..3} and SBM / 2 + ty * 4 + {0..3}; columns tx * 8 + {0..7}
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = (K + SBK - 1) / SBK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * SBK);
+#pragma unroll
+    for (int k = 0; k < SBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][SBM / 2 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);                          // the other buffer was last read before the previous barrier
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long r = row0 + (i < 4 ? ty * 4 + i : SBM / 2 + ty * 4 + (i - 4));
+    if (r >= row_end) continue;
+    epilogue_store8<float>(op.epi, r, 0, 0, 0, n0 + tx * 8, acc[i]);     // identity addressing: (image, y, x) are not used
+  }
+}
+
+bool sgemm_1x1_ok(const ConvOp& op) {
+  return op.kd == 1 && op.kh == 1 && op.kw == 1 && op.c1 == 0 && op.epi.mode == OUT_IDENTITY && op.c0 % 4 == 0 && op.ld0 % 4 == 0 &&
+         op.w_ld % 4 == 0 && op.w_group_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(op.a0) & 15) &&
+         !(reinterpret_cast<uintptr_t>(op.w) & 15);
+}
+
 }  // namespace
 
 template <typename T>
@@ -127,6 +223,18 @@ int conv_gemm_simt(const ConvOp& op, cudaStream_t s) {
   KD_CHECK(grid.y <= 65535 && grid.z <= 65535, "conv_gemm_simt: grid too large");
   ProfScope prof(PC_GEMM_SIMT, s, 2.0 * rows * op.epi.N * p.ktot,
                  sizeof(T) * ((double)rows * (p.ctot + op.epi.N * (op.epi.res ? 2 : 1)) + (double)op.groups * op.epi.N * p.ktot));
+  if constexpr (std::is_same<T, float>::value) {
+    if (sgemm_1x1_ok(op)) {
+      const int N = op.epi.N;
+      if (cdiv(N, 64) * 64 < cdiv(N, 128) * 128)        // narrow / ragged N: the 256 x 64 tile pads less
+        k_sgemm_1x1<8><<<dim3(cdiv(p.rows_per_group, 256), cdiv(N, 64), op.groups), 256, 0, s>>>(p);
+      else
+        k_sgemm_1x1<16><<<dim3(cdiv(p.rows_per_group, 128), cdiv(N, 128), op.groups), 256, 0, s>>>(p);
+      count_launch();
+      KD_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   k_conv_gemm_simt<T><<<grid, NT, 0, s>>>(p);
   count_launch();
   KD_LAUNCH_CHECK();

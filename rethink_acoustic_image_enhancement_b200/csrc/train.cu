@@ -74,14 +74,15 @@ __global__ void __launch_bounds__(128) k_dw_wgrad_part(const float* __restrict__
   float acc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  int x = (int)(p_begin % W), y = (int)((p_begin / W) % H);          // advanced incrementally: no division per pixel
   for (long p = p_begin; p < p_end; ++p) {
-    const int x = (int)(p % W), y = (int)((p / W) % H);
     const float g = du[p * C + c];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc[k] = fmaf(g, t[(p + (long)(k / 3 - 1) * W + (k % 3 - 1)) * C + c], acc[k]);
     }
+    if (++x == W) { x = 0; if (++y == H) y = 0; }
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) part[((long)split * 9 + k) * C + c] = acc[k];
@@ -166,6 +167,23 @@ int wgrad_1x1(const float* A, long lda, int N, const float* B, long ldb, int K, 
   return 0;
 }
 
+// The depthwise wgrad is a per-channel reduction over all pixels: a thread owns a channel, so the only parallelism besides the
+// channels is the pixel split - up to 512 splits of >= 32 pixels (with the 32 splits of the dense wgrads a block-backward spent a
+// third of its time here, one warp per SM walking thousands of pixels).
+constexpr int DW_SPLITS = 512;
+int dw_wgrad_splits(long P) { return (int)std::max<long>(1, std::min<long>(DW_SPLITS, P / 32)); }
+int dw_wgrad(const float* du, const float* t, int nimg, int H, int W, int C2, float* dw, float* part, cudaStream_t s) {
+  const long P = (long)nimg * H * W;
+  const int splits = dw_wgrad_splits(P), per = (int)((P + splits - 1) / splits);
+  k_dw_wgrad_part<<<dim3(cdiv(C2, 128), splits), 128, 0, s>>>(du, t, nimg, H, W, C2, per, part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  k_sum_parts<<<cdiv(9L * C2, 256), 256, 0, s>>>(part, splits, 9L * C2, dw);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
 int conv1x1_f32(const float* a, int C, const float* w, int N, const float* res, float* out, int nimg, int H, int W, cudaStream_t s) {
   ConvOp g;
   g.a0 = a; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.w = w; g.w_ld = C; g.w_tap_ld = C;
@@ -189,7 +207,7 @@ GdfnWs gdfn_layout(float* base, int nimg, int H, int W, int C, int hp) {
   L.dg = take(P * hp); L.du = take(P * 2 * hp); L.dt = take(P * 2 * hp); L.dy = take(P * C);
   L.wt = take((size_t)2 * hp * C); L.w9f = take((size_t)9 * 2 * hp);
   const size_t ln_blocks = (P + GD_LN_PIX - 1) / GD_LN_PIX;
-  L.part = take(std::max<size_t>((size_t)GD_SPLITS * 2 * hp * std::max(C, 9), ln_blocks * C));
+  L.part = take(std::max<size_t>({(size_t)GD_SPLITS * 2 * hp * C, (size_t)dw_wgrad_splits((long)P) * 9 * 2 * hp, ln_blocks * C}));
   L.total = off;
   return L;
 }
@@ -233,15 +251,7 @@ int gdfn_backward(const float* x, const float* gamma, const float* w_in, const f
   count_launch();
   KD_LAUNCH_CHECK();
   // depthwise conv: wgrad, dgrad (= the conv with reversed taps)
-  {
-    const int per = (int)((P + splits - 1) / splits);
-    k_dw_wgrad_part<<<dim3(cdiv(2 * hp, 128), splits), 128, 0, s>>>(L.du, L.t, nimg, H, W, 2 * hp, per, L.part);
-    count_launch();
-    KD_LAUNCH_CHECK();
-    k_sum_parts<<<cdiv(9L * 2 * hp, 256), 256, 0, s>>>(L.part, splits, 9L * 2 * hp, dw_dw);
-    count_launch();
-    KD_LAUNCH_CHECK();
-  }
+  KD_TRY(dw_wgrad(L.du, L.t, nimg, H, W, 2 * hp, dw_dw, L.part, s));
   k_flip9<<<cdiv(9 * 2 * hp, 256), 256, 0, s>>>(w_dw, 2 * hp, L.w9f);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -500,7 +510,8 @@ MdtaWs mdta_layout(float* base, int nimg, int H, int W, int C, int heads) {
   L.du = take(P * 3 * C); L.dt = take(P * 3 * C); L.dy = take(P * C);
   L.wt = take((size_t)3 * C * C); L.w9f = take((size_t)9 * 3 * C); L.dtp = take((size_t)nimg * heads);
   const size_t ln_blocks = (P + GD_LN_PIX - 1) / GD_LN_PIX;
-  L.part = take(std::max<size_t>({(size_t)GD_SPLITS * 3 * C * std::max(C, 9), ln_blocks * C, (size_t)nimg * heads * splits * psz}));
+  L.part = take(std::max<size_t>({(size_t)GD_SPLITS * 3 * C * C, (size_t)dw_wgrad_splits((long)P) * 9 * 3 * C, ln_blocks * C,
+                                  (size_t)nimg * heads * splits * psz}));
   L.total = off;
   return L;
 }
@@ -582,15 +593,7 @@ int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const 
   KD_LAUNCH_CHECK();
   KD_TRY(grouped_1x1_f32(L.u, 2 * C, 3 * C, L.Wqk, 2 * C, 4L * C * C, L.du, 3 * C, 0, nimg, H, W, s));
   // depthwise conv: wgrad, dgrad
-  {
-    const int per = (int)((P + splits - 1) / splits);
-    k_dw_wgrad_part<<<dim3(cdiv(3 * C, 128), splits), 128, 0, s>>>(L.du, L.t, nimg, H, W, 3 * C, per, L.part);
-    count_launch();
-    KD_LAUNCH_CHECK();
-    k_sum_parts<<<cdiv(27L * C, 256), 256, 0, s>>>(L.part, splits, 27L * C, dw_dw);
-    count_launch();
-    KD_LAUNCH_CHECK();
-  }
+  KD_TRY(dw_wgrad(L.du, L.t, nimg, H, W, 3 * C, dw_dw, L.part, s));
   k_flip9<<<cdiv(27 * C, 256), 256, 0, s>>>(w_dw, 3 * C, L.w9f);
   count_launch();
   KD_LAUNCH_CHECK();
