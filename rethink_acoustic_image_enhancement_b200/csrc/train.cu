@@ -196,7 +196,7 @@ struct GdfnWs {
   float *dg, *du, *dt, *dy, *wt, *w9f, *part;       // backward scratch
   size_t total;
 };
-constexpr int GD_SPLITS = 32, GD_LN_PIX = 256;
+constexpr int GD_SPLITS = 32, GD_LN_PIX = 64;     // 64 pixels per LayerNorm-backward block: 256 left 128 blocks for a 2 x 128^2 batch
 
 GdfnWs gdfn_layout(float* base, int nimg, int H, int W, int C, int hp) {
   const size_t P = (size_t)nimg * H * W;
