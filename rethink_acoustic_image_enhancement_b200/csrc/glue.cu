@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) k_mdta_gram(const T* __restrict__ qk, lon
 // Pixel splits per (image, head).  Depends on the image size only, so the reduction order - and therefore the
 // result - of an image does not depend on the batch or micro-batch it is processed in.
 int mdta_gram_splits(int HW, int /*nimg_heads*/) {
-  int s = HW / 512;       // 512 pixels per split at least: a 128 x 128 training crop still spreads over 32 CTAs per (image, head)
+  int s = HW / 2048;
   return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
 

@@ -497,9 +497,16 @@ struct MdtaWs {
   float *dov, *dAs, *Wqk, *du, *dt, *dy, *wt, *w9f, *dtp, *part;  // backward scratch
   size_t total;
 };
+// Pixel splits of the fp32 Gram reductions of the training step: 512 pixels per split (the inference rule, 2048, leaves a batch of
+// two 128 x 128 crops on 16-32 CTAs); depends on the image size only, like the inference rule.
+int train_gram_splits(int HW, int /*nimg_heads*/) {
+  const int s = HW / 512;
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
 MdtaWs mdta_layout(float* base, int nimg, int H, int W, int C, int heads) {
   const size_t P = (size_t)nimg * H * W, ch = C / heads, psz = ch * ch + 2 * ch;
-  const int splits = mdta_gram_splits(H * W, nimg * heads);
+  const int splits = train_gram_splits(H * W, nimg * heads);
   size_t off = 0;
   auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
   MdtaWs L;
@@ -533,7 +540,7 @@ int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, c
   KD_CHECK(heads > 0 && C % heads == 0 && ch % 8 == 0 && ch <= 96 && C <= 1024, "mdta_forward_train: C=%d heads=%d (channels per head <= 96)", C, heads);
   const MdtaWs L = mdta_layout(ws, nimg, H, W, C, heads);
   const long P = (long)nimg * H * W;
-  const int HW = H * W, splits = mdta_gram_splits(HW, nimg * heads);
+  const int HW = H * W, splits = train_gram_splits(HW, nimg * heads);
   const long psz = (long)ch * ch + 2 * ch;
   KD_TRY(ln_stats<float>(x, C, C, P, L.rstd, L.mu, s));
   k_ln_apply<<<cdiv(P * C, 256), 256, 0, s>>>(x, L.rstd, gamma, C, P * C, L.y);
@@ -558,7 +565,7 @@ int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const 
   const int ch = C / heads;
   const MdtaWs L = mdta_layout(ws, nimg, H, W, C, heads);
   const long P = (long)nimg * H * W;
-  const int HW = H * W, gsplits = mdta_gram_splits(HW, nimg * heads);
+  const int HW = H * W, gsplits = train_gram_splits(HW, nimg * heads);
   const int splits = (int)std::min<long>(GD_SPLITS, std::max<long>(1, P / 256));
   const long psz = (long)ch * ch + 2 * ch;
   // project_out: wgrad, dgrad (do -> columns [0, C) of dov)

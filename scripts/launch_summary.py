@@ -11,6 +11,7 @@ def main():
     lo, hi = (float(sys.argv[2]), float(sys.argv[3])) if len(sys.argv) > 3 else (0.0, 1.0)
     with open(path) as f:
         rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
+    rows = [d for d in rows if "gpu__time_duration" in d.get("Metric Name", "gpu__time_duration")]
     rows = rows[int(len(rows) * lo):int(len(rows) * hi)]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for d in rows:
