@@ -595,8 +595,8 @@ def main():
             roof["traffic_source"] = tj["_provenance"]
     roof["peak_source"] = pk_["source"] + (" sustained (kernel timed inside a long step)" if pk_["source"] == "measured" else "")
     if top.startswith("fused_conv1x1_dwconv3x3"):
-        roof["note"] = ("fused tcgen05 1x1 -> FFMA2 depthwise (+GELU gate) kernels (pwdw_t.cu: qkv and the C=96 GDFN pair, pwdw_f2.cu: the C=48 "
-                        "GDFN pair): the 3C / 2h wide intermediate never reaches HBM, so the HBM fraction is low by design (ncu DRAM traffic = "
+        roof["note"] = ("fused tcgen05 1x1 -> FFMA2 depthwise (+GELU gate) kernels (pwdw_t.cu, both the qkv and the GDFN pair of every "
+                        "block with C <= 128): the 3C / 2h wide intermediate never reaches HBM, so the HBM fraction is low by design (ncu DRAM traffic = "
                         "algorithmic bytes) and the tensor pipe only carries the small 1x1 (K = C); the class is bound by CUDA-core "
                         "instruction issue / FMA-pipe occupancy of the depthwise + GELU code - see roofline.issue (ncu --set full, "
                         "profiles/r02_issue.json, profiles/r02_summary.md)")
