@@ -28,6 +28,9 @@ constexpr int C3_THREADS = (2 + C3_EPI_WARPS + 2) * 32;
 constexpr uint32_t C3_SMEM = C3_ASLOTS * C3_A_SLOT + C3_BSLOTS * C3_B_SLOT + C3_NSLAB * C3_SLAB + 1024 + 512;   // streaming layout
 constexpr uint32_t C3_SMEM_MAX = 227 * 1024;
 constexpr int C3_STORE_BAR_THREADS = C3_EPI_WARPS * 32 + 32;
+#ifndef KDLAE_C3_RES2
+#define KDLAE_C3_RES2 1
+#endif
 
 struct C3Params {
   int kd, D;                 // temporal taps (1 or 3) and frames per batch element
@@ -126,8 +129,16 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       if (p.w_resident) {          // weight-stationary: 9 (27) x [nc x 64] tiles, one barrier, no per-tap handshakes afterwards
         if (elect_one()) {
           mbar_expect_tx(b_full(0), (uint32_t)p.w_tiles * (uint32_t)p.nc * 128);
-          for (int tap = 0; tap < p.w_tiles; tap += p.b_group)
-            tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), 0, 0, tap);
+          if (kchunks == 1) {
+            for (int tap = 0; tap < p.w_tiles; tap += p.b_group)
+              tma_load_3d(b_base + tap * p.nc * 128, &map_w, b_full(0), 0, 0, tap);
+          } else {                 // 2-D conv with two K chunks: tiles in [chunk][tap] order, the order the MMA loop walks them
+            for (int kc = 0; kc < kchunks; ++kc) {
+              const int wk = kc >= p.kc0 ? p.c0 + (kc - p.kc0) * 64 : kc * 64;
+              for (int tap = 0; tap < 9; tap += p.b_group)
+                tma_load_3d(b_base + (kc * 9 + tap) * p.nc * 128, &map_w, b_full(0), wk, 0, tap);
+            }
+          }
         }
         __syncwarp();
       }
@@ -181,7 +192,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           const uint32_t a_lo0 = (((a_base + s * C3_A_SLOT) & 0x3FFFF) >> 4) | lo_tag;
           // K = 16 steps that hold real channels in this chunk (a 16-channel layer needs 1 of the 4: the rest of the box is TMA
           // zero fill and would only burn tensor-pipe time - the KDLAE-S / ASDQE layers are 16..64 channels wide)
-          const int kci = p.w_resident ? 0 : ag / p.kd;      // resident modes have a single K chunk
+          const int kci = ag / p.kd;
           const int rem = kci < p.kc0 ? p.c0 - kci * 64 : p.c1 - (kci - p.kc0) * 64;
           const int ksn = rem >= 64 ? 4 : (rem + 15) >> 4;
           if (p.xpack_cin) {
@@ -224,17 +235,22 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             __syncwarp();
           } else if (p.w_resident) {
             // weight-stationary: no per-tap handshake - the 9 x ksn MMAs of this A tile go out back to back from one elected lane
+            // (descriptor offsets in warp-uniform code outside the elected region, as in the x-packed branch: inside it ptxas keeps
+            // them per thread and wraps every MMA in R2UR moves)
+            const uint32_t b_tap = (uint32_t)p.nc * 8;            // (nc * 128 bytes) >> 4 per tap tile
+            // the A group index is the frame tap (single K chunk) or the K chunk (2-D conv): its 9 spatial tap tiles start at 9 * ag
+            const uint32_t b_lo0 = (((b_base & 0x3FFFF) >> 4) | lo_tag) + (uint32_t)ag * 9u * b_tap;
+            uint32_t b_t[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) b_t[tap] = b_lo0 + tap * b_tap;
+            const uint32_t first = (ag == 0) ? 0u : 1u;
             if (elect_one()) {
-              const uint32_t b_tap = (uint32_t)p.nc * 8;            // (nc * 128 bytes) >> 4 per tap tile
-              // single K chunk: the A group index is the frame tap, whose 9 spatial tap tiles start at 9 * td
-              const uint32_t b_lo0 = (((b_base & 0x3FFFF) >> 4) | lo_tag) + (uint32_t)ag * 9u * b_tap;   // ag < kd here
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * C3_TW + tap % 3) * 8);
-                const uint32_t b_lo = b_lo0 + tap * b_tap;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (ag | tap | ks) != 0 ? 1u : 0u);
+                  if (ks < ksn) umma_bf16_lohi(d_tmem, a_lo + ks * 2, b_t[tap] + ks * 2, desc_hi, idesc, (tap | ks) != 0 ? 1u : first);
               }
             }
             __syncwarp();
@@ -454,12 +470,17 @@ int conv3x3_tc(const ConvOp& op, int nc, int n_chunks, cudaStream_t s) {
   // N <= 64 and the 3x3x3 layers of KDLAE-S up to 32 output channels (27 * 32 * 128 B = 108 KB).  Streaming the 27 tap tiles
   // per output tile (9 dependent TMA round trips of ~1 us) made the 16 -> 16 layer at 512^2 take 8500 clk per 120-pixel tile.
   p.xpack_cin = op.xpack_cin;
-  p.w_tiles = op.xpack_cin ? xconv_tiles(op.kd, op.xpack_cin) : 9 * op.kd;
+  p.w_tiles = op.xpack_cin ? xconv_tiles(op.kd, op.xpack_cin) : 9 * op.kd * (p.kc0 + p.kc1);
   p.nslab = C3_NSLAB;
   const uint32_t w_res_bytes = ((uint32_t)p.w_tiles * nc * 128 + 1023u) & ~1023u;
   p.w_resident = (p.kc0 + p.kc1 == 1 && n_chunks == 1 &&
                   w_res_bytes + C3_ASLOTS * C3_A_SLOT + C3_NSLAB * C3_SLAB + 1024 + 512 <= C3_SMEM_MAX &&
                   (op.kd == 3 || op.xpack_cin || 9u * nc * 128 <= C3_BSLOTS * C3_B_SLOT)) ? 1 : 0;
+  // 2-D convs whose 18 tap tiles (two K chunks x N <= 64) or 9 tap tiles (one K chunk x N <= 128) take 144 KB: resident next to
+  // two activation slots and a two-deep slab ring (the 128 -> 64 and 64 -> 128 layers of ASDQE at 512^2 / 256^2)
+  const bool res2 = KDLAE_C3_RES2 && !p.w_resident && op.kd == 1 && !op.xpack_cin && n_chunks == 1 && p.kc0 + p.kc1 <= 2 &&
+                    w_res_bytes + C3_ASLOTS * C3_A_SLOT + 2 * C3_SLAB + 1024 + 512 <= C3_SMEM_MAX;
+  if (res2) { p.w_resident = 1; p.nslab = 2; }
   if (op.xpack_cin) {
     KD_CHECK((op.xpack_cin == 16 || op.xpack_cin == 32) && op.c0 == 64 && op.c1 == 0 && n_chunks == 1 && nc % 16 == 0 && op.w_tap_ld == 64,
              "conv3x3_tc: bad x-packed conv (cin %d, c0 %d, N %d)", op.xpack_cin, op.c0, e.N);
