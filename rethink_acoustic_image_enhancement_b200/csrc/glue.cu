@@ -366,6 +366,22 @@ template int mdta_fold<bf16>(float*, int, int, int, int, const float*, const flo
 // predicated loads), the [taps*CIN][cout] weights sit in shared memory.
 // PXF = consecutive output pixels per thread: one weight fetch feeds PXF pixels (wide outputs: the weight LDS traffic is the
 // limiter); narrow outputs (ASDQE stems, 16 channels) keep PXF = 1 so a warp's input loads stay contiguous.
+// packed fp32 helpers (exact per lane: fma.rn.f32x2 = two IEEE fmaf): the 8 output channels of a thread are four pairs, so the
+// tap loop issues half as many FMA instructions
+__device__ __forceinline__ unsigned long long fi_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fi_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fi_unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 template <typename T, int CIN, int KD, int PXF, int DIL>
 __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin, int Win) {
   extern __shared__ __align__(16) float wsm_in[];   // [KD*9*CIN][cout]
@@ -384,11 +400,12 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
     const int cg = (int)(idx % cgroups); idx /= cgroups;
     const int x0 = (int)(idx % xgroups) * PXF;
     const int y = (int)(idx / xgroups);
-    float acc[PXF][8];
+    unsigned long long acc2[PXF][4];
 #pragma unroll
     for (int q = 0; q < PXF; ++q)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[q][i] = op.bias ? op.bias[cg * 8 + i] : 0.f;
+      for (int i = 0; i < 4; ++i)
+        acc2[q][i] = op.bias ? fi_pack2(op.bias[cg * 8 + 2 * i], op.bias[cg * 8 + 2 * i + 1]) : fi_pack2(0.f, 0.f);
 #pragma unroll
     for (int td = 0; td < KD; ++td) {
       const int dd = d + td - KD / 2;
@@ -422,21 +439,25 @@ __global__ void __launch_bounds__(128) k_conv_few_in(const SmallConv op, int Hin
 #pragma unroll
           for (int tx = 0; tx < 3; ++tx) {
             const float* wp = wsm_in + (((td * 3 + ty) * 3 + tx) * CIN + c) * op.cout + cg * 8;
-            const float4 wa = *reinterpret_cast<const float4*>(wp);
-            const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+            const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wp);        // channel pairs (0,1) (2,3)
+            const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wp + 4);    //               (4,5) (6,7)
 #pragma unroll
             for (int q = 0; q < PXF; ++q) {
               const float v = r[q + tx * DIL];
-              acc[q][0] = fmaf(v, wa.x, acc[q][0]); acc[q][1] = fmaf(v, wa.y, acc[q][1]);
-              acc[q][2] = fmaf(v, wa.z, acc[q][2]); acc[q][3] = fmaf(v, wa.w, acc[q][3]);
-              acc[q][4] = fmaf(v, wb.x, acc[q][4]); acc[q][5] = fmaf(v, wb.y, acc[q][5]);
-              acc[q][6] = fmaf(v, wb.z, acc[q][6]); acc[q][7] = fmaf(v, wb.w, acc[q][7]);
+              const unsigned long long v2 = fi_pack2(v, v);
+              acc2[q][0] = fi_ffma2(v2, wa.x, acc2[q][0]); acc2[q][1] = fi_ffma2(v2, wa.y, acc2[q][1]);
+              acc2[q][2] = fi_ffma2(v2, wb.x, acc2[q][2]); acc2[q][3] = fi_ffma2(v2, wb.y, acc2[q][3]);
             }
           }
         }
       }
     }
     T* out = reinterpret_cast<T*>(op.out);
+    float acc[PXF][8];
+#pragma unroll
+    for (int q = 0; q < PXF; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fi_unpack2(acc2[q][i], acc[q][2 * i], acc[q][2 * i + 1]);
 #pragma unroll
     for (int q = 0; q < PXF; ++q) {
       if (x0 + q < op.W) {
