@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(NT) k_conv_gemm_simt(const SimtParams p) {
 // operands.  CG = column groups: 16 -> tile 128 x 128, 8 -> tile 256 x 64 (narrow N such as the 48-channel project_out).
 // Same ConvOp / Epilogue contract as the generic kernel (row scale, bias, residual, ragged N, per-image weight groups).
 // ---------------------------------------------------------------------------------------------------------------------------
-template <int CG>
+// KS = 3: the same kernel as an implicit GEMM over the 9 taps of a dense 3x3 conv (dilation d, zero padding): K = 9 * C with
+// C % 8 == 0, so a K step of 8 stays inside one tap and only the A loader changes (shifted pixel, zero outside the image).
+template <int CG, int KS>
 __global__ void __launch_bounds__(256, 2) k_sgemm_1x1(const SimtParams p) {
   constexpr int RG = 256 / CG, SBM = RG * 8, SBN = CG * 8, SBK = 8;
   constexpr int NA = SBM / 128;                 // float4 loads of A per thread and step
@@ -128,18 +130,20 @@ __global__ void __launch_bounds__(256, 2) k_sgemm_1x1(const SimtParams p) {
   const int tid = threadIdx.x, g = blockIdx.z;
   const long row0 = (long)g * p.rows_per_group + (long)blockIdx.x * SBM;
   const long row_end = (long)(g + 1) * p.rows_per_group;
-  const int n0 = blockIdx.y * SBN, K = op.c0;
+  const int n0 = blockIdx.y * SBN, K = op.c0 * KS * KS;
   const float* __restrict__ a = reinterpret_cast<const float*>(op.a0);
   const float* __restrict__ w = reinterpret_cast<const float*>(op.w) + (long)g * op.w_group_stride;
   // loaders: float4 f of a tile covers row f / 2, k offset (f & 1) * 4
   const int lk = (tid & 1) * 4;
   const float* ap[NA];
   bool a_ok[NA];
+  int ay[NA], ax[NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     const long r = row0 + (tid >> 1) + i * 128;
     a_ok[i] = r < row_end;
     ap[i] = a + (a_ok[i] ? r : row0) * op.ld0 + lk;
+    ax[i] = (int)(r % op.W); ay[i] = (int)((r / op.W) % op.H);
   }
   const int brow = tid >> 1;
   const bool b_act = brow < SBN, b_ok = b_act && (n0 + brow) < op.epi.N;
@@ -148,8 +152,19 @@ __global__ void __launch_bounds__(256, 2) k_sgemm_1x1(const SimtParams p) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto gload = [&](int k0) {
     const bool k_ok = k0 + lk < K;              // K % 4 == 0: a float4 is entirely inside or outside
+    if (KS == 1) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) ra[i] = (a_ok[i] && k_ok) ? __ldg(reinterpret_cast<const float4*>(ap[i] + k0)) : zero4;
+      for (int i = 0; i < NA; ++i) ra[i] = (a_ok[i] && k_ok) ? __ldg(reinterpret_cast<const float4*>(ap[i] + k0)) : zero4;
+    } else {
+      const int tap = k0 / op.c0, c = k0 - tap * op.c0;
+      const int dy = (tap / 3 - 1) * op.dil, dx = (tap % 3 - 1) * op.dil;
+      const long shift = ((long)dy * op.W + dx) * op.ld0 + c;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const bool in = a_ok[i] && k_ok && ay[i] + dy >= 0 && ay[i] + dy < op.H && ax[i] + dx >= 0 && ax[i] + dx < op.W;
+        ra[i] = in ? __ldg(reinterpret_cast<const float4*>(ap[i] + shift)) : zero4;
+      }
+    }
     rb = (b_ok && k_ok) ? __ldg(reinterpret_cast<const float4*>(bp + k0)) : zero4;
   };
   auto sstore = [&](int buf) {
@@ -200,7 +215,9 @@ __global__ void __launch_bounds__(256, 2) k_sgemm_1x1(const SimtParams p) {
 }
 
 bool sgemm_1x1_ok(const ConvOp& op) {
-  return op.kd == 1 && op.kh == 1 && op.kw == 1 && op.c1 == 0 && op.epi.mode == OUT_IDENTITY && op.c0 % 4 == 0 && op.ld0 % 4 == 0 &&
+  const bool k1 = op.kh == 1 && op.kw == 1 && op.c0 % 4 == 0;
+  const bool k3 = op.kh == 3 && op.kw == 3 && op.c0 % 8 == 0 && op.w_tap_ld == op.c0 && op.groups == 1;   // taps contiguous in K
+  return op.kd == 1 && (k1 || k3) && op.c1 == 0 && op.epi.mode == OUT_IDENTITY && op.ld0 % 4 == 0 &&
          op.w_ld % 4 == 0 && op.w_group_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(op.a0) & 15) &&
          !(reinterpret_cast<uintptr_t>(op.w) & 15);
 }
@@ -226,10 +243,15 @@ int conv_gemm_simt(const ConvOp& op, cudaStream_t s) {
   if constexpr (std::is_same<T, float>::value) {
     if (sgemm_1x1_ok(op)) {
       const int N = op.epi.N;
-      if (cdiv(N, 64) * 64 < cdiv(N, 128) * 128)        // narrow / ragged N: the 256 x 64 tile pads less
-        k_sgemm_1x1<8><<<dim3(cdiv(p.rows_per_group, 256), cdiv(N, 64), op.groups), 256, 0, s>>>(p);
-      else
-        k_sgemm_1x1<16><<<dim3(cdiv(p.rows_per_group, 128), cdiv(N, 128), op.groups), 256, 0, s>>>(p);
+      const bool narrow = cdiv(N, 64) * 64 < cdiv(N, 128) * 128;       // narrow / ragged N: the 256 x 64 tile pads less
+      const dim3 g8(cdiv(p.rows_per_group, 256), cdiv(N, 64), op.groups), g16(cdiv(p.rows_per_group, 128), cdiv(N, 128), op.groups);
+      if (op.kh == 3) {
+        if (narrow) k_sgemm_1x1<8, 3><<<g8, 256, 0, s>>>(p);
+        else k_sgemm_1x1<16, 3><<<g16, 256, 0, s>>>(p);
+      } else {
+        if (narrow) k_sgemm_1x1<8, 1><<<g8, 256, 0, s>>>(p);
+        else k_sgemm_1x1<16, 1><<<g16, 256, 0, s>>>(p);
+      }
       count_launch();
       KD_LAUNCH_CHECK();
       return 0;
