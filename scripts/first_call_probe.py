@@ -15,5 +15,5 @@ with torch.no_grad():
     outs = [m(x) for _ in range(4)]
     torch.cuda.synchronize()
 for i in range(1, 4):
-    print(f"S={S} B={B} mode={os.environ.get('KDLAE_FUSE_PWDW', '7')} run{i} vs run0: hq {float((outs[i]['hq'] - outs[0]['hq']).abs().max()):.3e} "
+    print(f"S={S} B={B} mode={os.environ.get('KDLAE_FUSE_PWDW', '6')} run{i} vs run0: hq {float((outs[i]['hq'] - outs[0]['hq']).abs().max()):.3e} "
           f"sr {float((outs[i]['sr'] - outs[0]['sr']).abs().max()):.3e}", flush=True)
