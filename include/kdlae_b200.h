@@ -198,6 +198,12 @@ int kdlae_mdta_forward_train(const float* x, const float* gamma, const float* w_
 int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
                         const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg,
                         int H, int W, int C, int heads, float* ws, void* stream);
+/* Precision of the 1x1-conv GEMMs (forward and dgrad) of the training entry points below: 0 (default) = fp32 on the CUDA cores,
+ * 1 = TF32 on tcgen05 with fp32 accumulation (gemm_tf32.cu) - what torch.backends.cudnn.allow_tf32 (PyTorch's default) gives
+ * the reference's nn.Conv2d layers on this GPU.  Process-wide; the initial value follows KDLAE_TRAIN_TF32=1.  wgrad, the dense
+ * 3x3 convs, the depthwise convs and every reduction stay fp32. */
+int kdlae_set_train_matmul_tf32(int on);
+int kdlae_train_matmul_tf32(void);
 /* The dense convolutions of KDLAE-T outside its TransformerBlocks in training mode (OverlapPatchEmbed KDLAE_model.py:169-178, the
  * Downsample / Upsample bodies :182-200, reduce_chan_level*, output, output_param (dilation 2), output2, cen, upen, outputen
  * :239-268): 1x1 or 3x3, stride 1, zero padding dilation * (ksize / 2), no bias; fp32 NHWC, w [Cout][ksize*ksize][Cin].

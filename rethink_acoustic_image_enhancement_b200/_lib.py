@@ -86,6 +86,8 @@ SIGNATURES = {
     "kdlae_mdta_train_ws_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "kdlae_mdta_forward_train": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "kdlae_mdta_backward": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "kdlae_set_train_matmul_tf32": (C.c_int, [C.c_int]),
+    "kdlae_train_matmul_tf32": (C.c_int, []),
     "kdlae_conv_train_ws_floats": (C.c_size_t, [C.c_int] * 6),
     "kdlae_conv_train_forward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]),
     "kdlae_conv_train_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),

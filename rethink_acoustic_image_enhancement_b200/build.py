@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libkdlae_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "conv3x3_tc.cu", "glue.cu", "dwconv_f2.cu", "pwdw_f2.cu", "pwdw_t.cu", "gram_tc.cu", "pack.cu", "prepost.cu", "metrics.cu", "train.cu", "teacher.cu", "student.cu", "asdqe.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tf32.cu", "conv3x3_tc.cu", "glue.cu", "dwconv_f2.cu", "pwdw_f2.cu", "pwdw_t.cu", "gram_tc.cu", "pack.cu", "prepost.cu", "metrics.cu", "train.cu", "teacher.cu", "student.cu", "asdqe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

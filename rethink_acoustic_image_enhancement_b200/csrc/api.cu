@@ -436,6 +436,11 @@ int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, 
   return kd::mdta_backward(x, gamma, w_qkv, w_dw, w_proj, temp, dout, dx, dgamma, dw_qkv, dw_dw, dw_proj, dtemp, nimg, H, W, C, heads, ws,
                            reinterpret_cast<cudaStream_t>(stream));
 }
+int kdlae_set_train_matmul_tf32(int on) {
+  kd::set_train_matmul_tf32(on);
+  return 0;
+}
+int kdlae_train_matmul_tf32(void) { return kd::train_matmul_tf32(); }
 size_t kdlae_conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ksize) {
   return (nimg > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ksize == 1 || ksize == 3)) ? kd::conv_train_ws_floats(nimg, H, W, Cin, Cout, ksize)
                                                                                          : 0;

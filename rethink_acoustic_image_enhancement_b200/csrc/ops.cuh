@@ -117,6 +117,12 @@ int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, c
 int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
                   const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg, int H,
                   int W, int C, int heads, float* ws, cudaStream_t s);
+// TF32 tensor-core GEMM for plain fp32 1x1 convs (gemm_tf32.cu); the training step routes its forward / dgrad GEMMs here when
+// train_matmul_tf32() is on (default off: fp32 CUDA-core kernels)
+bool gemm_tf32_eligible(const ConvOp& op);
+int gemm_tf32(const ConvOp& op, cudaStream_t s);
+void set_train_matmul_tf32(int on);
+int train_matmul_tf32();
 // dense 1x1 / 3x3 conv (dilation, zero padding, no bias) with backward, fp32 NHWC, weights [Cout][k*k][Cin]
 size_t conv_train_ws_floats(int nimg, int H, int W, int Cin, int Cout, int ks);
 int conv_train_forward(const float* x, const float* w, float* out, int nimg, int H, int W, int Cin, int Cout, int ks, int dil,

@@ -9,11 +9,27 @@
 // The end of the file holds the fused clip-norm + AdamW step over flat buffers.  tcgen05 dgrad / wgrad for the bf16 path and the
 // MDTA half of the block are the next steps of this row.
 #include <algorithm>
+#include <atomic>
 #include "ops.cuh"
 
 namespace kd {
 
 namespace {
+std::atomic<int> g_train_tf32{-1};
+}
+void set_train_matmul_tf32(int on) { g_train_tf32.store(on ? 1 : 0); }
+int train_matmul_tf32() {
+  int v = g_train_tf32.load();
+  if (v < 0) { const char* e = getenv("KDLAE_TRAIN_TF32"); v = (e && e[0] == '1') ? 1 : 0; g_train_tf32.store(v); }
+  return v;
+}
+
+namespace {
+// every fp32 GEMM of the training step goes through here: tcgen05 kind::tf32 when switched on and the shape allows, else CUDA cores
+int train_gemm(const ConvOp& g, cudaStream_t s) {
+  if (train_matmul_tf32() && gemm_tf32_eligible(g)) return gemm_tf32(g, s);
+  return conv_gemm_simt<float>(g, s);
+}
 
 constexpr int WG_T = 64, WG_P = 32;      // wgrad tile: 64 x 64 outputs, 32 pixels per step
 
@@ -188,7 +204,7 @@ int conv1x1_f32(const float* a, int C, const float* w, int N, const float* res, 
   ConvOp g;
   g.a0 = a; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.w = w; g.w_ld = C; g.w_tap_ld = C;
   g.epi.res = res; g.epi.res_ld = N; g.epi.out = out; g.epi.out_ld = N; g.epi.N = N; g.epi.H = H; g.epi.W = W;
-  return conv_gemm_simt<float>(g, s);
+  return train_gemm(g, s);
 }
 
 struct GdfnWs {
@@ -528,7 +544,7 @@ int grouped_1x1_f32(const float* a, int Cin, long lda, const float* w, int N, lo
   g.a0 = a; g.c0 = Cin; g.ld0 = lda; g.nimg = nimg; g.H = H; g.W = W; g.w = w; g.w_ld = Cin; g.w_tap_ld = Cin;
   g.groups = nimg; g.w_group_stride = w_group_stride;
   g.epi.out = out; g.epi.out_ld = ldo; g.epi.out_coff = coff; g.epi.N = N; g.epi.H = H; g.epi.W = W;
-  return conv_gemm_simt<float>(g, s);
+  return train_gemm(g, s);
 }
 }  // namespace
 
@@ -577,7 +593,7 @@ int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const 
     ConvOp g;
     g.a0 = dout; g.c0 = C; g.ld0 = C; g.nimg = nimg; g.H = H; g.W = W; g.w = L.wt; g.w_ld = C; g.w_tap_ld = C;
     g.epi.out = L.dov; g.epi.out_ld = 2 * C; g.epi.N = C; g.epi.H = H; g.epi.W = W;
-    KD_TRY(conv_gemm_simt<float>(g, s));
+    KD_TRY(train_gemm(g, s));
   }
   k_copy_cols<<<cdiv(P * C, 256), 256, 0, s>>>(L.u + 2 * C, 3 * C, L.dov + C, 2 * C, C, P);              // v -> columns [C, 2C)
   count_launch();
@@ -702,7 +718,7 @@ int conv_f32(const float* a, int Cin, const float* w, int Cout, float* out, int 
   g.a0 = a; g.c0 = Cin; g.ld0 = Cin; g.nimg = nimg; g.H = H; g.W = W; g.kh = ks; g.kw = ks; g.dil = dil;
   g.w = w; g.w_ld = (long)ks * ks * Cin; g.w_tap_ld = Cin;
   g.epi.out = out; g.epi.out_ld = Cout; g.epi.N = Cout; g.epi.H = H; g.epi.W = W;
-  return conv_gemm_simt<float>(g, s);
+  return train_gemm(g, s);
 }
 
 }  // namespace

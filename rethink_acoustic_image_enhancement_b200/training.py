@@ -25,6 +25,19 @@ import torch.distributed as dist
 from . import _lib
 
 
+def set_matmul_precision(mode: str) -> None:
+    """'fp32' (default): every GEMM of the training step on the CUDA cores in fp32.  'tf32': the 1x1-conv GEMMs (forward and
+    dgrad) on tcgen05 in TF32 with fp32 accumulation - what ``torch.backends.cudnn.allow_tf32`` (PyTorch's default) gives the
+    reference's ``nn.Conv2d`` layers on this GPU.  Process-wide (``kdlae_set_train_matmul_tf32``)."""
+    if mode not in ("fp32", "tf32"):
+        raise ValueError("set_matmul_precision: mode must be 'fp32' or 'tf32'")
+    _lib.check(_lib.load().kdlae_set_train_matmul_tf32(int(mode == "tf32")), "kdlae_set_train_matmul_tf32")
+
+
+def get_matmul_precision() -> str:
+    return "tf32" if _lib.load().kdlae_train_matmul_tf32() else "fp32"
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -415,4 +428,4 @@ class BucketedAllReducer:
 
 
 __all__ = ["gdfn_block_train", "mdta_block_train", "transformer_block_train", "conv_train", "teacher_train_forward", "FlatAdamW",
-           "BucketedAllReducer"]
+           "BucketedAllReducer", "set_matmul_precision", "get_matmul_precision"]

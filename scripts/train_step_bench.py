@@ -25,7 +25,7 @@ import rethink_acoustic_image_enhancement_b200 as pk  # noqa: E402
 from oracle import synth  # noqa: E402
 from rethink_acoustic_image_enhancement_b200 import _lib  # noqa: E402
 from rethink_acoustic_image_enhancement_b200.metrics import L1LossSr  # noqa: E402
-from rethink_acoustic_image_enhancement_b200.training import BucketedAllReducer, FlatAdamW  # noqa: E402
+from rethink_acoustic_image_enhancement_b200.training import BucketedAllReducer, FlatAdamW, get_matmul_precision, set_matmul_precision  # noqa: E402
 
 
 def main():
@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--tf32", action="store_true", help="1x1-conv GEMMs (forward, dgrad) on tcgen05 in TF32 (training.set_matmul_precision)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -43,6 +44,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier(); torch.cuda.synchronize()
         sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    if a.tf32:
+        set_matmul_precision("tf32")
     kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
     m = pk.KDLAE_teacher(**kw)
     m.load_state_dict(synth.teacher_state_dict(seed=0, temp_scale=1.0, **kw), strict=True)
@@ -89,10 +92,10 @@ def main():
     launches = (_lib.load().kdlae_launch_count() - n0) // a.steps
     if rank == 0:
         ls = [float(l) for l in losses]
-        print(json.dumps({"metric": "KDLAE-T training step images/sec (fp32 CUDA forward + backward + clip + AdamW" +
+        print(json.dumps({"metric": "KDLAE-T training step images/sec (CUDA forward + backward + clip + AdamW" +
                           (" + bucketed NCCL all-reduce)" if world > 1 else ")"),
                           "value": round(B * world / (float(ms) / 1e3), 3), "unit": "images/s", "n_gpus": world, "ms_per_step": round(float(ms), 2),
-                          "per_gpu_batch": B, "crop": S, "dtype": "f32", "params": sum(p.numel() for p in params),
+                          "per_gpu_batch": B, "crop": S, "dtype": "f32", "matmul": get_matmul_precision(), "params": sum(p.numel() for p in params),
                           "grad_bytes": opt.grad.numel() * 4, "buckets": len(red.bounds), "gpu_launches_per_step": int(launches),
                           "loss_first": round(ls[0], 6), "loss_last": round(ls[-1], 6),
                           "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}))

@@ -205,6 +205,77 @@ def test_teacher_training_step_gradients_match_oracle_autograd():
     assert max(errs.values()) < 1e-4, worst          # fp32 kernels vs float64 autograd through ~20 layers
 
 
+@pytest.fixture
+def tf32_matmul():
+    from rethink_acoustic_image_enhancement_b200 import training
+    training.set_matmul_precision("tf32")
+    yield
+    training.set_matmul_precision("fp32")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(2, 48, 40, 36, 144), (1, 96, 33, 17, 96), (3, 256, 16, 16, 96), (1, 384, 8, 8, 1152), (2, 20, 9, 7, 12)])
+def test_tf32_gemm_matches_float64_at_tf32_precision(case, tf32_matmul):
+    """gemm_tf32.cu (tcgen05 kind::tf32) through conv_train: forward and dgrad within TF32 rounding of float64 (operands keep 10
+    mantissa bits: ~5e-4 per product, fp32 accumulation), wgrad (fp32 CUDA cores) within 1e-5; K / N / row tails included."""
+    import torch.nn.functional as F
+    from rethink_acoustic_image_enhancement_b200 import training
+    B, Cin, H, W, Cout = case
+    assert training.get_matmul_precision() == "tf32"
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    dout = torch.randn(B, Cout, H, W, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = F.conv2d(xr, wr)
+    ref.backward(dout.double())
+    xc, wc = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    out = training.conv_train(xc, wc)
+    out.backward(dout.to(DEV))
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max())
+    errs = {"out": rel(out.detach(), ref.detach()), "dx": rel(xc.grad, xr.grad), "dw": rel(wc.grad, wr.grad)}
+    print(case, errs)
+    assert errs["out"] < 2e-3 and errs["dx"] < 2e-3 and errs["dw"] < 1e-5, errs
+    assert errs["out"] > 1e-6, "the TF32 path did not run (result is fp32-exact)"
+
+
+@pytest.mark.gpu
+def test_teacher_training_step_in_tf32_mode(tf32_matmul):
+    """Whole-model step with the 1x1 GEMMs on tcgen05 / TF32: loss and gradients against float64 oracle autograd at the accuracy
+    TF32 convolutions give (the reference's own GPU numerics under torch's default allow_tf32)."""
+    from oracle import functional as ofn, metrics as om, synth
+    from rethink_acoustic_image_enhancement_b200.metrics import L1LossSr
+    m, sd, kw = _small_teacher("train", 12)
+    m.train()
+    B, H, W = 2, 32, 48
+    img = synth.seeded_tensor("tstep.img", (B, 1, H, W), 1, "sonar")
+    rate = torch.tensor([0.3, 0.9]).view(B, 1, 1, 1).expand(B, 1, H, W).contiguous()
+    gt_hq = synth.seeded_tensor("tstep.hq", (B, 1, H, W), 2, "sonar")
+    gt_sr = synth.seeded_tensor("tstep.sr", (B, 1, 2 * H, 2 * W), 3, "sonar")
+    ref_p = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    hq_r, sr_r = ofn.teacher_forward(ref_p, img.double(), rate.double(), heads=kw["heads"], static="train", params="cat")
+    loss_r = om.l1_loss_sr({"hq": hq_r, "sr": sr_r}, {"hq": gt_hq.double(), "sr": gt_sr.double()}, 1.0)
+    loss_r.backward()
+    out = m({"img": img.to(DEV), "denoise_rate": rate.to(DEV)})
+    loss = L1LossSr(loss_weight=1.0)(out, {"hq": gt_hq.to(DEV), "sr": gt_sr.to(DEV)})
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    e_hq, e_sr = rel(out["hq"].detach(), hq_r.detach()), rel(out["sr"].detach(), sr_r.detach())
+    # ~20 blocks deep, an L1 (sign) loss and a sharpened softmax amplify the 2e-3 per-block TF32 error of the gradients (measured
+    # per block by scripts/tf32_block_probe.py) to ten per cent of a tensor's largest element in places (the fp32 path amplifies
+    # its 5e-7 to 1e-4 the same way), so the whole-model check is on the direction of every gradient tensor
+    cos = {k: float(torch.nn.functional.cosine_similarity(p.grad.double().cpu().flatten(), ref_p[k].grad.flatten(), dim=0))
+           for k, p in m.named_parameters()}
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:3]
+    print(f"tf32: hq {e_hq:.2e} sr {e_sr:.2e} loss {abs(float(loss.detach()) - float(loss_r.detach())):.2e} lowest gradient cosines "
+          f"{[(k, f'{v:.4f}') for k, v in worst]}")
+    assert e_hq < 5e-3 and e_sr < 5e-3
+    assert abs(float(loss.detach()) - float(loss_r.detach())) < 1e-3 * abs(float(loss_r.detach()))
+    assert min(cos.values()) > 0.98, worst
+
+
 @pytest.mark.gpu
 def test_frozen_teacher_propagates_input_gradients():
     """eval() teacher as a loss term on another network's output (the KD setting): d loss / d input from the CUDA backward."""
