@@ -7,7 +7,7 @@ One step = what ImageCleanModel.optimize_parameters does (image_restoration_mode
 (dim 48, blocks 4/6/6/8, 1 channel, BiasFree, static='train'; 26.9 M parameters): zero_grad, forward on a batch of lq crops with a
 denoise-rate map, L1LossSr against hq and 2x sr targets, backward, clip_grad_norm_(0.01) + AdamW - and, with N > 1 ranks, the DDP
 gradient all-reduce (25 MB buckets on a communication stream, launched from gradient hooks while the backward still runs).  Every
-arithmetic kernel is from libkdlae_b200.so (fp32 CUDA-core kernels: a correctness-first slice).  KDLAET.yml trains
+arithmetic kernel is from libkdlae_b200.so (fp32 CUDA-core kernels by default, --tf32 puts the 1x1-conv GEMMs on tcgen05: DESIGN.md).  KDLAET.yml trains
 on 128 x 128 crops with 1-6 crops per GPU.  Timed on the device with CUDA events, max over ranks; rank 0 prints one JSON line.
 """
 import argparse
