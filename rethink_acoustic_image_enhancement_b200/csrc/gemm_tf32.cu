@@ -6,6 +6,9 @@
 // Operands arrive by TMA as 128-byte-swizzled K-major tiles of 32 floats per row (one swizzle atom), four K = 8 MMAs per tile;
 // persistent CTAs, warp 0 producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue (one TMEM lane quarter each),
 // two 256-column accumulators so the epilogue of a tile overlaps the MMAs of the next.  K and N tails are TMA zero fill.
+// (wgrad needs MN-major operands - the reduction runs over pixels.  A kind::tf32 MMA over 128B-swizzled MN-major fp32 tiles, the
+// layout gram_tc.cu uses for bf16, returned zeros on B200: 32-bit MN-major operands need the 32-byte-atom swizzle mode
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / descriptor layout type 1), not brought up here - wgrad stays on the CUDA cores.)
 #include <algorithm>
 #include "sm100.cuh"
 
