@@ -6,9 +6,9 @@
 // Operands arrive by TMA as 128-byte-swizzled K-major tiles of 32 floats per row (one swizzle atom), four K = 8 MMAs per tile;
 // persistent CTAs, warp 0 producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue (one TMEM lane quarter each),
 // two 256-column accumulators so the epilogue of a tile overlaps the MMAs of the next.  K and N tails are TMA zero fill.
-// (wgrad needs MN-major operands - the reduction runs over pixels.  A kind::tf32 MMA over 128B-swizzled MN-major fp32 tiles, the
-// layout gram_tc.cu uses for bf16, returned zeros on B200: 32-bit MN-major operands need the 32-byte-atom swizzle mode
-// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / descriptor layout type 1), not brought up here - wgrad stays on the CUDA cores.)
+// The wgrad kernel below runs over MN-major operands (the reduction is over pixels): 32-bit MN-major tiles need the 128-byte swizzle
+// with 32-byte atoms (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1, K groups of 4 rows) - with the ordinary
+// 128B swizzle that gram_tc.cu uses for bf16 a kind::tf32 MMA returns zeros.
 #include <algorithm>
 #include "sm100.cuh"
 
@@ -180,18 +180,200 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 }
 
-int make_map_f32(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+int make_map_f32(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   KD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// wgrad of a 1x1 conv on the same tensor-core path:  part[split][n][k] = sum_{p in split} A[p][n] * B[p][k]
+// (A = dY [P][N], B = X [P][K], both row-major in the pixel).  The reduction runs over pixels, so both operands are MN-major:
+// a TMA box {32 floats, 32 pixels} lands as rows of 128 bytes whose 32-byte pieces are permuted by (row mod 4) - the MN-major
+// canonical layout for 32-bit operands; M = 128 rows of n per CTA = four such chunks (LBO = chunk stride), N = up to 256 columns
+// of k = eight, K = 8 pixels per tcgen05.mma = two 4-row groups (SBO = 512 B), fp32 accumulation in TMEM over the CTA's whole
+// pixel split; the partials are reduced in fixed order by the caller.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int WT_PIX = 32, WT_STAGES = 4;
+constexpr uint32_t WT_CHUNK = WT_PIX * 128;                       // 32 pixels x 32 floats
+constexpr uint32_t WT_STAGE = (4 + 8) * WT_CHUNK;                 // A chunks, then up to 8 B chunks
+constexpr uint32_t WT_SMEM = WT_STAGES * WT_STAGE + 1024 + 128;
+
+struct WtParams {
+  int N, K, kc, nbch, k_tiles;
+  long P;
+  int per;               // pixels per split, a multiple of WT_PIX
+  float* part;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // stride between 32-float MN chunks
+  d |= (uint64_t)(512 >> 4) << 32;                        // stride between 4-pixel K groups
+  d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;                                 // layout type 1: SWIZZLE_128B with 32-byte atoms
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1)
+k_wgrad_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + WT_STAGES * WT_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WT_STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * WT_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WT_STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x / p.k_tiles, kt = blockIdx.x % p.k_tiles, split = blockIdx.y;
+  const long p_begin = (long)split * p.per, p_end = min(p.P, p_begin + p.per);
+  const int nsteps = p_end > p_begin ? (int)((p_end - p_begin + WT_PIX - 1) / WT_PIX) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % WT_STAGES;
+      mbar_wait_relaxed(empty_bar(s), ((i / WT_STAGES) & 1) ^ 1);
+      const uint32_t dst = sbase + s * WT_STAGE;
+      const int px = (int)(p_begin + (long)i * WT_PIX);
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), (uint32_t)(4 + p.nbch) * WT_CHUNK);
+        for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * WT_CHUNK, &map_a, full_bar(s), nt * 128 + c * 32, px, 0);
+        for (int c = 0; c < p.nbch; ++c) tma_load_3d(dst + (4 + c) * WT_CHUNK, &map_b, full_bar(s), kt * 256 + c * 32, px, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // D = f32, A = B = tf32, both MN-major, M = 128, N = kc
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.kc >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % WT_STAGES;
+      mbar_wait(full_bar(s), (i / WT_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t aa = sbase + s * WT_STAGE, ba = aa + 4 * WT_CHUNK;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < WT_PIX / 8; ++k)
+          umma_tf32(tmem_base, make_desc_mn32(aa + k * 1024, WT_CHUNK), make_desc_mn32(ba + k * 1024, WT_CHUNK), idesc, (i | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  }
+  __syncwarp();
+
+  // epilogue: all four warps, thread = accumulator row n
+  const int n = nt * 128 + warp * 32 + lane;
+  float* dst = p.part + ((long)split * p.N + n) * p.K + kt * 256;
+  if (nsteps > 0) {
+    mbar_wait_relaxed(done_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.kc; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16_issue(t_row + c0, v);
+      tmem_ld16_wait(v);
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (kt * 256 + c0 + j < p.K) dst[c0 + j] = __uint_as_float(v[j]);
+      }
+    }
+  } else if (n < p.N) {
+    for (int j = 0; j < p.kc; ++j)
+      if (kt * 256 + j < p.K) dst[j] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
 }  // namespace
+
+bool wgrad_tf32_eligible(const float* A, long lda, int N, const float* B, long ldb, int K) {
+  return N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && !(reinterpret_cast<uintptr_t>(A) & 15) &&
+         !(reinterpret_cast<uintptr_t>(B) & 15);
+}
+
+// part[split][n][k] over pixel ranges that are multiples of 32 pixels; *splits_out = the number of splits written (<= splits)
+int wgrad_tf32(const float* A, long lda, int N, const float* B, long ldb, int K, long P, float* part, int splits, int* splits_out,
+               cudaStream_t s) {
+  KD_CHECK(wgrad_tf32_eligible(A, lda, N, B, ldb, K), "wgrad_tf32: shape not eligible");
+  static DeviceOnce once;
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  if (first) {
+    KD_CUDA(cudaFuncSetAttribute(k_wgrad_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    device_mark(once, dev);
+  }
+  WtParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.K = K; p.P = P; p.part = part;
+  p.k_tiles = (K + 255) / 256;
+  p.kc = p.k_tiles == 1 ? (K + 15) / 16 * 16 : 256;
+  p.nbch = (p.kc + 31) / 32;
+  long per = (P + splits - 1) / splits;
+  per = (per + WT_PIX - 1) / WT_PIX * WT_PIX;
+  p.per = (int)per;
+  const int used = (int)((P + per - 1) / per);
+  *splits_out = used;
+  CUtensorMap ma, mb;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)P, 1};
+    const cuuint64_t str[2] = {(cuuint64_t)lda * 4, (cuuint64_t)lda * 4 * P};
+    const cuuint32_t box[3] = {32, WT_PIX, 1};
+    KD_TRY(make_map_f32(&ma, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)P, 1};
+    const cuuint64_t str[2] = {(cuuint64_t)ldb * 4, (cuuint64_t)ldb * 4 * P};
+    const cuuint32_t box[3] = {32, WT_PIX, 1};
+    KD_TRY(make_map_f32(&mb, B, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  const int n_tiles = (N + 127) / 128;
+  ProfScope prof(PC_GEMM_TC, s, 2.0 * P * N * K, 4.0 * (double)P * (N + K));
+  k_wgrad_tf32<<<dim3(n_tiles * p.k_tiles, used), 128, WT_SMEM, s>>>(ma, mb, p);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
 
 // 1x1, one source, identity addressing, no row scale / bias / ReLU / statistics: what the training step's GEMMs use
 bool gemm_tf32_eligible(const ConvOp& op) {

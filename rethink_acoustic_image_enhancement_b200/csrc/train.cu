@@ -172,6 +172,14 @@ __global__ void k_flip9(const float* __restrict__ w9c, int C, float* __restrict_
 
 int wgrad_1x1(const float* A, long lda, int N, const float* B, long ldb, int K, long P, float* out, float* part, int splits,
               cudaStream_t s) {
+  if (train_matmul_tf32() && wgrad_tf32_eligible(A, lda, N, B, ldb, K)) {     // tcgen05 kind::tf32, MN-major operands (gemm_tf32.cu)
+    int used = splits;
+    KD_TRY(wgrad_tf32(A, lda, N, B, ldb, K, P, part, splits, &used, s));
+    k_sum_parts<<<cdiv((long)N * K, 256), 256, 0, s>>>(part, used, (long)N * K, out);
+    count_launch();
+    KD_LAUNCH_CHECK();
+    return 0;
+  }
   const int per = (int)((P + splits - 1) / splits);
   ProfScope prof(PC_GEMM_SIMT, s, 2.0 * P * N * K, 4.0 * (double)P * (N + K));
   k_wgrad_part<<<dim3(cdiv(N, WG_T), cdiv(K, WG_T), splits), 256, 0, s>>>(A, lda, N, B, ldb, K, P, per, part);
@@ -749,6 +757,7 @@ int conv_train_backward(const float* x, const float* w, const float* dout, float
     KD_LAUNCH_CHECK();
     KD_TRY(conv_f32(dout, Cout, wt, Cin, dx, nimg, H, W, ks, dil, s));
   }
+  if (ks == 1) return wgrad_1x1(dout, Cout, Cout, x, Cin, Cin, P, dw, part, splits, s);   // same reduction as the blocks' 1x1 convs
   const int per = (int)((P + splits - 1) / splits);
   KD_CHECK((long)splits * taps <= 65535, "conv_train_backward: grid too large");
   {

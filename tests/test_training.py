@@ -214,10 +214,13 @@ def tf32_matmul():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [(2, 48, 40, 36, 144), (1, 96, 33, 17, 96), (3, 256, 16, 16, 96), (1, 384, 8, 8, 1152), (2, 20, 9, 7, 12)])
+@pytest.mark.parametrize("case", [(2, 48, 40, 36, 144), (1, 96, 33, 17, 96), (3, 256, 16, 16, 96), (1, 384, 8, 8, 1152), (2, 20, 9, 7, 12),
+                                  (1, 512, 12, 10, 96)])
 def test_tf32_gemm_matches_float64_at_tf32_precision(case, tf32_matmul):
-    """gemm_tf32.cu (tcgen05 kind::tf32) through conv_train: forward and dgrad within TF32 rounding of float64 (operands keep 10
-    mantissa bits: ~5e-4 per product, fp32 accumulation), wgrad (fp32 CUDA cores) within 1e-5; K / N / row tails included."""
+    """gemm_tf32.cu (tcgen05 kind::tf32) through conv_train: forward, dgrad (K-major operands) and wgrad (MN-major operands with
+    the 32-byte-atom swizzle, pixel splits) within TF32 rounding of float64 (operands keep 10 mantissa bits: ~5e-4 per product,
+    fp32 accumulation); K / N / row / pixel-split tails included.  Shapes the tensor-core kernels do not take (channels not a
+    multiple of 4) fall back to the fp32 CUDA-core kernels."""
     import torch.nn.functional as F
     from rethink_acoustic_image_enhancement_b200 import training
     B, Cin, H, W, Cout = case
@@ -236,8 +239,8 @@ def test_tf32_gemm_matches_float64_at_tf32_precision(case, tf32_matmul):
     rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max())
     errs = {"out": rel(out.detach(), ref.detach()), "dx": rel(xc.grad, xr.grad), "dw": rel(wc.grad, wr.grad)}
     print(case, errs)
-    assert errs["out"] < 2e-3 and errs["dx"] < 2e-3 and errs["dw"] < 1e-5, errs
-    assert errs["out"] > 1e-6, "the TF32 path did not run (result is fp32-exact)"
+    assert errs["out"] < 2e-3 and errs["dx"] < 2e-3 and errs["dw"] < 2e-3, errs
+    assert errs["out"] > 1e-6 and errs["dw"] > 1e-6, "the TF32 kernels did not run (results are fp32-exact)"
 
 
 @pytest.mark.gpu
