@@ -198,9 +198,9 @@ int kdlae_mdta_forward_train(const float* x, const float* gamma, const float* w_
 int kdlae_mdta_backward(const float* x, const float* gamma, const float* w_qkv, const float* w_dw, const float* w_proj, const float* temp,
                         const float* dout, float* dx, float* dgamma, float* dw_qkv, float* dw_dw, float* dw_proj, float* dtemp, int nimg,
                         int H, int W, int C, int heads, float* ws, void* stream);
-/* Precision of the 1x1-conv GEMMs (forward and dgrad) of the training entry points below: 0 (default) = fp32 on the CUDA cores,
+/* Precision of the 1x1-conv GEMMs (forward, dgrad and wgrad) of the training entry points below: 0 (default) = fp32 on the CUDA cores,
  * 1 = TF32 on tcgen05 with fp32 accumulation (gemm_tf32.cu) - what torch.backends.cudnn.allow_tf32 (PyTorch's default) gives
- * the reference's nn.Conv2d layers on this GPU.  Process-wide; the initial value follows KDLAE_TRAIN_TF32=1.  wgrad, the dense
+ * the reference's nn.Conv2d layers on this GPU.  Process-wide; the initial value follows KDLAE_TRAIN_TF32=1.  The dense
  * 3x3 convs, the depthwise convs and every reduction stay fp32. */
 int kdlae_set_train_matmul_tf32(int on);
 int kdlae_train_matmul_tf32(void);

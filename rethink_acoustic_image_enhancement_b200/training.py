@@ -26,8 +26,8 @@ from . import _lib
 
 
 def set_matmul_precision(mode: str) -> None:
-    """'fp32' (default): every GEMM of the training step on the CUDA cores in fp32.  'tf32': the 1x1-conv GEMMs (forward and
-    dgrad) on tcgen05 in TF32 with fp32 accumulation - what ``torch.backends.cudnn.allow_tf32`` (PyTorch's default) gives the
+    """'fp32' (default): every GEMM of the training step on the CUDA cores in fp32.  'tf32': the 1x1-conv GEMMs (forward,
+    dgrad and wgrad) on tcgen05 in TF32 with fp32 accumulation - what ``torch.backends.cudnn.allow_tf32`` (PyTorch's default) gives the
     reference's ``nn.Conv2d`` layers on this GPU.  Process-wide (``kdlae_set_train_matmul_tf32``)."""
     if mode not in ("fp32", "tf32"):
         raise ValueError("set_matmul_precision: mode must be 'fp32' or 'tf32'")

@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--tf32", action="store_true", help="1x1-conv GEMMs (forward, dgrad) on tcgen05 in TF32 (training.set_matmul_precision)")
+    ap.add_argument("--tf32", action="store_true", help="1x1-conv GEMMs (forward, dgrad, wgrad) on tcgen05 in TF32 (training.set_matmul_precision)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
