@@ -118,7 +118,26 @@ class L1LossSr(torch.nn.Module):
         return _L1SrFn.apply(hq, target["hq"], sr, target["sr"] if sr is not None else None, self.loss_weight)
 
 
-def validate(model, batches: Iterable[dict], crop_border: int = 0, use_image: bool = True, key: str = "hq") -> Dict[str, float]:
+def pad_test(model, lq: Dict[str, torch.Tensor], window_size: int = 8) -> Dict[str, Optional[torch.Tensor]]:
+    """``ImageCleanModel.pad_test`` (image_restoration_model.py:226-237) for the dict-input teacher: reflect-pad ``lq['img']`` (and a
+    full-size rate map) at the bottom / right to a multiple of ``window_size``, run the forward, crop ``hq`` back and ``sr`` back
+    at twice the size.  (The reference calls ``self.lq.size()`` on the dict there and cannot run this hook for KDLAE-T; the
+    padding itself is torch data movement on the device.)"""
+    img, rate = lq["img"], lq["denoise_rate"]
+    _, _, h, w = img.shape
+    ph, pw = (-h) % window_size, (-w) % window_size
+    if ph or pw:
+        img = torch.nn.functional.pad(img, (0, pw, 0, ph), "reflect")
+        if rate.dim() == 4 and rate.shape[-2:] == (h, w):
+            rate = torch.nn.functional.pad(rate, (0, pw, 0, ph), "reflect")
+    out = model({"img": img, "denoise_rate": rate})
+    hq = out["hq"][:, :, :h, :w]
+    sr = out["sr"][:, :, :2 * h, :2 * w] if out.get("sr") is not None else None
+    return {"hq": hq, "sr": sr}
+
+
+def validate(model, batches: Iterable[dict], crop_border: int = 0, use_image: bool = True, key: str = "hq",
+             window_size: int = 0) -> Dict[str, float]:
     """Metric part of ``nondist_validation`` (image_restoration_model.py:264-348) for the dict-input teacher: for every batch
     ``{'lq': {'img','denoise_rate'}, 'gt': {'hq','sr'}}`` run the forward and accumulate PSNR **on the device** - no per-image
     ``.cpu()``, no ``torch.cuda.empty_cache()`` per iteration (:299); one host read at the end."""
@@ -129,7 +148,7 @@ def validate(model, batches: Iterable[dict], crop_border: int = 0, use_image: bo
     try:
         with torch.no_grad():
             for data in batches:
-                out = model(data["lq"])
+                out = pad_test(model, data["lq"], window_size) if window_size else model(data["lq"])   # val.window_size (:283-287)
                 p = psnr_batch(out[key], data["gt"][key].to(out[key].device), crop_border, as_uint8=use_image)
                 total = p.sum() if total is None else total + p.sum()
                 cnt += p.numel()
@@ -138,4 +157,4 @@ def validate(model, batches: Iterable[dict], crop_border: int = 0, use_image: bo
     return {"psnr": float(total.item()) / max(cnt, 1) if total is not None else math.nan, "count": cnt}
 
 
-__all__: List[str] = ["psnr_batch", "calculate_psnr", "L1LossSr", "validate"]
+__all__: List[str] = ["psnr_batch", "calculate_psnr", "L1LossSr", "pad_test", "validate"]

@@ -110,3 +110,32 @@ def test_validation_loop_psnr_on_device():
     # uint8 quantisation can flip a pixel by one level where the fp32 paths differ by 1e-6: tolerance on the mean PSNR
     assert abs(res["psnr"] - float(np.mean(ref))) < 0.02, (res, ref)
     assert not m.training
+
+
+@pytest.mark.gpu
+def test_pad_test_hook_matches_oracle_on_a_ragged_image():
+    """pad_test (image_restoration_model.py:226-237): a 36 x 44 image is reflect-padded to 40 x 48, run, and cropped back -
+    against the same recipe around the oracle forward (fp32 path), through validate(window_size=8) as well."""
+    import torch.nn.functional as F
+    import oracle
+    from oracle import synth
+    import rethink_acoustic_image_enhancement_b200 as pk
+    from rethink_acoustic_image_enhancement_b200 import metrics as pm
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="train")
+    sd = synth.teacher_state_dict(seed=6, temp_scale=2.0, **kw)
+    m = pk.KDLAE_teacher(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision("fp32")
+    img = synth.seeded_tensor("padtest.img", (1, 1, 36, 44), 6, "sonar")
+    rate = torch.full((1, 1, 36, 44), 0.4)
+    with torch.no_grad():
+        got = pm.pad_test(m, {"img": img.to(DEV), "denoise_rate": rate.to(DEV)}, 8)
+        pi, pr = F.pad(img, (0, 4, 0, 4), "reflect"), F.pad(rate, (0, 4, 0, 4), "reflect")
+        hq_ref, sr_ref = oracle.teacher_forward(sd, pi, pr)
+    assert got["hq"].shape == (1, 1, 36, 44) and got["sr"].shape == (1, 1, 72, 88)
+    assert float((got["hq"].cpu() - hq_ref[:, :, :36, :44]).abs().max()) < 1e-4
+    assert float((got["sr"].cpu() - sr_ref[:, :, :72, :88]).abs().max()) < 1e-4
+    gt = (img * 0.8).clamp(0, 1)
+    res = pm.validate(m, [{"lq": {"img": img.to(DEV), "denoise_rate": rate.to(DEV)}, "gt": {"hq": gt.to(DEV)}}], window_size=8)
+    ref = om.calculate_psnr(om.tensor2img_u8(hq_ref[0, :, :36, :44]), om.tensor2img_u8(gt[0]), 0)
+    assert res["count"] == 1 and abs(res["psnr"] - ref) < 0.02
