@@ -344,6 +344,10 @@ class FlatAdamW:
                                             self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1],
                                             self.eps, self.weight_decay, self.steps, float(self.max_norm or 0.0),
                                             self._norm_sq.data_ptr() if clip else None, _stream()), "kdlae_adamw_step")
+            # the kernel wrote the parameters through raw pointers: bump their autograd version counters (one multi-tensor no-op),
+            # so that everything keyed on them - the packed-weight cache of the fused inference forward - sees the update
+            with torch.no_grad():
+                torch._foreach_add_(self.params, 0.0)
 
     def _require_cuda(self) -> None:
         if self.flat.device.type != "cuda":

@@ -322,3 +322,33 @@ def test_fused_clip_adamw_matches_torch():
     torch.cuda.synchronize()
     for p, q in zip(ref, cu):
         assert torch.allclose(q.detach().cpu(), p.detach(), rtol=2e-6, atol=2e-7), float((q.detach().cpu() - p.detach()).abs().max())
+
+
+@pytest.mark.gpu
+def test_inference_after_a_training_step_uses_the_updated_weights():
+    """FlatAdamW writes the parameters from a CUDA kernel; the fused eval() forward caches packed weights keyed on the tensors'
+    version counters - after a step it must repack (compare with a fresh module loaded from the trained state_dict)."""
+    import rethink_acoustic_image_enhancement_b200 as pk
+    from oracle import synth
+    from rethink_acoustic_image_enhancement_b200.metrics import L1LossSr
+    from rethink_acoustic_image_enhancement_b200.training import FlatAdamW
+    m, sd, kw = _small_teacher("train", 21)
+    x = {"img": synth.seeded_tensor("upd.img", (1, 1, 32, 32), 1, "sonar").to(DEV), "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)}
+    gt = {"hq": torch.rand(1, 1, 32, 32, device=DEV), "sr": torch.rand(1, 1, 64, 64, device=DEV)}
+    m.eval().set_precision("fp32")
+    with torch.no_grad():
+        before = m(x)["hq"].clone()                       # fills the packed-weight cache
+    opt = FlatAdamW(m.parameters(), lr=1e-2, max_norm=0.0)
+    m.train()
+    opt.zero_grad()
+    L1LossSr()(m(x), gt).backward()
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        after = m(x)["hq"]
+        fresh = pk.KDLAE_teacher(**kw)
+        fresh.load_state_dict({k: v.detach().clone() for k, v in m.state_dict().items()}, strict=True)
+        fresh = fresh.to(DEV).eval().set_precision("fp32")
+        ref = fresh(x)["hq"]
+    assert float((after - before).abs().max()) > 1e-4, "the step did not change the output: stale packed weights"
+    assert torch.equal(after, ref)
