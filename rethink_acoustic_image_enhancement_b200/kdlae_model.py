@@ -131,6 +131,18 @@ class _FusedModule(nn.Module):
         self._engine.invalidate()
         return super()._apply(fn, *args, **kwargs)
 
+    def train(self, mode: bool = True):
+        """The packed kernel weights are keyed on the parameters' (data_ptr, version counter).  An in-place update through
+        ``param.data`` (the reference's own ``model_ema``, base_model.py) does not move either, so every ``train()`` / ``eval()``
+        call - which the reference's validation hooks make before each forward - also drops the packed copy."""
+        self._engine.invalidate()
+        return super().train(mode)
+
+    def refresh_weights(self) -> "_FusedModule":
+        """Force a re-pack of the kernel weights at the next forward (after modifying parameters through ``.data``)."""
+        self._engine.invalidate()
+        return self
+
     def _wants_autograd(self, *inputs: Optional[torch.Tensor]) -> bool:
         if not torch.is_grad_enabled():
             return False

@@ -395,3 +395,21 @@ def test_minimum_and_ragged_sizes_against_oracle(precision):
         err = (got - ref).abs().max().item()
         print(f"asdqe {h}x{w} {precision}: score max|d|={err:.3e}")
         assert err <= 1e-3
+
+
+def test_in_place_update_through_data_is_picked_up_at_the_next_eval_call():
+    """The reference's model_ema updates `param.data` in place, which moves neither data_ptr nor the version counter: the packed
+    kernel weights must be dropped by the eval() call its validation hook makes before the forward."""
+    kw = dict(inp_channels=1, out_channels=1, LayerNorm_type="BiasFree", static="no")
+    m = _teacher(kw, 5, 1.0, "fp32")
+    x = {"img": synth.seeded_tensor("ema.img", (1, 1, 32, 32), 5, "sonar").to(DEV), "denoise_rate": torch.full((1, 1, 1, 1), 0.5, device=DEV)}
+    with torch.no_grad():
+        a = m(x)["hq"].clone()
+        for p in m.parameters():
+            p.data.mul_(0.9)                 # model_ema-style update
+        m.eval()
+        b = m(x)["hq"].clone()
+        fresh = pk.KDLAE_teacher(**kw)
+        fresh.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+        c = fresh.to(DEV).eval().set_precision("fp32")(x)["hq"]
+    assert float((a - b).abs().max()) > 1e-5 and torch.equal(b, c)
