@@ -17,6 +17,8 @@
 // with the gate 8 x 4 columns in two passes).
 // t tiles are double buffered, so the conversion of item n+1 and the GEMM of item n+2 run under the depthwise of item n
 // (item = (tile, channel block)).
+// Role in the default schedule: every fused pair of a WithBias-LayerNorm model (this kernel carries the mean / bias fold, template
+// WB) and the bit-identical-to-unfused reference of the tests; BiasFree models take pwdw_t.cu (KDLAE_FUSE_PWDW, teacher.cu).
 #include <algorithm>
 #include "sm100.cuh"
 
