@@ -1,5 +1,7 @@
-// TF32 tensor-core GEMM for the 1x1 convolutions of the training step (fp32 storage, tcgen05 kind::tf32, fp32 accumulation):
+// TF32 tensor-core GEMM for the dense convolutions of the training step (fp32 storage, tcgen05 kind::tf32, fp32 accumulation):
 //   out[p][n] = sum_k A[p][k] * W[n][k] (+ res[p][n]),   A [P][K] fp32 (row stride ld0), W [N][K] fp32 (per-image groups optional)
+// and, for the dense 3x3 convs, the same sum over nine taps: the A tile of a tap is the 16 x 8 pixel patch shifted by the tap
+// (TMA box coordinates; zero padding = out-of-bounds fill; dilation = a longer shift), W [N][tap][K].
 // Opt-in (training.set_matmul_precision("tf32") / KDLAE_TRAIN_TF32=1): PyTorch itself runs the reference's nn.Conv2d layers in
 // TF32 on an Ampere-or-newer GPU by default (torch.backends.cudnn.allow_tf32), the fp32 CUDA-core path stays the default here
 // because the gradient-parity tests hold it to 1e-5 of float64 autograd.
@@ -27,6 +29,9 @@ struct TfParams {
   int tiles_per_group;
   long items;
   float inv_n_chunks, inv_tiles_per_group;
+  // dense 3x3 conv (dilation dil, zero padding = TMA out-of-bounds fill): tiles are 16 x 8 pixel patches, 9 taps x kchunks K steps
+  int spatial, taps, dil, H, W, tiles_x, tiles_y;
+  float inv_tiles_x, inv_tiles_y;
   const float* res; long res_ld;
   float* out; long out_ld; int out_coff;
 };
@@ -45,6 +50,7 @@ __device__ __forceinline__ void umma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, u
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TfParams p) {
+  constexpr int TW = 16, TH = 8;          // spatial tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + TF_STAGES * TF_STAGE;
@@ -71,12 +77,20 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // linear mode: g = weight group, r0 = first row in the group.  spatial mode: g = image, r0 = (ty0 << 16) | tx0
   auto coord = [&](long item64, int& g, int& r0, int& nchunk) {
     const int item = (int)item64;
     const int mt = fast_div(item, p.n_chunks, p.inv_n_chunks);
     nchunk = item - mt * p.n_chunks;
-    g = fast_div(mt, p.tiles_per_group, p.inv_tiles_per_group);
-    r0 = (mt - g * p.tiles_per_group) * TF_BM;
+    if (p.spatial) {
+      const int rowt = fast_div(mt, p.tiles_x, p.inv_tiles_x);
+      const int txi = mt - rowt * p.tiles_x;
+      g = fast_div(rowt, p.tiles_y, p.inv_tiles_y);
+      r0 = (((rowt - g * p.tiles_y) * TH) << 16) | (txi * TW);
+    } else {
+      g = fast_div(mt, p.tiles_per_group, p.inv_tiles_per_group);
+      r0 = (mt - g * p.tiles_per_group) * TF_BM;
+    }
   };
 
   if (warp == 0) {
@@ -86,16 +100,24 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
       int g, r0, nchunk;
       coord(item, g, r0, nchunk);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait_relaxed(empty_bar(s), ph ^ 1);
-        if (elect_one()) {
-          const uint32_t a_dst = smem_base + s * TF_STAGE;
-          mbar_expect_tx(full_bar(s), stage_tx);
-          tma_load_3d(a_dst, &map_a, full_bar(s), kc * TF_BK, r0, g);
-          tma_load_3d(a_dst + TF_A_BYTES, &map_w, full_bar(s), kc * TF_BK, nchunk * p.nc, g);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dx = (tap % 3 - 1) * p.dil, dy = (tap / 3 - 1) * p.dil;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait_relaxed(empty_bar(s), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + s * TF_STAGE;
+            mbar_expect_tx(full_bar(s), stage_tx);
+            if (p.spatial) {
+              tma_load_4d(a_dst, &map_a, full_bar(s), kc * TF_BK, (r0 & 0xFFFF) + dx, (r0 >> 16) + dy, g);
+              tma_load_3d(a_dst + TF_A_BYTES, &map_w, full_bar(s), kc * TF_BK, nchunk * p.nc, tap);
+            } else {
+              tma_load_3d(a_dst, &map_a, full_bar(s), kc * TF_BK, r0, g);
+              tma_load_3d(a_dst + TF_A_BYTES, &map_w, full_bar(s), kc * TF_BK, nchunk * p.nc, g);
+            }
+          }
+          __syncwarp();
+          if (++s == TF_STAGES) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == TF_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -110,14 +132,15 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(tempty_bar(acc), aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * TF_NC_MAX;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int kt = 0; kt < p.taps * p.kchunks; ++kt) {
+        const int kc = p.taps == 1 ? kt : kt % p.kchunks;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t a_lo = (((smem_base + s * TF_STAGE) & 0x3FFFF) >> 4) | lo_tag;
         const uint32_t b_lo = (((smem_base + s * TF_STAGE + TF_A_BYTES) & 0x3FFFF) >> 4) | lo_tag;
         const int rem = p.K - kc * TF_BK;
         const int ksn = rem >= TF_BK ? 4 : (rem + 7) >> 3;      // K = 8 steps that hold real channels (the rest is zero fill)
-        const uint32_t first = kc != 0 ? 1u : 0u;
+        const uint32_t first = kt != 0 ? 1u : 0u;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -139,9 +162,17 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int g, r0, nchunk;
       coord(item, g, r0, nchunk);
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-      const long rr = (long)r0 + r;
-      const bool valid = rr < p.rows_per_group;
-      const long prow = (long)g * p.rows_per_group + rr;
+      bool valid;
+      long prow;
+      if (p.spatial) {
+        const int x = (r0 & 0xFFFF) + (r % TW), y = (r0 >> 16) + (r / TW);
+        valid = x < p.W && y < p.H;
+        prow = ((long)g * p.H + y) * p.W + x;
+      } else {
+        const long rr = (long)r0 + r;
+        valid = rr < p.rows_per_group;
+        prow = (long)g * p.rows_per_group + rr;
+      }
       const uint32_t t_row = tmem_base + acc * TF_NC_MAX + ((uint32_t)(quarter * 32) << 16);
       const int nbase = nchunk * p.nc;
       mbar_wait_relaxed(tfull_bar(acc), aph);
@@ -181,11 +212,11 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 int make_map_f32(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int rank = 3) {
   EncodeTiledFn fn = get_encode_fn();
   KD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
@@ -378,7 +409,9 @@ int wgrad_tf32(const float* A, long lda, int N, const float* B, long ldb, int K,
 // 1x1, one source, identity addressing, no row scale / bias / ReLU / statistics: what the training step's GEMMs use
 bool gemm_tf32_eligible(const ConvOp& op) {
   const Epilogue& e = op.epi;
-  return op.kd == 1 && op.kh == 1 && op.kw == 1 && op.c1 == 0 && op.xpack_cin == 0 && e.mode == OUT_IDENTITY && e.row_scale == nullptr &&
+  const bool k1 = op.kh == 1 && op.kw == 1;
+  const bool k3 = op.kh == 3 && op.kw == 3 && op.groups == 1 && op.w_tap_ld % 4 == 0 && op.W < 65536 && op.H < 32768;
+  return op.kd == 1 && (k1 || k3) && op.c1 == 0 && op.xpack_cin == 0 && e.mode == OUT_IDENTITY && e.row_scale == nullptr &&
          e.row_mu == nullptr && e.col_bias == nullptr && !e.relu && e.stat_rstd == nullptr && e.planar_out == nullptr &&
          op.c0 % 4 == 0 && op.ld0 % 4 == 0 && op.w_ld % 4 == 0 && op.w_group_stride % 4 == 0 && e.N % 4 == 0 && e.out_ld % 4 == 0 &&
          e.out_coff % 4 == 0 && (e.res == nullptr || e.res_ld % 4 == 0) && !(reinterpret_cast<uintptr_t>(op.a0) & 15) &&
@@ -409,25 +442,41 @@ int gemm_tf32(const ConvOp& op, cudaStream_t s) {
   p.rows_per_group = rows / op.groups;
   p.tiles_per_group = (int)cdiv(p.rows_per_group, TF_BM);
   p.items = (long)p.tiles_per_group * op.groups * p.n_chunks;
+  p.spatial = op.kh == 3 ? 1 : 0;
+  p.taps = op.kh * op.kw; p.dil = op.dil; p.H = op.H; p.W = op.W;
+  if (p.spatial) {
+    p.tiles_x = (int)cdiv(op.W, 16); p.tiles_y = (int)cdiv(op.H, 8);
+    p.items = (long)op.nimg * p.tiles_x * p.tiles_y * p.n_chunks;
+    p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  }
   KD_CHECK(p.items < (1L << 24), "gemm_tf32: too many tiles (%ld)", p.items);
   p.inv_n_chunks = 1.0f / (float)p.n_chunks; p.inv_tiles_per_group = 1.0f / (float)p.tiles_per_group;
   p.res = reinterpret_cast<const float*>(e.res); p.res_ld = e.res_ld;
   p.out = reinterpret_cast<float*>(e.out); p.out_ld = e.out_ld; p.out_coff = (int)e.out_coff;
   CUtensorMap ma, mw;
-  {
+  if (p.spatial) {
+    const cuuint64_t dims[4] = {(cuuint64_t)op.c0, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.nimg};
+    const cuuint64_t str[3] = {(cuuint64_t)op.ld0 * 4, (cuuint64_t)op.ld0 * 4 * op.W, (cuuint64_t)op.ld0 * 4 * op.W * op.H};
+    const cuuint32_t box[4] = {TF_BK, 16, 8, 1};
+    KD_TRY(make_map_f32(&ma, op.a0, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, 4));
+    // weights [n][tap][c] seen as {c, n, tap}: channels past C are zero fill, so a K chunk never runs into the next tap
+    const cuuint64_t wdims[3] = {(cuuint64_t)op.c0, (cuuint64_t)e.N, (cuuint64_t)p.taps};
+    const cuuint64_t wstr[2] = {(cuuint64_t)op.w_ld * 4, (cuuint64_t)op.w_tap_ld * 4};
+    const cuuint32_t wbox[3] = {TF_BK, (cuuint32_t)p.nc, 1};
+    KD_TRY(make_map_f32(&mw, op.w, wdims, wstr, wbox));
+  } else {
     const cuuint64_t dims[3] = {(cuuint64_t)op.c0, (cuuint64_t)p.rows_per_group, (cuuint64_t)op.groups};
     const cuuint64_t str[2] = {(cuuint64_t)op.ld0 * 4, (cuuint64_t)op.ld0 * 4 * p.rows_per_group};
     const cuuint32_t box[3] = {TF_BK, TF_BM, 1};
     KD_TRY(make_map_f32(&ma, op.a0, dims, str, box));
-  }
-  {
-    const cuuint64_t dims[3] = {(cuuint64_t)op.c0, (cuuint64_t)e.N, (cuuint64_t)op.groups};
-    const cuuint64_t str[2] = {(cuuint64_t)op.w_ld * 4, (cuuint64_t)(op.groups > 1 ? op.w_group_stride : (long)op.w_ld * e.N) * 4};
-    const cuuint32_t box[3] = {TF_BK, (cuuint32_t)p.nc, 1};
-    KD_TRY(make_map_f32(&mw, op.w, dims, str, box));
+    const cuuint64_t wdims[3] = {(cuuint64_t)op.c0, (cuuint64_t)e.N, (cuuint64_t)op.groups};
+    const cuuint64_t wstr[2] = {(cuuint64_t)op.w_ld * 4, (cuuint64_t)(op.groups > 1 ? op.w_group_stride : (long)op.w_ld * e.N) * 4};
+    const cuuint32_t wbox[3] = {TF_BK, (cuuint32_t)p.nc, 1};
+    KD_TRY(make_map_f32(&mw, op.w, wdims, wstr, wbox));
   }
   const int grid = (int)std::min<long>(p.items, (long)sms);
-  ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * e.N * op.c0, 4.0 * ((double)rows * (op.c0 + e.N * (e.res ? 2 : 1)) + (double)op.groups * e.N * op.c0));
+  ProfScope prof(PC_GEMM_TC, s, 2.0 * rows * e.N * op.c0 * p.taps,
+                 4.0 * ((double)rows * (op.c0 + e.N * (e.res ? 2 : 1)) + (double)op.groups * e.N * op.c0 * p.taps));
   k_gemm_tf32<<<grid, TF_THREADS, TF_SMEM, s>>>(ma, mw, p);
   count_launch();
   KD_LAUNCH_CHECK();
