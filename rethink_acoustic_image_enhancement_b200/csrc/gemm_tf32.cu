@@ -358,6 +358,153 @@ k_wgrad_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// MDTA Gram reductions of the training step (KDLAE_model.py:134-137 and their backward) on the same MN-major path:
+// for every (image, head, pixel split)   G = q^T k,  Nq = q^T q,  Nk = k^T k   (only the diagonals of Nq, Nk are used)
+// with q at channel head * ch and k at channel C + head * ch of a [pixel][ld] fp32 tensor - the layout, grid and partial-sum
+// format of k_mdta_gram<float> (glue.cu) / gram_tc.cu, so the fixed-order reduction that follows is unchanged.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int GT_STAGES = 4;
+constexpr uint32_t GT_STAGE = 8 * WT_CHUNK;              // q: 4 chunks of 32 channels (M = 128 rows), k: 4 chunks
+
+__global__ void __launch_bounds__(128, 1)
+k_gram_tf32(const __grid_constant__ CUtensorMap map, int HW, int C, int heads, int splits, int per, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + GT_STAGES * GT_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GT_STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * GT_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * GT_STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = C / heads, kc = (ch + 15) / 16 * 16;
+  const int split = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int p_begin = split * per, p_end = min(HW, p_begin + per);
+  const int nsteps = p_end > p_begin ? (p_end - p_begin + WT_PIX - 1) / WT_PIX : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map);
+    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % GT_STAGES;
+      mbar_wait_relaxed(empty_bar(s), ((i / GT_STAGES) & 1) ^ 1);
+      const uint32_t dst = sbase + s * GT_STAGE;
+      const int px = p_begin + i * WT_PIX;
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), GT_STAGE);
+        for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * WT_CHUNK, &map, full_bar(s), head * ch + c * 32, px, img);
+        for (int c = 0; c < 4; ++c) tma_load_3d(dst + (4 + c) * WT_CHUNK, &map, full_bar(s), C + head * ch + c * 32, px, img);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kc >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % GT_STAGES;
+      mbar_wait(full_bar(s), (i / GT_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t qa = sbase + s * GT_STAGE, ka = qa + 4 * WT_CHUNK;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < WT_PIX / 8; ++k) {
+          const uint64_t dq = make_desc_mn32(qa + k * 1024, WT_CHUNK), dk = make_desc_mn32(ka + k * 1024, WT_CHUNK);
+          const uint32_t accum = (i | k) != 0 ? 1u : 0u;
+          umma_tf32(tmem_base + 0, dq, dk, idesc, accum);       // G  = q^T k
+          umma_tf32(tmem_base + 128, dq, dq, idesc, accum);     // Nq = q^T q
+          umma_tf32(tmem_base + 256, dk, dk, idesc, accum);     // Nk = k^T k
+        }
+        umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  }
+  __syncwarp();
+
+  float* dst = part + (((long)img * heads + head) * splits + split) * (long)(ch * ch + 2 * ch);
+  const int i = warp * 32 + lane;
+  if (nsteps > 0) {
+    mbar_wait_relaxed(done_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float nq = 0.f, nk = 0.f;
+    for (int c0 = 0; c0 < kc; c0 += 16) {
+      uint32_t g[16], a[16], b[16];
+      tmem_ld16_issue(t_row + c0, g); tmem_ld16_wait(g);
+      tmem_ld16_issue(t_row + 128 + c0, a); tmem_ld16_wait(a);
+      tmem_ld16_issue(t_row + 256 + c0, b); tmem_ld16_wait(b);
+      if (i < ch) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < ch) dst[(long)i * ch + c0 + j] = __uint_as_float(g[j]);
+          if (c0 + j == i) { nq = __uint_as_float(a[j]); nk = __uint_as_float(b[j]); }
+        }
+      }
+    }
+    if (i < ch) { dst[ch * ch + i] = nq; dst[ch * ch + ch + i] = nk; }
+  } else {
+    for (int e = threadIdx.x; e < ch * ch + 2 * ch; e += 128) dst[e] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace
+
+bool gram_tf32_eligible(const float* qk, long ld, int C, int heads) {
+  const int ch = heads > 0 ? C / heads : 0;
+  return heads > 0 && C % heads == 0 && ch % 4 == 0 && ch >= 8 && ch <= 96 && ld % 4 == 0 && !(reinterpret_cast<uintptr_t>(qk) & 15);
+}
+
+// same contract as mdta_gram<float> (glue.cu): part[((img * heads + head) * splits + split)][ch*ch + 2ch]
+int gram_tf32(const float* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s) {
+  KD_CHECK(gram_tf32_eligible(qk, ld, C, heads), "gram_tf32: shape not eligible");
+  static DeviceOnce once;
+  bool first; int dev;
+  KD_TRY(device_first_use(once, &first, &dev));
+  const uint32_t smem = GT_STAGES * GT_STAGE + 1024 + 128;
+  if (first) {
+    KD_CUDA(cudaFuncSetAttribute(k_gram_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    device_mark(once, dev);
+  }
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)HW, (cuuint64_t)nimg};
+  const cuuint64_t str[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * HW};
+  const cuuint32_t box[3] = {32, WT_PIX, 1};
+  KD_TRY(make_map_f32(&map, qk, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  int per = (HW + splits - 1) / splits;
+  per = (per + WT_PIX - 1) / WT_PIX * WT_PIX;           // split boundaries on 32-pixel steps; the tail is TMA zero fill
+  const int ch = C / heads;
+  ProfScope prof(PC_MDTA_GRAM, s, 2.0 * nimg * HW * C * ch + 4.0 * nimg * HW * C,
+                 (double)nimg * HW * 2 * C * 4.0 + 4.0 * nimg * heads * splits * (ch * ch + 2 * ch));
+  k_gram_tf32<<<dim3(splits, heads, nimg), 128, smem, s>>>(map, HW, C, heads, splits, per, part);
+  count_launch();
+  KD_LAUNCH_CHECK();
+  return 0;
+}
+
 bool wgrad_tf32_eligible(const float* A, long lda, int N, const float* B, long ldb, int K) {
   return N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && !(reinterpret_cast<uintptr_t>(A) & 15) &&
          !(reinterpret_cast<uintptr_t>(B) & 15);

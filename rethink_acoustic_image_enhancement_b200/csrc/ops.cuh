@@ -124,6 +124,8 @@ int gemm_tf32(const ConvOp& op, cudaStream_t s);
 bool wgrad_tf32_eligible(const float* A, long lda, int N, const float* B, long ldb, int K);
 int wgrad_tf32(const float* A, long lda, int N, const float* B, long ldb, int K, long P, float* part, int splits, int* splits_out,
                cudaStream_t s);
+bool gram_tf32_eligible(const float* qk, long ld, int C, int heads);
+int gram_tf32(const float* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s);
 void set_train_matmul_tf32(int on);
 int train_matmul_tf32();
 // dense 1x1 / 3x3 conv (dilation, zero padding, no bias) with backward, fp32 NHWC, weights [Cout][k*k][Cin]

@@ -26,6 +26,10 @@ int train_matmul_tf32() {
 
 namespace {
 // every fp32 GEMM of the training step goes through here: tcgen05 kind::tf32 when switched on and the shape allows, else CUDA cores
+int train_gram(const float* qk, long ld, int nimg, int HW, int C, int heads, int splits, float* part, cudaStream_t s) {
+  if (train_matmul_tf32() && gram_tf32_eligible(qk, ld, C, heads)) return gram_tf32(qk, ld, nimg, HW, C, heads, splits, part, s);
+  return mdta_gram<float>(qk, ld, nimg, HW, C, heads, splits, part, s);
+}
 int train_gemm(const ConvOp& g, cudaStream_t s) {
   if (train_matmul_tf32() && gemm_tf32_eligible(g)) return gemm_tf32(g, s);
   return conv_gemm_simt<float>(g, s);
@@ -572,7 +576,7 @@ int mdta_forward_train(const float* x, const float* gamma, const float* w_qkv, c
   KD_LAUNCH_CHECK();
   KD_TRY(conv1x1_f32(L.y, C, w_qkv, 3 * C, nullptr, L.t, nimg, H, W, s));
   KD_TRY(dwconv3x3<float>(L.t, 3 * C, L.u, 3 * C, w_dw, nullptr, nimg, H, W, 3 * C, 0, s));
-  KD_TRY(mdta_gram<float>(L.u, 3 * C, nimg, HW, C, heads, splits, L.part, s));
+  KD_TRY(train_gram(L.u, 3 * C, nimg, HW, C, heads, splits, L.part, s));
   k_sum_groups<<<cdiv((long)nimg * heads * psz, 256), 256, 0, s>>>(L.part, splits, psz, (long)nimg * heads * psz, L.gs);
   count_launch();
   KD_LAUNCH_CHECK();
@@ -607,7 +611,7 @@ int mdta_backward(const float* x, const float* gamma, const float* w_qkv, const 
   count_launch();
   KD_LAUNCH_CHECK();
   // dA = do v^T (pixel reduction), dv = A^T do
-  KD_TRY(mdta_gram<float>(L.dov, 2 * C, nimg, HW, C, heads, gsplits, L.part, s));
+  KD_TRY(train_gram(L.dov, 2 * C, nimg, HW, C, heads, gsplits, L.part, s));
   k_sum_groups<<<cdiv((long)nimg * heads * psz, 256), 256, 0, s>>>(L.part, gsplits, psz, (long)nimg * heads * psz, L.dAs);
   count_launch();
   KD_LAUNCH_CHECK();
