@@ -323,7 +323,7 @@ def time_training_step(pk, synth, dev, world, rank, timed, batch=2, crop=256):
             "ms_per_step": ms, "dtype": "f32", "grad_bytes": 26874300 * 4, "allreduce": "25 MB buckets, overlapped with backward" if world > 1 else None,
             "loss_first": ls[0], "loss_last": ls[-1],
             "tf32_matmul": {"value": batch * world / ms_tf32 * 1e3, "unit": "images/s", "ms_per_step": ms_tf32,
-                            "what": "same step with the 1x1-conv GEMMs (forward, dgrad, wgrad) on tcgen05 kind::tf32 (gemm_tf32.cu)"}}
+                            "what": "same step with the dense-conv GEMMs (1x1 forward, dgrad, wgrad; 3x3 forward, dgrad) and the Gram reductions on tcgen05 kind::tf32 (gemm_tf32.cu)"}}
 
 
 def run_reference(args, rank):
