@@ -214,7 +214,8 @@ class _ConvFn(torch.autograd.Function):
             _lib.check(lib.kdlae_conv_train_backward(xh.data_ptr(), w.data_ptr(), dout.data_ptr(), None if dx is None else dx.data_ptr(),
                                                      dw.data_ptr(), B, H, W, Cin, Cout, k, dil, ws.data_ptr(), _stream()),
                        "kdlae_conv_train_backward")
-        return dx, dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), None
+        # contiguous in the parameter's own layout (DDP's bucket views and the flat gradient buffer expect that)
+        return dx, dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous(), None
 
 
 def conv_train(x: torch.Tensor, weight: torch.Tensor, dilation: int = 1) -> torch.Tensor:
