@@ -134,9 +134,12 @@ def test_transformer_block_backward_matches_oracle_autograd(shape, heads):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [(2, 5, 12, 20, 17, 3, 1), (1, 2, 16, 16, 32, 3, 2), (2, 64, 8, 24, 16, 1, 1), (1, 48, 9, 7, 96, 3, 1)])
+@pytest.mark.parametrize("case", [(2, 5, 12, 20, 17, 3, 1), (1, 2, 16, 16, 32, 3, 2), (2, 64, 8, 24, 16, 1, 1), (1, 48, 9, 7, 96, 3, 1),
+                                  (2, 1, 20, 24, 48, 3, 1), (1, 2, 18, 20, 96, 3, 2), (2, 96, 12, 20, 1, 3, 1), (1, 48, 17, 9, 1, 3, 1),
+                                  (1, 1, 10, 9, 96, 3, 1), (1, 3, 16, 16, 24, 3, 1)])
 def test_conv_train_matches_torch_autograd(case):
-    """Dense conv forward / dgrad / wgrad of the layers outside the blocks (any channel counts, dilation 2 of output_param)."""
+    """Dense conv forward / dgrad / wgrad of the layers outside the blocks (any channel counts, dilation 2 of output_param),
+    including the thin ends of the model (1 or 2 input channels, 1 output channel)."""
     import torch.nn.functional as F
     from rethink_acoustic_image_enhancement_b200.training import conv_train
     B, Cin, H, W, Cout, k, dil = case
