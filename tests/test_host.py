@@ -151,3 +151,14 @@ def test_checkpoint_round_trip_and_restormer_pretrained_partial_load(tmp_path):
         assert set(ref) <= set(ours), sorted(set(ref) - set(ours))[:5]
         assert all(tuple(ref[k].shape) == tuple(ours[k].shape) for k in ref)
         assert set(ref) == set(restormer)
+
+
+def test_nhwc_pixel_shuffle_helpers_match_torch():
+    """The NHWC PixelShuffle / PixelUnshuffle data movement of the training forward (training.py) against torch's NCHW ops."""
+    import torch.nn.functional as F
+    from rethink_acoustic_image_enhancement_b200.training import _shuffle2, _unshuffle2
+    x = torch.arange(2 * 6 * 8 * 12, dtype=torch.float32).reshape(2, 12, 6, 8)             # NCHW
+    nhwc = x.permute(0, 2, 3, 1)
+    assert torch.equal(_unshuffle2(nhwc).permute(0, 3, 1, 2), F.pixel_unshuffle(x, 2))
+    assert torch.equal(_shuffle2(nhwc).permute(0, 3, 1, 2), F.pixel_shuffle(x, 2))
+    assert torch.equal(_shuffle2(_unshuffle2(nhwc)), nhwc)
