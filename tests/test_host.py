@@ -162,3 +162,24 @@ def test_nhwc_pixel_shuffle_helpers_match_torch():
     assert torch.equal(_unshuffle2(nhwc).permute(0, 3, 1, 2), F.pixel_unshuffle(x, 2))
     assert torch.equal(_shuffle2(nhwc).permute(0, 3, 1, 2), F.pixel_shuffle(x, 2))
     assert torch.equal(_shuffle2(_unshuffle2(nhwc)), nhwc)
+
+
+def test_pad_test_geometry_with_a_stub_model():
+    """metrics.pad_test (image_restoration_model.py:226-237): reflect padding to the window, crop of hq and of the 2x sr output."""
+    import torch.nn.functional as F
+    from rethink_acoustic_image_enhancement_b200.metrics import pad_test
+    seen = {}
+
+    def stub(inp):
+        seen["img"], seen["rate"] = inp["img"], inp["denoise_rate"]
+        return {"hq": inp["img"] * 2, "sr": F.interpolate(inp["img"], scale_factor=2, mode="nearest")}
+
+    img = torch.rand(2, 1, 21, 30)
+    rate = torch.full((2, 1, 21, 30), 0.25)
+    out = pad_test(stub, {"img": img, "denoise_rate": rate}, 8)
+    assert seen["img"].shape == (2, 1, 24, 32) and seen["rate"].shape == (2, 1, 24, 32)
+    assert torch.equal(seen["img"], F.pad(img, (0, 2, 0, 3), "reflect"))
+    assert out["hq"].shape == (2, 1, 21, 30) and torch.equal(out["hq"], img * 2)
+    assert out["sr"].shape == (2, 1, 42, 60)
+    out = pad_test(stub, {"img": img[:, :, :16, :24], "denoise_rate": torch.full((2, 1, 1, 1), 0.5)}, 8)     # nothing to pad
+    assert seen["img"].shape == (2, 1, 16, 24) and seen["rate"].shape == (2, 1, 1, 1) and out["hq"].shape == (2, 1, 16, 24)
