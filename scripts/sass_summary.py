@@ -8,7 +8,8 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "rethink_acoustic_image_enhancement_b200", "libkdlae_b200.so")
-HOT = ["k_pwdw_f2ILi1ELi0", "k_pwdw_tILi1", "k_pwdw_tILi0", "k_conv_gemm_tcILi1ELi20", "k_conv3_tcILi1", "k_mdta_gram_tcILi1"]
+HOT = ["k_pwdw_f2ILi1ELi0", "k_pwdw_tILi1", "k_pwdw_tILi0", "k_conv_gemm_tcILi1ELi20", "k_conv3_tcILi1", "k_mdta_gram_tcILi1",
+       "k_gemm_tf32", "k_wgrad_tf32", "k_gram_tf32"]
 OPS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "FFMA2", "FMUL2", "FFMA", "MUFU", "SYNCS", "LDS", "STS", "LDG", "STG", "F2FP", "BAR"]
 
 sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
